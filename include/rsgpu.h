@@ -1,0 +1,203 @@
+/* rsgpu.h — C ABI of the B200 (sm_100a) implementation of Rescan's pose_proposal hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no CUDA / torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the mhalber/Rescan tree).
+ * Host-buffer calls take and return exactly the layouts the reference's callers already hold
+ * (AoS xyz floats, column-major 4x4 msh_mat4_t, row-major [n_query][k] result rows); the `_dev`
+ * variants take device pointers of the same layouts for callers that keep data resident in HBM.
+ *
+ * Conventions
+ *   - every function returns RSGPU_OK (0) or a negative rsgpu_status; rsgpu_last_error() gives the text.
+ *     The reference itself reports nothing (assert-only) — callers that ignore the status
+ *     get reference behaviour on success and untouched outputs on failure.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with RSGPU_ERR_NO_DEVICE.
+ *   - handles are opaque and own device memory; destroy them with the matching *_destroy.
+ *   - all work is enqueued on one stream per process (legacy default stream unless rsgpu_set_stream
+ *     was called); host-buffer calls synchronise that stream before returning.
+ */
+#ifndef RSGPU_H
+#define RSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rsgpu_status
+{
+  RSGPU_OK = 0,
+  RSGPU_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
+  RSGPU_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
+  RSGPU_ERR_INVALID = -3,     /* bad argument */
+  RSGPU_ERR_UNSUPPORTED = -4, /* outside the supported envelope (e.g. k > RSGPU_MAX_K) */
+  RSGPU_ERR_OOM = -5
+} rsgpu_status;
+
+#define RSGPU_MAX_K 512           /* largest k / max_n_neigh of the search API */
+#define RSGPU_MAX_CELLS_PER_QUERY 512 /* msh_hash_grid.h:1101 MAX_BIN_COUNT: cells examined per query */
+
+typedef struct rsgpu_grid rsgpu_grid_t;   /* device hash grid      <-> msh_hash_grid_t   (msh_hash_grid.h:262-283) */
+typedef struct rsgpu_cloud rsgpu_cloud_t; /* device point set      <-> one level of rs_pointcloud_t (rs_pointcloud.h:77-97) */
+
+/* ------------------------------------------------------------------------------------------------ runtime */
+int rsgpu_device_count( void );
+int rsgpu_set_device( int device );       /* cudaSetDevice for this process; default 0 */
+int rsgpu_set_stream( void* cuda_stream );/* cudaStream_t to enqueue on; NULL = legacy default stream */
+int rsgpu_synchronize( void );
+const char* rsgpu_last_error( void );
+const char* rsgpu_version( void );
+
+/* Per-kernel device timing with CUDA events on the launch stream (used by bench.py for the roofline line).
+   names: "grid_build", "search", "score_dense" (pose-grid launches), "score" (explicit pose lists), "icp",
+   "labels", "unary", "edges".  ms = summed event time. */
+int rsgpu_profile_enable( int on );
+int rsgpu_profile_reset( void );
+int rsgpu_profile_get( const char* name, double* ms, int64_t* launches );
+/* number of this library's own kernels launched so far by this process (CUB / memcpy / memset not counted) */
+int64_t rsgpu_launch_count( void );
+
+/* ------------------------------------------------------------------------------------------------ hash grid */
+/* replaces msh_hash_grid_init_3d (msh_hash_grid.h:222, impl :388-541, 550-555).  `pts` = n_pts x {x,y,z}
+   floats; radius > 0 gives cell = 2*radius, radius <= 0 the reference's automatic cell size. */
+int rsgpu_grid_create( const float* pts, int32_t n_pts, float radius, rsgpu_grid_t** out );
+int rsgpu_grid_create_dev( const float* d_pts, int32_t n_pts, float radius, rsgpu_grid_t** out );
+/* replaces msh_hash_grid_term (msh_hash_grid.h:225) */
+void rsgpu_grid_destroy( rsgpu_grid_t* grid );
+
+/* Per-point unit normals in ORIGINAL point order (the scan level's normals the reference indexes with the
+   returned point index: pose_proposal.cpp:137, icp.h:372); stored re-laid in cell order next to the points. */
+int rsgpu_grid_set_normals( rsgpu_grid_t* grid, const float* normals );
+int rsgpu_grid_set_normals_dev( rsgpu_grid_t* grid, const float* d_normals );
+
+typedef struct rsgpu_grid_info
+{
+  int64_t width, height, depth;   /* msh_hash_grid_t::width/height/depth */
+  double cell_size, inv_cell_size;
+  float min_pt[3], max_pt[3];
+  int64_t n_pts;
+  int64_t n_bins;                 /* non-empty cells */
+  int64_t max_n_pts_in_bin;
+} rsgpu_grid_info_t;
+int rsgpu_grid_get_info( const rsgpu_grid_t* grid, rsgpu_grid_info_t* info );
+/* the re-laid point records = msh_hash_grid_t::data_buffer (msh_hash_grid.h:238-242, order :501-532) */
+int rsgpu_grid_get_data( const rsgpu_grid_t* grid, float* xyz, int32_t* idx );
+
+/* field-for-field msh_hash_grid_search_desc_t (msh_hash_grid.h:196-216) */
+typedef struct rsgpu_search_desc
+{
+  float* query_pts;       /* n_query_pts x {x,y,z} */
+  size_t n_query_pts;
+  float* distances_sq;    /* [n_query_pts][k] */
+  int32_t* indices;       /* [n_query_pts][k] */
+  size_t* n_neighbors;    /* [n_query_pts], may be NULL */
+  float radius;
+  union { size_t k; size_t max_n_neigh; };
+  int sort;               /* rows are always written ascending, which satisfies both sort = 0 and 1 */
+} rsgpu_search_desc_t;
+
+/* replace msh_hash_grid_radius_search / _knn_search (msh_hash_grid.h:227-230; impl :1090-1259, :1294-1450).
+   *total = the reference's return value (sum of per-query counts). */
+int rsgpu_grid_radius_search( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, size_t* total );
+int rsgpu_grid_knn_search( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, size_t* total );
+/* same with every buffer of `desc` in device memory (n_neighbors then is uint64 on the device) */
+int rsgpu_grid_radius_search_dev( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, size_t* total );
+int rsgpu_grid_knn_search_dev( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, size_t* total );
+
+/* ------------------------------------------------------------------------------------------------ clouds */
+/* positions + normals of one sampling level of an object model (rs_pointcloud_t::positions[lvl] / normals[lvl]) */
+int rsgpu_cloud_create( const float* pos, const float* nor, int32_t n_pts, rsgpu_cloud_t** out );
+void rsgpu_cloud_destroy( rsgpu_cloud_t* cloud );
+int32_t rsgpu_cloud_size( const rsgpu_cloud_t* cloud );
+
+/* ------------------------------------------------------------------------------------------------ pose scoring */
+/* replaces mgs_compute_object_alignment_score (pose_proposal.h:46-49, impl pose_proposal.cpp:93-158) for a
+   batch of poses.  `scene` is the scan's level-`search_lvl` grid WITH normals set; radius = sigma =
+   search_radii[search_lvl] (0.10 for level 1, pose_proposal.cpp:98); max_n_neigh = storage->max_n_neigh.
+   xforms: n_poses x 16 floats, column-major msh_mat4_t.  scores: n_poses floats. */
+int rsgpu_score_poses( const rsgpu_cloud_t* object, const rsgpu_grid_t* scene, const float* xforms,
+                       int64_t n_poses, int32_t max_n_neigh, float radius, float* scores );
+int rsgpu_score_poses_dev( const rsgpu_cloud_t* object, const rsgpu_grid_t* scene, const float* d_xforms,
+                           int64_t n_poses, int32_t max_n_neigh, float radius, float* d_scores );
+
+/* Dense pose grid = rotations x translations, pose (t, r) = rotation r with its translation column replaced
+   by translation t (pose_proposal.cpp:221-222).  rotations: n_rot x 16 floats (column-major);
+   translations: n_trans x 3 floats; scores: [n_trans][n_rot]. */
+int rsgpu_score_pose_grid( const rsgpu_cloud_t* object, const rsgpu_grid_t* scene, const float* rotations,
+                           int32_t n_rot, const float* translations, int64_t n_trans, int32_t max_n_neigh,
+                           float radius, float* scores );
+int rsgpu_score_pose_grid_dev( const rsgpu_cloud_t* object, const rsgpu_grid_t* scene, const float* d_rotations,
+                               int32_t n_rot, const float* d_translations, int64_t n_trans,
+                               int32_t max_n_neigh, float radius, float* d_scores );
+
+/* Algorithmic-byte accounting of one scoring call: per query 8*B (non-empty cells overlapping
+   the +-radius box) + 16*C (points stored in them) + 12*T (scene normals the reference fetches), per pose
+   +68.  Counting pass only (slow, exact); results in counts[4] = {queries, B, C, T}. */
+int rsgpu_score_pose_grid_count( const rsgpu_cloud_t* object, const rsgpu_grid_t* scene, const float* rotations,
+                                 int32_t n_rot, const float* translations, int64_t n_trans,
+                                 int32_t max_n_neigh, float radius, int64_t counts[4] );
+
+/* pose_proposal_t (pose_proposal.h:6-10): 16 floats column-major xform + score = 17 floats */
+#define RSGPU_POSE_FLOATS 17
+
+typedef struct rsgpu_propose_opts
+{
+  int32_t max_n_neigh;      /* 64  (pose_proposal.cpp:179) */
+  float radius;             /* 0.10 = search_radii[search_lvl = 1] (pose_proposal.cpp:98, 178) */
+  float thresholds[3];      /* 0.25, 0.35, 0.40 for object levels 4, 3, 2 (pose_proposal.cpp:160-168) */
+  int32_t top_k;            /* <= 0: keep every survivor in translation order (reference behaviour);
+                               > 0: keep the top_k best per object, descending score, ties by pose id */
+} rsgpu_propose_opts_t;
+void rsgpu_propose_default_opts( rsgpu_propose_opts_t* opts );
+
+/* replaces mgs_propose_poses for ONE object (pose_proposal.cpp:325-369 = levels 4 -> 3 -> 2:
+   mgs__initial_pose_proposals :170-254 then mgs__pose_verification :256-303 twice).
+   object_lvl4/3/2: the object's level-4/3/2 point sets.  On return *n_out proposals are written to
+   `out` (capacity out_cap x 17 floats) and their dense pose ids t*n_rot + r to `out_pose_id` (nullable).
+   Survivors include verification failures with score -1, as in the reference (:348-359). */
+int rsgpu_propose_poses( const rsgpu_cloud_t* object_lvl4, const rsgpu_cloud_t* object_lvl3,
+                         const rsgpu_cloud_t* object_lvl2, const rsgpu_grid_t* scene, const float* rotations,
+                         int32_t n_rot, const float* translations, int64_t n_trans,
+                         const rsgpu_propose_opts_t* opts, float* out, int64_t* out_pose_id, int64_t out_cap,
+                         int64_t* n_out );
+
+/* ------------------------------------------------------------------------------------------------ ICP */
+/* replaces icp_align (icp.h:84-88, impl :416-500) for a batch of starting poses of one object against one
+   scan level.  `object` = pts1/nor1, `scan` = grid over pts2 WITH normals (any cell size: the search is
+   exact, so results do not depend on it).  T1: n_batch x 16 floats column-major, updated in place;
+   T2: 16 floats (the reference's callers pass identity).  errs: the return values; iters (nullable):
+   estimation steps taken. */
+int rsgpu_icp_align_batch( const rsgpu_cloud_t* object, const rsgpu_grid_t* scan, float* T1, int32_t n_batch,
+                           const float* T2, float max_dist, float max_angle, float* errs, int32_t* iters );
+/* same with the iteration cap exposed (the reference hard-codes max_iter = 100, icp.h:443); <= 0 means 100 */
+int rsgpu_icp_align_batch_ex( const rsgpu_cloud_t* object, const rsgpu_grid_t* scan, float* T1, int32_t n_batch,
+                              const float* T2, float max_dist, float max_angle, int32_t max_iter, float* errs,
+                              int32_t* iters );
+
+/* ------------------------------------------------------------------------------------------------ labels / unary terms */
+/* replaces rspf__assign_temporary_labels (rs_pointcloud_filters.cpp:738-778) over placements
+   [first, last): scan level-1 positions/normals (n_vertices), one pose + object level-1 grid (with normals)
+   per placement.  labels (int8, value = placement index + 1) and min_dists (float, squared) are read and
+   updated in place, exactly like the reference's running arg-min. */
+int rsgpu_assign_labels( const float* scan_pos, const float* scan_nor, int32_t n_vertices, const float* poses,
+                         const rsgpu_grid_t* const* object_grids, int32_t first, int32_t last, float radius,
+                         int8_t* labels, float* min_dists );
+
+/* replaces the data_cost block of rspf_smooth_labels (rs_pointcloud_filters.cpp:926-939):
+   cost[v*n_labels + l] = (l == labels[v]) ? 0 : c, c = 30, 15 when label_is_static[labels[v]], 1 when label 0. */
+int rsgpu_unary_costs( const int32_t* labels, const uint8_t* label_is_static, int32_t n_vertices,
+                       int32_t n_labels, int32_t* data_cost );
+
+/* candidate edges of rspf_compute_neighborhood (rs_pointcloud_filters.cpp:674-722) before its hashtable
+   de-duplication: per vertex its <= max_nn nearest neighbours within sqrt(radius_sq) (self included) and
+   weight (1-(d2/(4 r^2))^dist_exp) * clamp(n.m,0,1)^angle_exp.  neighbors/weights: [n][max_nn], -1 / 0 where absent.
+   `grid` = the cloud's own grid with normals set. */
+int rsgpu_neighborhood( const rsgpu_grid_t* grid, const float* pos, const float* nor, int32_t n_vertices,
+                        int32_t max_nn, float radius_sq, float dist_exp, float angle_exp, int32_t* neighbors,
+                        float* weights );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSGPU_H */

@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's hot-path interface, over the C ABI of ``include/rsgpu.h``.
+
+Everything here is a thin ctypes view of ``rescan_b200/librsgpu.so`` (hand-written sm_100a CUDA, built by
+``rescan_b200/csrc/Makefile``).  Names and argument meaning follow the reference entry points they replace:
+
+  ================================  ==========================================================
+  here                              reference
+  ================================  ==========================================================
+  ``HashGrid(pts, radius)``         ``msh_hash_grid_init_3d``        (lib/msh/msh_hash_grid.h:222)
+  ``HashGrid.radius_search``        ``msh_hash_grid_radius_search``  (msh_hash_grid.h:227)
+  ``HashGrid.knn_search``           ``msh_hash_grid_knn_search``     (msh_hash_grid.h:229)
+  ``compute_object_alignment_scores`` ``mgs_compute_object_alignment_score`` (apps/pose_proposal/pose_proposal.h:46)
+  ``propose_poses``                 ``mgs_propose_poses``            (pose_proposal.h:51)
+  ``icp_align``                     ``icp_align``                    (lib/rs/icp.h:84)
+  ``assign_labels`` / ``unary_costs`` / ``neighborhood``
+                                    ``rspf__assign_temporary_labels`` / data_cost block / ``rspf_compute_neighborhood``
+                                    (lib/rs/rs_pointcloud_filters.cpp:738, 926, 674)
+  ================================  ==========================================================
+
+There is no CPU fallback: if the library is missing or no CUDA device is present every call raises.
+Nothing in this module imports or calls ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librsgpu.so")
+
+RSGPU_MAX_K = 512
+POSE_FLOATS = 17
+
+
+class RsgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rsgpu error {code}: {msg}")
+        self.code = code
+
+
+class GridInfo(C.Structure):
+    _fields_ = [("width", C.c_int64), ("height", C.c_int64), ("depth", C.c_int64),
+                ("cell_size", C.c_double), ("inv_cell_size", C.c_double),
+                ("min_pt", C.c_float * 3), ("max_pt", C.c_float * 3),
+                ("n_pts", C.c_int64), ("n_bins", C.c_int64), ("max_n_pts_in_bin", C.c_int64)]
+
+
+class SearchDesc(C.Structure):
+    _fields_ = [("query_pts", C.c_void_p), ("n_query_pts", C.c_size_t), ("distances_sq", C.c_void_p),
+                ("indices", C.c_void_p), ("n_neighbors", C.c_void_p), ("radius", C.c_float),
+                ("k", C.c_size_t), ("sort", C.c_int)]
+
+
+class ProposeOpts(C.Structure):
+    _fields_ = [("max_n_neigh", C.c_int32), ("radius", C.c_float), ("thresholds", C.c_float * 3), ("top_k", C.c_int32)]
+
+
+_lib = None
+
+# every symbol include/rsgpu.h declares: (restype, argtypes)
+_vp, _i32, _i64, _f32, _sz, _int = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_int
+SIGNATURES = {
+    "rsgpu_device_count": (_int, []),
+    "rsgpu_set_device": (_int, [_int]),
+    "rsgpu_set_stream": (_int, [_vp]),
+    "rsgpu_synchronize": (_int, []),
+    "rsgpu_last_error": (C.c_char_p, []),
+    "rsgpu_version": (C.c_char_p, []),
+    "rsgpu_profile_enable": (_int, [_int]),
+    "rsgpu_profile_reset": (_int, []),
+    "rsgpu_profile_get": (_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "rsgpu_launch_count": (_i64, []),
+    "rsgpu_grid_create": (_int, [_vp, _i32, _f32, C.POINTER(_vp)]),
+    "rsgpu_grid_create_dev": (_int, [_vp, _i32, _f32, C.POINTER(_vp)]),
+    "rsgpu_grid_destroy": (None, [_vp]),
+    "rsgpu_grid_set_normals": (_int, [_vp, _vp]),
+    "rsgpu_grid_set_normals_dev": (_int, [_vp, _vp]),
+    "rsgpu_grid_get_info": (_int, [_vp, C.POINTER(GridInfo)]),
+    "rsgpu_grid_get_data": (_int, [_vp, _vp, _vp]),
+    "rsgpu_grid_radius_search": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
+    "rsgpu_grid_knn_search": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
+    "rsgpu_grid_radius_search_dev": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
+    "rsgpu_grid_knn_search_dev": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
+    "rsgpu_cloud_create": (_int, [_vp, _vp, _i32, C.POINTER(_vp)]),
+    "rsgpu_cloud_destroy": (None, [_vp]),
+    "rsgpu_cloud_size": (_i32, [_vp]),
+    "rsgpu_score_poses": (_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "rsgpu_score_poses_dev": (_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "rsgpu_score_pose_grid": (_int, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _vp]),
+    "rsgpu_score_pose_grid_dev": (_int, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, _vp]),
+    "rsgpu_score_pose_grid_count": (_int, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, _f32, C.POINTER(_i64)]),
+    "rsgpu_propose_default_opts": (None, [C.POINTER(ProposeOpts)]),
+    "rsgpu_propose_poses": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(ProposeOpts), _vp, _vp, _i64,
+                                   C.POINTER(_i64)]),
+    "rsgpu_icp_align_batch": (_int, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _vp, _vp]),
+    "rsgpu_icp_align_batch_ex": (_int, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _vp, _vp]),
+    "rsgpu_assign_labels": (_int, [_vp, _vp, _i32, _vp, C.POINTER(_vp), _i32, _i32, _f32, _vp, _vp]),
+    "rsgpu_unary_costs": (_int, [_vp, _vp, _i32, _i32, _vp]),
+    "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
+}
+
+
+def lib():
+    """Load librsgpu.so (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RsgpuError(-1, f"{LIB_PATH} is missing - build it with `make -f rescan_b200/csrc/Makefile` "
+                             f"(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(code):
+    if code != 0:
+        raise RsgpuError(code, lib().rsgpu_last_error().decode("utf-8", "replace"))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    return lib().rsgpu_device_count()
+
+
+def set_device(i):
+    _check(lib().rsgpu_set_device(int(i)))
+
+
+def synchronize():
+    _check(lib().rsgpu_synchronize())
+
+
+def launch_count():
+    return int(lib().rsgpu_launch_count())
+
+
+def profile_enable(on=True):
+    lib().rsgpu_profile_enable(int(bool(on)))
+
+
+def profile_reset():
+    lib().rsgpu_profile_reset()
+
+
+def profile_get(name):
+    ms, n = C.c_double(0), C.c_int64(0)
+    lib().rsgpu_profile_get(name.encode(), C.byref(ms), C.byref(n))
+    return float(ms.value), int(n.value)
+
+
+class PointCloud:
+    """One sampling level of an object model resident in HBM (positions + normals)."""
+
+    def __init__(self, pos, nor):
+        self.pos, self.nor = _f32(pos).reshape(-1, 3), _f32(nor).reshape(-1, 3)
+        assert self.pos.shape == self.nor.shape
+        h = C.c_void_p()
+        _check(lib().rsgpu_cloud_create(_ptr(self.pos), _ptr(self.nor), len(self.pos), C.byref(h)))
+        self.h = h
+
+    def __len__(self):
+        return len(self.pos)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rsgpu_cloud_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class HashGrid:
+    """msh_hash_grid_t on the GPU.  ``normals`` (original point order) are needed by scoring / ICP / labels."""
+
+    def __init__(self, pts=None, radius=0.05, normals=None, device_ptr=None, n_pts=None):
+        h = C.c_void_p()
+        if device_ptr is not None:
+            _check(lib().rsgpu_grid_create_dev(C.c_void_p(device_ptr), int(n_pts), radius, C.byref(h)))
+            self.pts = None
+        else:
+            self.pts = _f32(pts).reshape(-1, 3)
+            _check(lib().rsgpu_grid_create(_ptr(self.pts), len(self.pts), radius, C.byref(h)))
+        self.h = h
+        if normals is not None:
+            self.set_normals(normals)
+
+    def set_normals(self, normals):
+        n = _f32(normals).reshape(-1, 3)
+        assert len(n) == self.info()["n_pts"]
+        _check(lib().rsgpu_grid_set_normals(self.h, _ptr(n)))
+
+    def info(self):
+        gi = GridInfo()
+        _check(lib().rsgpu_grid_get_info(self.h, C.byref(gi)))
+        return dict(dims=np.array([gi.width, gi.height, gi.depth], np.int64), cell_size=gi.cell_size,
+                    inv_cell_size=gi.inv_cell_size, min_pt=np.array(gi.min_pt[:], np.float32),
+                    max_pt=np.array(gi.max_pt[:], np.float32), n_pts=int(gi.n_pts), n_bins=int(gi.n_bins),
+                    max_n_pts_in_bin=int(gi.max_n_pts_in_bin))
+
+    def data(self):
+        n = self.info()["n_pts"]
+        xyz = np.zeros((n, 3), np.float32)
+        idx = np.zeros(n, np.int32)
+        _check(lib().rsgpu_grid_get_data(self.h, _ptr(xyz), _ptr(idx)))
+        return xyz, idx
+
+    def _search(self, fn, q, radius, k, sort):
+        q = _f32(q).reshape(-1, 3)
+        nq = len(q)
+        d2 = np.full((nq, k), np.nan, np.float32)
+        idx = np.full((nq, k), -1, np.int32)
+        nn = np.zeros(nq, np.uint64)
+        sd = SearchDesc(q.ctypes.data, nq, d2.ctypes.data, idx.ctypes.data, nn.ctypes.data, radius, k, sort)
+        tot = C.c_size_t(0)
+        _check(fn(self.h, C.byref(sd), C.byref(tot)))
+        return idx, d2, nn.astype(np.int64), int(tot.value)
+
+    def radius_search(self, q, radius, k, sort=1):
+        """-> indices [nq,k], distances_sq [nq,k], n_neighbors [nq], total (entries past a row's count are unspecified)"""
+        return self._search(lib().rsgpu_grid_radius_search, q, radius, k, sort)
+
+    def knn_search(self, q, k, sort=1):
+        return self._search(lib().rsgpu_grid_knn_search, q, 0.0, k, sort)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rsgpu_grid_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def compute_object_alignment_scores(obj: PointCloud, scene: HashGrid, xforms, max_n_neigh=64, radius=0.10):
+    """mgs_compute_object_alignment_score for a batch of column-major 4x4 poses -> float32 [P]"""
+    x = _f32(xforms).reshape(-1, 16)
+    out = np.zeros(len(x), np.float32)
+    _check(lib().rsgpu_score_poses(obj.h, scene.h, _ptr(x), len(x), max_n_neigh, radius, _ptr(out)))
+    return out
+
+
+def score_pose_grid(obj: PointCloud, scene: HashGrid, rotations, translations, max_n_neigh=64, radius=0.10):
+    """scores [T, R] of the dense pose grid rotations x translations (pose_proposal.cpp:213-236)"""
+    r, t = _f32(rotations).reshape(-1, 16), _f32(translations).reshape(-1, 3)
+    out = np.zeros((len(t), len(r)), np.float32)
+    _check(lib().rsgpu_score_pose_grid(obj.h, scene.h, _ptr(r), len(r), _ptr(t), len(t), max_n_neigh, radius, _ptr(out)))
+    return out
+
+
+def score_pose_grid_count(obj: PointCloud, scene: HashGrid, rotations, translations, max_n_neigh=64, radius=0.10):
+    """exact algorithmic-byte census of one dense scoring call -> dict(queries, B, C, T, bytes)"""
+    r, t = _f32(rotations).reshape(-1, 16), _f32(translations).reshape(-1, 3)
+    c = (C.c_int64 * 4)()
+    _check(lib().rsgpu_score_pose_grid_count(obj.h, scene.h, _ptr(r), len(r), _ptr(t), len(t), max_n_neigh, radius, c))
+    q, b, cc, tt = (int(v) for v in c)
+    n_poses = len(r) * len(t)
+    return dict(queries=q, B=b, C=cc, T=tt, poses=n_poses, bytes=8 * b + 16 * cc + 12 * tt + 68 * n_poses + 24 * len(obj))
+
+
+def propose_poses(obj_lvl4: PointCloud, obj_lvl3: PointCloud, obj_lvl2: PointCloud, scene: HashGrid, rotations,
+                  translations, max_n_neigh=64, radius=0.10, thresholds=(0.25, 0.35, 0.40), top_k=0, cap=None):
+    """mgs_propose_poses for one object -> (proposals float32 [n,17] = 16 xform + score, pose_ids int64 [n])"""
+    r, t = _f32(rotations).reshape(-1, 16), _f32(translations).reshape(-1, 3)
+    opts = ProposeOpts(max_n_neigh, radius, (C.c_float * 3)(*thresholds), top_k)
+    cap = int(cap if cap is not None else max(len(t), 1))
+    while True:
+        out = np.zeros((cap, POSE_FLOATS), np.float32)
+        ids = np.zeros(cap, np.int64)
+        n = C.c_int64(0)
+        _check(lib().rsgpu_propose_poses(obj_lvl4.h, obj_lvl3.h, obj_lvl2.h, scene.h, _ptr(r), len(r), _ptr(t), len(t),
+                                         C.byref(opts), _ptr(out), _ptr(ids), cap, C.byref(n)))
+        if n.value <= cap:
+            return out[: n.value].copy(), ids[: n.value].copy()
+        cap = int(n.value)
+
+
+def icp_align(obj: PointCloud, scan: HashGrid, T1, max_dist, max_angle, T2=None, max_iter=0):
+    """icp_align for a batch of starting poses -> (T1 refined [B,16], err [B], iters [B])"""
+    T = _f32(T1).reshape(-1, 16).copy()
+    T2 = _f32(T2 if T2 is not None else np.eye(4).reshape(16)).reshape(16)
+    err = np.zeros(len(T), np.float32)
+    it = np.zeros(len(T), np.int32)
+    _check(lib().rsgpu_icp_align_batch_ex(obj.h, scan.h, _ptr(T), len(T), _ptr(T2), max_dist, max_angle, max_iter,
+                                          _ptr(err), _ptr(it)))
+    return T, err, it
+
+
+def assign_labels(scan_pos, scan_nor, poses, object_grids, first, last, radius, labels, min_dists):
+    """rspf__assign_temporary_labels over placements [first, last); labels (int8) / min_dists (float32) updated in place"""
+    sp, sn = _f32(scan_pos).reshape(-1, 3), _f32(scan_nor).reshape(-1, 3)
+    ps = _f32(poses).reshape(-1, 16)
+    assert labels.dtype == np.int8 and min_dists.dtype == np.float32 and labels.flags.c_contiguous
+    gh = (C.c_void_p * len(object_grids))(*[g.h for g in object_grids])
+    _check(lib().rsgpu_assign_labels(_ptr(sp), _ptr(sn), len(sp), _ptr(ps), gh, first, last, radius, _ptr(labels),
+                                     _ptr(min_dists)))
+
+
+def unary_costs(labels, label_is_static, n_labels):
+    lab = np.ascontiguousarray(labels, np.int32)
+    st = np.ascontiguousarray(label_is_static, np.uint8)
+    out = np.zeros((len(lab), n_labels), np.int32)
+    _check(lib().rsgpu_unary_costs(_ptr(lab), _ptr(st), len(lab), n_labels, _ptr(out)))
+    return out
+
+
+def neighborhood(grid: HashGrid, pos, nor, max_nn=8, radius_sq=np.float32(0.05) * np.float32(0.05), dist_exp=15.0,
+                 angle_exp=16.0):
+    p, n = _f32(pos).reshape(-1, 3), _f32(nor).reshape(-1, 3)
+    nbr = np.zeros((len(p), max_nn), np.int32)
+    w = np.zeros((len(p), max_nn), np.float32)
+    _check(lib().rsgpu_neighborhood(grid.h, _ptr(p), _ptr(n), len(p), max_nn, radius_sq, dist_exp, angle_exp, _ptr(nbr),
+                                    _ptr(w)))
+    return nbr, w

@@ -1,0 +1,523 @@
+// Batched point-to-plane ICP: replaces icp_align (reference lib/rs/icp.h:416-500) with its per-iteration
+// icp_find_corrs (:306-412) and icp_estimate_rigid_xform_pt2pl (:210-298, LDL^T from lineqn.h:153-218).
+//
+// One thread block per starting pose, resident for the whole alignment (no host round trips, one launch for
+// the batch).  Every iteration: (A) the block's warps find correspondences with nearest_compatible (k = 16
+// rank rule, acosf gate folded into a dot threshold); (B) three block-wide fp64 reductions — distance
+// statistics for the 2.5 sigma rejection, weighted centroids, the 6x6 normal equations — each reduced with
+// warp shuffles in a fixed order (deterministic); (C) thread 0 factors and solves the 6x6 system in fp64
+// exactly like trimesh::ldltdc/ldltsl and composes the update with the reference's float msh_translate /
+// msh_rotate / msh_mat4_mul order.  The scan grid is built ONCE by the caller and shared by all poses: the
+// search is exact, so the reference's per-call grid rebuild (:434-437) is not reproduced.
+//
+// Deliberate deviation: the reference accumulates its sums sequentially in float; here the terms
+// are formed in float exactly as the reference forms them and summed in fp64.  Results agree to the
+// tolerance stated in tests (1e-5 m / 1e-5 rad), not bit for bit.
+#include "rsgpu_internal.cuh"
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+
+using namespace rs;
+
+namespace
+{
+constexpr int ICP_THREADS = 512;
+constexpr int ICP_WARPS = ICP_THREADS / 32;
+constexpr int ICP_MAX_NV = 32;
+
+struct IcpShared
+{
+  float T[16];        // current T1
+  float M[16];        // T2i applied after T1 is done point by point, kept separately
+  float max_dist, prev_err, err;
+  int stop, steps;
+  double red[ICP_WARPS][ICP_MAX_NV];
+  double out[ICP_MAX_NV];
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce( double* v, IcpShared& sh )
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for( int i = 0; i < NV; ++i )
+  {
+    double x = v[i];
+#pragma unroll
+    for( int o = 16; o > 0; o >>= 1 ) { x += __shfl_down_sync( RS_FULL, x, o ); }
+    if( lane == 0 ) { sh.red[warp][i] = x; }
+  }
+  __syncthreads();
+  if( threadIdx.x < NV )
+  {
+    double s = 0.0;
+    for( int w = 0; w < ICP_WARPS; ++w ) { s += sh.red[w][threadIdx.x]; }
+    sh.out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// msh_translate (msh_vec_math.h:2064-2073): col3 = (col0*tx + col1*ty) + (col2*tz + col3)
+__device__ void xf_translate( float* m, float tx, float ty, float tz )
+{
+  for( int r = 0; r < 4; ++r )
+  {
+    m[12 + r] = __fadd_rn( __fadd_rn( __fmul_rn( m[r], tx ), __fmul_rn( m[4 + r], ty ) ), __fadd_rn( __fmul_rn( m[8 + r], tz ), m[12 + r] ) );
+  }
+}
+
+// msh_rotate (msh_vec_math.h:2089-2136) about a unit coordinate axis
+__device__ void xf_rotate( float* m, float angle, float ax, float ay, float az )
+{
+  // cosf/sinf of the host libm are (almost always) correctly rounded; fp64 evaluation rounded to float matches them
+  float c = (float)cos( (double)angle ), s = (float)sin( (double)angle ), t = __fsub_rn( 1.0f, c );
+  float inv = __fdiv_rn( 1.0f, sqrtf( __fadd_rn( __fadd_rn( __fmul_rn( ax, ax ), __fmul_rn( ay, ay ) ), __fmul_rn( az, az ) ) ) );
+  ax = __fmul_rn( ax, inv ); ay = __fmul_rn( ay, inv ); az = __fmul_rn( az, inv );
+  float R[16];
+  for( int i = 0; i < 16; ++i ) { R[i] = 0.f; }
+  R[0] = __fadd_rn( c, __fmul_rn( __fmul_rn( ax, ax ), t ) );
+  R[5] = __fadd_rn( c, __fmul_rn( __fmul_rn( ay, ay ), t ) );
+  R[10] = __fadd_rn( c, __fmul_rn( __fmul_rn( az, az ), t ) );
+  float a = __fmul_rn( __fmul_rn( ax, ay ), t ), b = __fmul_rn( az, s );
+  R[1] = __fadd_rn( a, b ); R[4] = __fsub_rn( a, b );
+  a = __fmul_rn( __fmul_rn( ax, az ), t ); b = __fmul_rn( ay, s );
+  R[2] = __fsub_rn( a, b ); R[8] = __fadd_rn( a, b );
+  a = __fmul_rn( __fmul_rn( ay, az ), t ); b = __fmul_rn( ax, s );
+  R[6] = __fadd_rn( a, b ); R[9] = __fsub_rn( a, b );
+  float o[16];
+  for( int i = 0; i < 16; ++i ) { o[i] = m[i]; }
+  for( int j = 0; j < 3; ++j )
+    for( int r = 0; r < 4; ++r )
+    {
+      o[4 * j + r] = __fadd_rn( __fmul_rn( m[r], R[4 * j] ), __fadd_rn( __fmul_rn( m[4 + r], R[4 * j + 1] ), __fmul_rn( m[8 + r], R[4 * j + 2] ) ) );
+    }
+  for( int i = 0; i < 16; ++i ) { m[i] = o[i]; }
+}
+
+// msh_mat4_mul (msh_vec_math.h:1441-1480): o = a*b, each entry a 4-term left-to-right sum
+__device__ void xf_mul( const float* a, const float* b, float* o )
+{
+  float t[16];
+  for( int c = 0; c < 4; ++c )
+    for( int r = 0; r < 4; ++r )
+    {
+      t[4 * c + r] = __fadd_rn( __fadd_rn( __fadd_rn( __fmul_rn( b[4 * c], a[r] ), __fmul_rn( b[4 * c + 1], a[4 + r] ) ),
+                                           __fmul_rn( b[4 * c + 2], a[8 + r] ) ), __fmul_rn( b[4 * c + 3], a[12 + r] ) );
+    }
+  for( int i = 0; i < 16; ++i ) { o[i] = t[i]; }
+}
+
+// trimesh::ldltdc + ldltsl for N = 6 (lineqn.h:177-193, 206-217).  A zero pivot aborts the factorisation but
+// the caller ignores that (icp.h:276-277) and still runs the sweeps with the remaining reciprocal pivots 0.
+__device__ void ldlt_solve6( double A[6][6], const double* b, double* x )
+{
+  double rd[6] = { 0, 0, 0, 0, 0, 0 }, v[5];
+  bool ok = true;
+  for( int i = 0; i < 6 && ok; ++i )
+  {
+    for( int k = 0; k < i; ++k ) { v[k] = __dmul_rn( A[i][k], rd[k] ); }
+    for( int j = i; j < 6; ++j )
+    {
+      double s = A[i][j];
+      for( int k = 0; k < i; ++k ) { s = __dsub_rn( s, __dmul_rn( v[k], A[j][k] ) ); }
+      if( i == j ) { if( s == 0 ) { ok = false; break; } rd[i] = __ddiv_rn( 1.0, s ); }
+      else { A[j][i] = s; }
+    }
+  }
+  for( int i = 0; i < 6; ++i )
+  {
+    double s = b[i];
+    for( int k = 0; k < i; ++k ) { s = __dsub_rn( s, __dmul_rn( A[i][k], x[k] ) ); }
+    x[i] = __dmul_rn( s, rd[i] );
+  }
+  for( int i = 5; i >= 0; --i )
+  {
+    double s = 0;
+    for( int k = i + 1; k < 6; ++k ) { s = __dadd_rn( s, __dmul_rn( A[k][i], x[k] ) ); }
+    x[i] = __dsub_rn( x[i], __dmul_rn( s, rd[i] ) );
+  }
+}
+
+// Sums in the reference's own order.  The reference accumulates every sum of an ICP step sequentially in
+// float over the correspondences in point order (msh_std.h:1778-1808, icp.h:137-148, 226-252); since the 2.5
+// sigma cut and the stopping rule are discontinuous in those sums, matching its poses to 1e-5 needs the same
+// rounding.  All threads form the per-point terms in parallel into a padded shared tile (one row per thread),
+// then the 32 lanes of warp 0 each run ONE accumulator down the rows in point order: the dependent chain is a
+// single FADD (and a DADD for the two fp64 sums) per row, loads are conflict-free.  Rows of points without a
+// correspondence hold zeros, which leave a float sum unchanged.
+constexpr int TILE_LD = 33;
+
+template <int NV, class TermFn>
+__device__ __forceinline__ void ordered_sums( int n, TermFn term_fn, float* tile, float* fout, double* dout )
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float fa = 0.0f; double da = 0.0;
+  for( int base = 0; base < n; base += ICP_THREADS )
+  {
+    float t[NV];
+#pragma unroll
+    for( int v = 0; v < NV; ++v ) { t[v] = 0.0f; }
+    if( base + tid < n ) { term_fn( base + tid, t ); }
+#pragma unroll
+    for( int v = 0; v < NV; ++v ) { tile[tid * TILE_LD + v] = t[v]; }
+    __syncthreads();
+    if( warp == 0 && lane < NV )
+    {
+      const int rows = min( ICP_THREADS, n - base );
+#pragma unroll 8
+      for( int r = 0; r < rows; ++r )
+      {
+        float x = tile[r * TILE_LD + lane];
+        fa = __fadd_rn( fa, x );
+        da = __dadd_rn( da, (double)x );
+      }
+    }
+    __syncthreads();
+  }
+  if( warp == 0 ) { fout[lane] = fa; dout[lane] = da; }
+  __syncthreads();
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const float* __restrict__ p1, const float* __restrict__ n1, int c1n,
+                                                             float* __restrict__ T1_io, const float* __restrict__ T2i, float max_dist0,
+                                                             float dot_thr, int max_iter, float4* __restrict__ scratch_q,
+                                                             uint2* __restrict__ scratch_m, float* __restrict__ errs,
+                                                             int* __restrict__ iters )
+{
+  __shared__ IcpShared sh;
+  extern __shared__ float tile[]; // EXACT: ICP_THREADS * TILE_LD floats
+  __shared__ float fout[32];
+  __shared__ double dout[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4* cq = scratch_q + (size_t)b * c1n;  // {q, d2}
+  uint2* cm = scratch_m + (size_t)b * c1n;   // {recs position or ~0, dot bits}
+  if( tid < 16 ) { sh.T[tid] = T1_io[16 * (size_t)b + tid]; sh.M[tid] = T2i[tid]; }
+  if( tid == 0 ) { sh.max_dist = max_dist0; sh.prev_err = 1e6f; sh.err = 1e6f; sh.stop = 0; sh.steps = 0; }
+  __syncthreads();
+
+  for( int it = 0; it < max_iter; ++it )
+  {
+    if( tid == 0 ) { sh.prev_err = sh.err; }
+    const float max_dist = sh.max_dist;
+    const double radius = (double)max_dist;
+    const float r2f = (float)__dmul_rn( radius, radius );
+    // ---- (A) correspondences (icp.h:339-391): one warp per object point
+    for( int i = warp; i < c1n; i += ICP_WARPS )
+    {
+      float ax, ay, az, bx, by, bz, qx, qy, qz, mx, my, mz;
+      xf_apply( sh.T, __ldg( p1 + 3 * (size_t)i ), __ldg( p1 + 3 * (size_t)i + 1 ), __ldg( p1 + 3 * (size_t)i + 2 ), 1.0f, ax, ay, az );
+      xf_apply( sh.T, __ldg( n1 + 3 * (size_t)i ), __ldg( n1 + 3 * (size_t)i + 1 ), __ldg( n1 + 3 * (size_t)i + 2 ), 0.0f, bx, by, bz );
+      xf_apply( sh.M, ax, ay, az, 1.0f, qx, qy, qz );
+      xf_apply( sh.M, bx, by, bz, 0.0f, mx, my, mz );
+      NearestHit h = nearest_compatible<false>( g, qx, qy, qz, mx, my, mz, radius, r2f, dot_thr, 16, nullptr );
+      if( lane == 0 )
+      {
+        cq[i] = make_float4( qx, qy, qz, h.d2 );
+        float dot = h.dot > 0.0f ? h.dot : 0.0f;
+        cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
+      }
+    }
+    __syncthreads();
+    // ---- (B1) statistics of the squared distances (icp.h:394-396; msh_std.h:1778-1824)
+    int nc; float sum_d, sum_dd;
+    if( EXACT )
+    {
+      int mine = 0;
+      for( int i = tid; i < c1n; i += ICP_THREADS ) { mine += cm[i].x != 0xffffffffu; }
+      {
+        double v[1] = { (double)mine };
+        block_reduce<1>( v, sh );
+        nc = (int)sh.out[0];
+      }
+      ordered_sums<2>( c1n, [&]( int i, float* t ) {
+        if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; t[0] = d; t[1] = __fmul_rn( d, d ); }
+      }, tile, fout, dout );
+      sum_d = fout[0]; sum_dd = fout[1];
+    }
+    else
+    {
+      double v[3] = { 0, 0, 0 };
+      for( int i = tid; i < c1n; i += ICP_THREADS )
+      {
+        if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; v[0] += 1.0; v[1] += (double)d; v[2] += (double)__fmul_rn( d, d ); }
+      }
+      block_reduce<3>( v, sh );
+      nc = (int)sh.out[0]; sum_d = (float)sh.out[1]; sum_dd = (float)sh.out[2];
+    }
+    if( nc == 0 ) { break; } // (icp.h:453-457)
+    const float mean = __fdiv_rn( sum_d, (float)nc );
+    const float sd = (float)sqrt( (double)__fsub_rn( __fdiv_rn( sum_dd, (float)nc ), __fmul_rn( mean, mean ) ) );
+    const bool reject = (double)sd > 0.000001;
+    const float cut = __fmul_rn( 2.5f, sd );
+    __syncthreads();
+    // weight of correspondence i (icp.h:387, 397-402)
+    auto weight = [&]( const float4& q, const uint2& m ) {
+      float w = __fmul_rn( __fsub_rn( 1.0f, __fdiv_rn( q.w, max_dist ) ), __uint_as_float( m.y ) );
+      if( reject && q.w > cut ) { w = 0.0f; }
+      return w;
+    };
+    // ---- (B2) weighted centroids (icp.h:137-148)
+    float s7[7];
+    if( EXACT )
+    {
+      ordered_sums<7>( c1n, [&]( int i, float* t ) {
+        uint2 m = cm[i];
+        if( m.x == 0xffffffffu ) { return; }
+        float4 q = cq[i];
+        float w = weight( q, m );
+        float4 p2 = __ldg( g.recs + m.x );
+        t[0] = w;
+        t[1] = __fmul_rn( q.x, w ); t[2] = __fmul_rn( q.y, w ); t[3] = __fmul_rn( q.z, w );
+        t[4] = __fmul_rn( p2.x, w ); t[5] = __fmul_rn( p2.y, w ); t[6] = __fmul_rn( p2.z, w );
+      }, tile, fout, dout );
+#pragma unroll
+      for( int j = 0; j < 7; ++j ) { s7[j] = fout[j]; }
+    }
+    else
+    {
+      double v[7] = { 0, 0, 0, 0, 0, 0, 0 };
+      for( int i = tid; i < c1n; i += ICP_THREADS )
+      {
+        uint2 m = cm[i];
+        if( m.x == 0xffffffffu ) { continue; }
+        float4 q = cq[i];
+        float w = weight( q, m );
+        float4 p2 = __ldg( g.recs + m.x );
+        v[0] += (double)w;
+        v[1] += (double)__fmul_rn( q.x, w ); v[2] += (double)__fmul_rn( q.y, w ); v[3] += (double)__fmul_rn( q.z, w );
+        v[4] += (double)__fmul_rn( p2.x, w ); v[5] += (double)__fmul_rn( p2.y, w ); v[6] += (double)__fmul_rn( p2.z, w );
+      }
+      block_reduce<7>( v, sh );
+#pragma unroll
+      for( int j = 0; j < 7; ++j ) { s7[j] = (float)sh.out[j]; }
+    }
+    const float tw = s7[0];
+    if( (double)tw <= 1e-7 ) { break; } // (icp.h:459-468)
+    const float itw = __fdiv_rn( 1.0f, tw ); // msh_vec3_scalar_div multiplies by the reciprocal (msh_vec_math.h:754-758)
+    const float c1x = __fmul_rn( s7[1], itw ), c1y = __fmul_rn( s7[2], itw ), c1z = __fmul_rn( s7[3], itw );
+    const float c2x = __fmul_rn( s7[4], itw ), c2y = __fmul_rn( s7[5], itw ), c2z = __fmul_rn( s7[6], itw );
+    __syncthreads();
+    // ---- (B3) normal equations (icp.h:226-252): TL = sum w c c^T, TR = sum w c n^T, BR = sum w n n^T, b = sum w [c;n] (d.n)
+    // 29 terms per correspondence: TL (6 unique), TR (9), BR (6 unique), b (6), w (d.n)^2, w
+    auto terms29 = [&]( int i, float* t ) -> bool {
+      uint2 m = cm[i];
+      if( m.x == 0xffffffffu ) { return false; }
+      float4 q4 = cq[i];
+      float w = weight( q4, m );
+      float4 p2 = __ldg( g.recs + m.x ), nn = __ldg( g.nrm + m.x );
+      float px = __fsub_rn( q4.x, c1x ), py = __fsub_rn( q4.y, c1y ), pz = __fsub_rn( q4.z, c1z );
+      float qx = __fsub_rn( p2.x, c2x ), qy = __fsub_rn( p2.y, c2y ), qz = __fsub_rn( p2.z, c2z );
+      float dx = __fsub_rn( px, qx ), dy = __fsub_rn( py, qy ), dz = __fsub_rn( pz, qz );
+      float c[3], n[3] = { nn.x, nn.y, nn.z };
+      c[0] = __fsub_rn( __fmul_rn( py, nn.z ), __fmul_rn( pz, nn.y ) );
+      c[1] = __fsub_rn( __fmul_rn( pz, nn.x ), __fmul_rn( px, nn.z ) );
+      c[2] = __fsub_rn( __fmul_rn( px, nn.y ), __fmul_rn( py, nn.x ) );
+      float dn = dot3_exact( dx, dy, dz, nn.x, nn.y, nn.z );
+      int o = 0;
+#pragma unroll
+      for( int col = 0; col < 3; ++col )
+#pragma unroll
+        for( int row = col; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( c[row], c[col] ), w ); }
+#pragma unroll
+      for( int col = 0; col < 3; ++col )
+#pragma unroll
+        for( int row = 0; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( c[row], n[col] ), w ); }
+#pragma unroll
+      for( int col = 0; col < 3; ++col )
+#pragma unroll
+        for( int row = col; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( n[row], n[col] ), w ); }
+#pragma unroll
+      for( int a = 0; a < 3; ++a ) { t[21 + a] = __fmul_rn( __fmul_rn( w, c[a] ), dn ); t[24 + a] = __fmul_rn( __fmul_rn( w, n[a] ), dn ); }
+      t[27] = __fmul_rn( __fmul_rn( w, dn ), dn );
+      t[28] = w;
+      return true;
+    };
+    if( EXACT )
+    {
+      ordered_sums<29>( c1n, [&]( int i, float* t ) { terms29( i, t ); }, tile, fout, dout );
+      if( tid < 27 ) { sh.out[tid] = (double)fout[tid]; }
+      if( tid == 27 || tid == 28 ) { sh.out[tid] = dout[tid]; }
+      __syncthreads();
+    }
+    else
+    {
+      double v[29];
+#pragma unroll
+      for( int j = 0; j < 29; ++j ) { v[j] = 0.0; }
+      for( int i = tid; i < c1n; i += ICP_THREADS )
+      {
+        float t[29];
+        if( terms29( i, t ) )
+        {
+#pragma unroll
+          for( int j = 0; j < 29; ++j ) { v[j] += (double)t[j]; }
+        }
+      }
+      block_reduce<29>( v, sh );
+    }
+    // ---- (C) solve + compose (icp.h:253-295), one thread
+    if( tid == 0 )
+    {
+      const double* s = sh.out;
+      float TL[3][3], TR[3][3], BR[3][3]; // [col][row]
+      int o = 0;
+      for( int col = 0; col < 3; ++col ) for( int row = col; row < 3; ++row ) { TL[col][row] = TL[row][col] = (float)s[o++]; }
+      for( int col = 0; col < 3; ++col ) for( int row = 0; row < 3; ++row ) { TR[col][row] = (float)s[o++]; }
+      for( int col = 0; col < 3; ++col ) for( int row = col; row < 3; ++row ) { BR[col][row] = BR[row][col] = (float)s[o++]; }
+      float err = (float)sqrt( __ddiv_rn( s[27], s[28] ) );
+      double A[6][6], rhs[6], x[6] = { 0, 0, 0, 0, 0, 0 };
+      for( int r = 0; r < 3; ++r )
+        for( int c = 0; c < 3; ++c )
+        {
+          A[r][c] = TL[c][r]; A[r][3 + c] = TR[c][r];
+          A[3 + r][c] = TR[r][c]; A[3 + r][3 + c] = BR[c][r];
+        }
+      for( int a = 0; a < 6; ++a ) { rhs[a] = -(double)(float)s[21 + a]; }
+      ldlt_solve6( A, rhs, x );
+      float T[16];
+      for( int i = 0; i < 16; ++i ) { T[i] = ( i % 5 == 0 ) ? 1.0f : 0.0f; }
+      xf_translate( T, c1x, c1y, c1z );
+      xf_translate( T, (float)x[3], (float)x[4], (float)x[5] );
+      xf_rotate( T, (float)x[0], 1.0f, 0.0f, 0.0f );
+      xf_rotate( T, (float)x[1], 0.0f, 1.0f, 0.0f );
+      xf_rotate( T, (float)x[2], 0.0f, 0.0f, 1.0f );
+      xf_translate( T, -c1x, -c1y, -c1z );
+      float Tn[16];
+      xf_mul( T, sh.T, Tn );
+      for( int i = 0; i < 16; ++i ) { sh.T[i] = Tn[i]; }
+      sh.err = err; sh.steps += 1;
+      float delta = fabsf( __fsub_rn( sh.prev_err, err ) );
+      if( it > 5 && (double)delta < 1e-5 ) { sh.stop = 1; }
+      double shrunk = __dmul_rn( (double)max_dist, 0.95 );
+      sh.max_dist = (float)( shrunk > 0.05 ? shrunk : 0.05 );
+    }
+    __syncthreads();
+    if( sh.stop ) { break; }
+  }
+  __syncthreads();
+  if( tid < 16 ) { T1_io[16 * (size_t)b + tid] = sh.T[tid]; }
+  if( tid == 0 ) { errs[b] = sh.err; if( iters ) { iters[b] = sh.steps; } }
+}
+
+// msh_mat4_inverse (msh_vec_math.h:1818-1917): cofactor expansion over 2x2 minors, all float, each cofactor
+// a three-term expression evaluated left to right, scaled by 1.0f/det
+float tri( float a, float x, float b, float y, float c, float z, int s2, int s3 )
+{
+  volatile float r = a * x;
+  volatile float t = b * y;
+  r = s2 > 0 ? r + t : r - t;
+  t = c * z;
+  r = s3 > 0 ? r + t : r - t;
+  return r;
+}
+float det2( float a, float b, float c, float d )
+{
+  volatile float x = a * b, y = c * d;
+  volatile float r = x - y;
+  return r;
+}
+} // namespace
+
+namespace rs
+{
+void mat4_inverse_ref( const float* m, float* o )
+{
+  float C[16], d[6];
+  d[0] = det2( m[10], m[15], m[14], m[11] ); d[1] = det2( m[6], m[11], m[10], m[7] ); d[2] = det2( m[2], m[7], m[6], m[3] );
+  d[3] = det2( m[6], m[15], m[14], m[7] );   d[4] = det2( m[2], m[11], m[10], m[3] ); d[5] = det2( m[2], m[15], m[14], m[3] );
+  C[0] = tri( m[5], d[0], m[9], d[3], m[13], d[1], -1, +1 );
+  C[1] = tri( m[9], d[5], m[1], d[0], m[13], d[4], -1, -1 );
+  C[2] = tri( m[1], d[3], m[5], d[5], m[13], d[2], -1, +1 );
+  C[3] = tri( m[5], d[4], m[9], d[2], m[1], d[1], -1, -1 );
+  C[4] = tri( m[8], d[3], m[4], d[0], m[12], d[1], -1, -1 );
+  C[5] = tri( m[0], d[0], m[8], d[5], m[12], d[4], -1, +1 );
+  C[6] = tri( m[4], d[5], m[0], d[3], m[12], d[2], -1, -1 );
+  C[7] = tri( m[0], d[1], m[4], d[4], m[8], d[2], -1, +1 );
+  d[0] = det2( m[8], m[13], m[12], m[9] ); d[1] = det2( m[4], m[9], m[8], m[5] );  d[2] = det2( m[0], m[5], m[4], m[1] );
+  d[3] = det2( m[4], m[13], m[12], m[5] ); d[4] = det2( m[0], m[9], m[8], m[1] );  d[5] = det2( m[0], m[13], m[12], m[1] );
+  C[8]  = tri( m[7], d[0], m[11], d[3], m[15], d[1], -1, +1 );
+  C[9]  = tri( m[11], d[5], m[3], d[0], m[15], d[4], -1, -1 );
+  C[10] = tri( m[3], d[3], m[7], d[5], m[15], d[2], -1, +1 );
+  C[11] = tri( m[7], d[4], m[3], d[1], m[11], d[2], -1, -1 );
+  C[12] = tri( m[10], d[3], m[6], d[0], m[14], d[1], -1, -1 );
+  C[13] = tri( m[2], d[0], m[10], d[5], m[14], d[4], -1, +1 );
+  C[14] = tri( m[6], d[5], m[2], d[3], m[14], d[2], -1, -1 );
+  C[15] = tri( m[2], d[1], m[6], d[4], m[10], d[2], -1, +1 );
+  volatile float det = m[0] * C[0];
+  volatile float t = m[4] * C[1]; det = det + t;
+  t = m[8] * C[2]; det = det + t;
+  t = m[12] * C[3]; det = det + t;
+  float s = 1.0f / det;
+  for( int i = 0; i < 16; ++i ) { o[i] = s * C[i]; }
+}
+
+// smallest float dot with acosf(dot) < max_angle (icp.h:373-374); -inf when even dot = 0 passes, because the
+// reference clamps negative dots to 0 before the test
+float compat_threshold_acosf( float max_angle )
+{
+  auto ok = [&]( float d ) { return acosf( d ) < max_angle; };
+  if( ok( 0.0f ) ) { return -INFINITY; }
+  if( !ok( 1.0f ) ) { return 2.0f; }
+  uint32_t lo, hi; float f0 = 0.0f, f1 = 1.0f;
+  memcpy( &lo, &f0, 4 ); memcpy( &hi, &f1, 4 );
+  while( hi - lo > 1 )
+  {
+    uint32_t mid = lo + ( hi - lo ) / 2; float fm; memcpy( &fm, &mid, 4 );
+    if( ok( fm ) ) { hi = mid; } else { lo = mid; }
+  }
+  float out; memcpy( &out, &hi, 4 );
+  return out;
+}
+} // namespace rs
+
+extern "C" int rsgpu_icp_align_batch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scan, float* T1, int32_t n_batch, const float* T2,
+                                      float max_dist, float max_angle, float* errs, int32_t* iters )
+{
+  return rsgpu_icp_align_batch_ex( obj, scan, T1, n_batch, T2, max_dist, max_angle, 100, errs, iters );
+}
+
+extern "C" int rsgpu_icp_align_batch_ex( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scan, float* T1, int32_t n_batch, const float* T2,
+                                         float max_dist, float max_angle, int32_t max_iter, float* errs, int32_t* iters )
+{
+  if( max_iter <= 0 ) { max_iter = 100; }
+  // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
+  const char* mode = getenv( "RSGPU_ICP_SUMS" );
+  const bool exact = !( mode && strcmp( mode, "fp64" ) == 0 );
+  if( !obj || !scan || n_batch < 0 || ( n_batch > 0 && ( !T1 || !errs ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align_batch: bad argument" ); }
+  RS_TRY( ensure_device() );
+  if( n_batch == 0 ) { return RSGPU_OK; }
+  if( !scan->has_normals ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align_batch: the scan grid has no normals" ); }
+  if( !( max_dist > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align_batch: max_dist must be > 0" ); }
+  cudaStream_t st = rt().stream;
+  float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
+  mat4_inverse_ref( T2 ? T2 : ident, T2i );
+  const int n = obj->n;
+  DevBuf<float> dT, dT2i, derr; DevBuf<int> dit; DevBuf<float4> sq; DevBuf<uint2> sm;
+  RS_CUDA( dT.alloc( (size_t)n_batch * 16 ) ); RS_CUDA( dT2i.alloc( 16 ) ); RS_CUDA( derr.alloc( n_batch ) ); RS_CUDA( dit.alloc( n_batch ) );
+  RS_CUDA( sq.alloc( (size_t)n_batch * ( n > 0 ? n : 1 ) ) ); RS_CUDA( sm.alloc( (size_t)n_batch * ( n > 0 ? n : 1 ) ) );
+  RS_CUDA( cudaMemcpyAsync( dT.p, T1, sizeof( float ) * 16 * (size_t)n_batch, cudaMemcpyHostToDevice, st ) );
+  RS_CUDA( cudaMemcpyAsync( dT2i.p, T2i, 64, cudaMemcpyHostToDevice, st ) );
+  {
+    ProfScope prof( "icp" );
+    const size_t tile_bytes = sizeof( float ) * ICP_THREADS * TILE_LD;
+    if( exact )
+    {
+      RS_CUDA( cudaFuncSetAttribute( icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
+      icp_kernel<true><<<n_batch, ICP_THREADS, tile_bytes, st>>>( scan->view(), obj->pos.p, obj->nor.p, n, dT.p, dT2i.p, max_dist,
+                                                                   compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
+    }
+    else
+    {
+      icp_kernel<false><<<n_batch, ICP_THREADS, 0, st>>>( scan->view(), obj->pos.p, obj->nor.p, n, dT.p, dT2i.p, max_dist,
+                                                           compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
+    }
+    RS_CHECK_LAUNCH();
+  }
+  RS_CUDA( cudaMemcpyAsync( T1, dT.p, sizeof( float ) * 16 * (size_t)n_batch, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( errs, derr.p, sizeof( float ) * (size_t)n_batch, cudaMemcpyDeviceToHost, st ) );
+  if( iters ) { RS_CUDA( cudaMemcpyAsync( iters, dit.p, sizeof( int32_t ) * (size_t)n_batch, cudaMemcpyDeviceToHost, st ) ); }
+  RS_CUDA( cudaStreamSynchronize( st ) );
+  return RSGPU_OK;
+}

@@ -1,0 +1,301 @@
+// Internal declarations shared by the rsgpu translation units (sm_100a only).
+//
+// Exactness contract (SURVEY.md §7 "hard parts" 1): the reference is x86-64 gcc -O3 without FMA, so every
+// float/double expression a result depends on is written here with the non-contracting intrinsics
+// (__fmul_rn/__fadd_rn/__dmul_rn/...) in the reference's evaluation order; the library is additionally built
+// with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "rsgpu.h"
+
+#define RS_FULL 0xffffffffu
+#define RS_INF_BITS 0x7f800000u
+
+// ---------------------------------------------------------------------------------------------- host runtime
+namespace rs
+{
+struct Runtime
+{
+  cudaStream_t stream = 0;
+  int device = 0;
+  bool profile = false;
+};
+Runtime& rt();
+int fail( int code, const std::string& msg );
+int cuda_fail( cudaError_t e, const char* what, const char* file, int line );
+int ensure_device();
+void count_launch(); // one of OUR kernels was launched (library kernels such as CUB are not counted)
+
+// RAII device buffer
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf( const DevBuf& ) = delete;
+  DevBuf& operator=( const DevBuf& ) = delete;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if( p ) { cudaFree( p ); }
+    p = nullptr; n = 0;
+  }
+  cudaError_t alloc( size_t count )
+  {
+    release();
+    n = count;
+    return cudaMalloc( (void**)&p, sizeof( T ) * ( count ? count : 1 ) );
+  }
+};
+
+// scoped per-kernel event timer (active only when profiling is enabled)
+struct ProfScope
+{
+  const char* name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit ProfScope( const char* n );
+  ~ProfScope();
+};
+} // namespace rs
+
+#define RS_CUDA( call )                                                                     \
+  do {                                                                                      \
+    cudaError_t e__ = ( call );                                                             \
+    if( e__ != cudaSuccess ) { return rs::cuda_fail( e__, #call, __FILE__, __LINE__ ); }    \
+  } while( 0 )
+#define RS_CHECK_LAUNCH() do { rs::count_launch(); RS_CUDA( cudaGetLastError() ); } while( 0 )
+#define RS_TRY( call )                                                                      \
+  do { int s__ = ( call ); if( s__ != RSGPU_OK ) { return s__; } } while( 0 )
+
+// ---------------------------------------------------------------------------------------------- device views
+// Grid as kernels see it.  Dense layout: cell (x,y,z) -> id = (z*H + y)*W + x (x fastest, like
+// msh_hash_grid.h:375-379), points of cell id are recs[cell_start[id] .. cell_start[id+1]) in ascending
+// original index (msh_hash_grid.h:501-532), one 16-byte record {x, y, z, bitcast(idx)} per point like the
+// reference's msh_hg_v3i_t, normals (if set) in the same order as 16-byte {nx, ny, nz, 0}.
+struct GridView
+{
+  const float4* __restrict__ recs;
+  const float4* __restrict__ nrm;
+  const uint32_t* __restrict__ cell_start;
+  float mnx, mny, mnz;
+  int W, H, D;
+  double cell, inv_cell;
+  int n_pts;
+};
+
+struct rsgpu_grid
+{
+  rs::DevBuf<float4> recs;
+  rs::DevBuf<float4> nrm;
+  rs::DevBuf<uint32_t> cell_start;
+  bool has_normals = false;
+  rsgpu_grid_info_t info;
+  GridView view() const
+  {
+    GridView v;
+    v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p;
+    v.mnx = info.min_pt[0]; v.mny = info.min_pt[1]; v.mnz = info.min_pt[2];
+    v.W = (int)info.width; v.H = (int)info.height; v.D = (int)info.depth;
+    v.cell = info.cell_size; v.inv_cell = info.inv_cell_size; v.n_pts = (int)info.n_pts;
+    return v;
+  }
+};
+
+struct rsgpu_cloud
+{
+  rs::DevBuf<float> pos; // n x 3
+  rs::DevBuf<float> nor; // n x 3
+  int32_t n = 0;
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------- exact math
+// msh_mat4_vec3_mul (msh_vec_math.h:1554-1561): ((m0*x + m4*y) + m8*z) + w*m12, float, left to right
+__device__ __forceinline__ void xf_apply( const float* __restrict__ m, float x, float y, float z, float w,
+                                          float& ox, float& oy, float& oz )
+{
+  ox = __fadd_rn( __fadd_rn( __fadd_rn( __fmul_rn( m[0], x ), __fmul_rn( m[4], y ) ), __fmul_rn( m[8], z ) ), __fmul_rn( w, m[12] ) );
+  oy = __fadd_rn( __fadd_rn( __fadd_rn( __fmul_rn( m[1], x ), __fmul_rn( m[5], y ) ), __fmul_rn( m[9], z ) ), __fmul_rn( w, m[13] ) );
+  oz = __fadd_rn( __fadd_rn( __fadd_rn( __fmul_rn( m[2], x ), __fmul_rn( m[6], y ) ), __fmul_rn( m[10], z ) ), __fmul_rn( w, m[14] ) );
+}
+
+// squared distance of msh_hash_grid__find_neighbors_in_bin (msh_hash_grid.h:852-855): (vx*vx + vy*vy) + vz*vz
+__device__ __forceinline__ float dist2_exact( const float4& r, float px, float py, float pz )
+{
+  float vx = __fsub_rn( r.x, px ), vy = __fsub_rn( r.y, py ), vz = __fsub_rn( r.z, pz );
+  return __fadd_rn( __fadd_rn( __fmul_rn( vx, vx ), __fmul_rn( vy, vy ) ), __fmul_rn( vz, vz ) );
+}
+
+__device__ __forceinline__ float dot3_exact( float ax, float ay, float az, float bx, float by, float bz )
+{
+  return __fadd_rn( __fadd_rn( __fmul_rn( ax, bx ), __fmul_rn( ay, by ) ), __fmul_rn( az, bz ) );
+}
+
+// ---------------------------------------------------------------------------------------------- cell window
+// The block of cells one radius query examines (msh_hash_grid.h:1150-1225), warp-uniform.
+struct CellWindow
+{
+  float qx, qy, qz;          // query minus grid min, float (:1159-1161)
+  int c0x, c0y, c0z;         // the query's own cell (:1165-1167), may lie outside the grid
+  int lox, loy, loz;         // clipped inclusive range
+  int nx, ny, nz;            // clipped extents (0 when empty)
+  int n_cells;               // min(nx*ny*nz, RSGPU_MAX_CELLS_PER_QUERY)  (:1213 cap)
+};
+
+__device__ __forceinline__ int clamp_ll( long long v, long long lo, long long hi )
+{
+  return (int)( v < lo ? lo : ( v > hi ? hi : v ) );
+}
+
+__device__ __forceinline__ CellWindow make_window( const GridView& g, float px, float py, float pz, double radius )
+{
+  CellWindow w;
+  w.qx = __fsub_rn( px, g.mnx ); w.qy = __fsub_rn( py, g.mny ); w.qz = __fsub_rn( pz, g.mnz );
+  double dq[3] = { (double)w.qx, (double)w.qy, (double)w.qz };
+  long long c0[3], lo[3], hi[3];
+#pragma unroll
+  for( int a = 0; a < 3; ++a )
+  {
+    c0[a] = __double2ll_rz( __dmul_rn( dq[a], g.inv_cell ) );
+    hi[a] = __double2ll_rz( __dmul_rn( __dadd_rn( dq[a], radius ), g.inv_cell ) );
+    lo[a] = __double2ll_rz( __dmul_rn( __dsub_rn( dq[a], radius ), g.inv_cell ) );
+  }
+  const long long big = 1 << 28;
+  w.c0x = clamp_ll( c0[0], -big, big ); w.c0y = clamp_ll( c0[1], -big, big ); w.c0z = clamp_ll( c0[2], -big, big );
+  int hx, hy, hz;
+  w.lox = clamp_ll( lo[0], 0, g.W ); hx = clamp_ll( hi[0], -1, g.W - 1 );
+  w.loy = clamp_ll( lo[1], 0, g.H ); hy = clamp_ll( hi[1], -1, g.H - 1 );
+  w.loz = clamp_ll( lo[2], 0, g.D ); hz = clamp_ll( hi[2], -1, g.D - 1 );
+  w.nx = hx - w.lox + 1; w.ny = hy - w.loy + 1; w.nz = hz - w.loz + 1;
+  if( w.nx <= 0 || w.ny <= 0 || w.nz <= 0 ) { w.nx = w.ny = w.nz = 0; }
+  long long n = (long long)w.nx * w.ny * w.nz;
+  w.n_cells = n > RSGPU_MAX_CELLS_PER_QUERY ? RSGPU_MAX_CELLS_PER_QUERY : (int)n;
+  return w;
+}
+
+// one axis of the cell-to-query gap (:1196-1198): float of a double expression, 0 for the query's own slab
+__device__ __forceinline__ float axis_gap( int c, int c0, float q, double cell )
+{
+  if( c < c0 ) { return (float)__dsub_rn( (double)q, __dmul_rn( (double)( c + 1 ), cell ) ); }
+  if( c > c0 ) { return (float)__dsub_rn( __dmul_rn( (double)c, cell ), (double)q ); }
+  return 0.0f;
+}
+
+// Cell number `e` (enumeration order z-outer, y, x-inner like the reference) of a window: its point range
+// and the squared gap between the query and the cell (:1221).  Empty / out-of-window cells give s == e.
+__device__ __forceinline__ void window_cell( const GridView& g, const CellWindow& w, int e, uint32_t& s,
+                                             uint32_t& t, float& gap2 )
+{
+  s = t = 0; gap2 = __int_as_float( RS_INF_BITS );
+  if( e >= w.n_cells ) { return; }
+  int ix = e % w.nx; int r = e / w.nx; int iy = r % w.ny; int iz = r / w.ny;
+  int cx = w.lox + ix, cy = w.loy + iy, cz = w.loz + iz;
+  size_t id = ( (size_t)cz * g.H + cy ) * g.W + cx;
+  s = __ldg( g.cell_start + id ); t = __ldg( g.cell_start + id + 1 );
+  float gz = axis_gap( cz, w.c0z, w.qz, g.cell ), gy = axis_gap( cy, w.c0y, w.qy, g.cell ), gx = axis_gap( cx, w.c0x, w.qx, g.cell );
+  gap2 = __fadd_rn( __fadd_rn( __fmul_rn( gz, gz ), __fmul_rn( gy, gy ) ), __fmul_rn( gx, gx ) );
+}
+
+// ---------------------------------------------------------------------------------------------- nearest compatible
+// What both mgs_compute_object_alignment_score (pose_proposal.cpp:124-148) and icp_find_corrs
+// (icp.h:349-380) ask of the grid, without materialising the k-list: the nearest point within `radius`
+// whose normal is compatible (dot in [dot_thr, 1]), accepted only when fewer than k points are strictly
+// closer (= it would have been inside the reference's k-nearest list).  Warp-cooperative: all 32 lanes
+// call it with the same arguments.  Returns found; d2 / dot / pos (index into recs) of the accepted point.
+struct NearestHit
+{
+  float d2, dot;
+  uint32_t pos;
+  bool found;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ NearestHit nearest_compatible( const GridView& g, float px, float py, float pz,
+                                                          float nx, float ny, float nz, double radius, float r2f,
+                                                          float dot_thr, int k, unsigned long long* counts )
+{
+  const int lane = threadIdx.x & 31;
+  NearestHit hit; hit.found = false; hit.d2 = 0.f; hit.dot = 0.f; hit.pos = 0;
+  CellWindow w = make_window( g, px, py, pz, radius );
+  if( w.n_cells == 0 ) { return hit; }
+  const uint32_t r2bits = __float_as_uint( r2f );
+
+  // ---- phase 1: nearest compatible point, cells visited nearest-first and pruned by the running best
+  uint32_t best = r2bits;          // lane-local best d2 (as ordered bits; d2 >= 0)
+  uint32_t best_pos = 0xffffffffu; float best_dot = 0.f;
+  uint32_t dc = r2bits;            // warp-uniform bound: nothing at or beyond it can win
+  unsigned long long nB = 0, nC = 0, nHits = 0;
+  for( int base = 0; base < w.n_cells; base += 32 )
+  {
+    uint32_t s, t; float gap2;
+    window_cell( g, w, base + lane, s, t, gap2 );
+    if( COUNT ) { nB += __popc( __ballot_sync( RS_FULL, s < t ) ); nC += __reduce_add_sync( RS_FULL, t - s ); }
+    uint32_t gbits = ( s < t ) ? __float_as_uint( gap2 ) : RS_INF_BITS;
+    while( true )
+    {
+      uint32_t gmin = __reduce_min_sync( RS_FULL, gbits );
+      if( !COUNT && gmin >= dc ) { break; }
+      if( COUNT && gmin == RS_INF_BITS ) { break; }
+      int src = __ffs( __ballot_sync( RS_FULL, gbits == gmin ) ) - 1;
+      uint32_t cs = __shfl_sync( RS_FULL, s, src ), ce = __shfl_sync( RS_FULL, t, src );
+      if( lane == src ) { gbits = RS_INF_BITS; }
+      for( uint32_t p = cs + lane; p < ce; p += 32 )
+      {
+        float4 rec = __ldg( g.recs + p );
+        float d2 = dist2_exact( rec, px, py, pz );
+        uint32_t db = __float_as_uint( d2 );
+        if( COUNT && d2 < r2f ) { nHits++; }
+        if( d2 < r2f && db < best && db < dc )
+        {
+          float4 m = __ldg( g.nrm + p );
+          float dot = dot3_exact( m.x, m.y, m.z, nx, ny, nz );
+          if( dot >= dot_thr && dot <= 1.0f ) { best = db; best_pos = p; best_dot = dot; }
+        }
+      }
+      dc = __reduce_min_sync( RS_FULL, best );
+    }
+  }
+  if( COUNT ) { nHits = __reduce_add_sync( RS_FULL, (unsigned)nHits ); }
+  bool any = dc < r2bits;
+  uint32_t cnt = 0;
+  if( any )
+  {
+    // winner: smallest recs position among the lanes holding dc (deterministic tie-break)
+    uint32_t wpos = __reduce_min_sync( RS_FULL, best == dc ? best_pos : 0xffffffffu );
+    int src = __ffs( __ballot_sync( RS_FULL, best == dc && best_pos == wpos ) ) - 1;
+    hit.d2 = __uint_as_float( dc ); hit.pos = wpos; hit.dot = __shfl_sync( RS_FULL, best_dot, src );
+    // ---- phase 2: rank of the winner = number of points strictly closer; k or more => it is not in the k-list
+    const float dcf = hit.d2;
+    for( int base = 0; base < w.n_cells && cnt < (uint32_t)k; base += 32 )
+    {
+      uint32_t s, t; float gap2;
+      window_cell( g, w, base + lane, s, t, gap2 );
+      unsigned todo = __ballot_sync( RS_FULL, s < t && gap2 < dcf );
+      while( todo && cnt < (uint32_t)k )
+      {
+        int src2 = __ffs( todo ) - 1; todo &= todo - 1;
+        uint32_t cs = __shfl_sync( RS_FULL, s, src2 ), ce = __shfl_sync( RS_FULL, t, src2 );
+        for( uint32_t p0 = cs; p0 < ce && cnt < (uint32_t)k; p0 += 32 )
+        {
+          uint32_t p = p0 + lane;
+          bool closer = false;
+          if( p < ce ) { float4 rec = __ldg( g.recs + p ); closer = dist2_exact( rec, px, py, pz ) < dcf; }
+          cnt += __popc( __ballot_sync( RS_FULL, closer ) );
+        }
+      }
+    }
+    hit.found = cnt < (uint32_t)k;
+  }
+  if( COUNT && lane == 0 && counts )
+  {
+    // normals the reference fetches: up to and including the accepted neighbour, else the whole k-list
+    unsigned long long kk = (unsigned long long)k;
+    unsigned long long T = hit.found ? (unsigned long long)cnt + 1 : ( nHits < kk ? nHits : kk );
+    atomicAdd( counts + 0, 1ull ); atomicAdd( counts + 1, nB ); atomicAdd( counts + 2, nC ); atomicAdd( counts + 3, T );
+  }
+  return hit;
+}
+#endif // __CUDACC__

@@ -1,0 +1,177 @@
+// Runtime glue of librsgpu: device/stream selection, error text, per-kernel event profiling, clouds.
+#include "rsgpu_internal.cuh"
+#include <map>
+#include <vector>
+#include <mutex>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+namespace rs
+{
+static thread_local std::string g_err;
+static std::mutex g_prof_mu;
+struct ProfEntry { double ms = 0; int64_t launches = 0; };
+static std::map<std::string, ProfEntry> g_prof;
+struct Pending { std::string name; cudaEvent_t a, b; };
+static std::vector<Pending>* g_pending = nullptr;
+
+static std::atomic<long long> g_launches{ 0 };
+void count_launch() { g_launches.fetch_add( 1, std::memory_order_relaxed ); }
+long long launches() { return g_launches.load(); }
+
+Runtime& rt()
+{
+  static Runtime r;
+  return r;
+}
+
+int fail( int code, const std::string& msg )
+{
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail( cudaError_t e, const char* what, const char* file, int line )
+{
+  char buf[1024];
+  snprintf( buf, sizeof( buf ), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString( e ), file, line, what );
+  cudaGetLastError();
+  int code = RSGPU_ERR_CUDA;
+  if( e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ) { code = RSGPU_ERR_NO_DEVICE; }
+  if( e == cudaErrorMemoryAllocation ) { code = RSGPU_ERR_OOM; }
+  return fail( code, buf );
+}
+
+int ensure_device()
+{
+  static int state = 0; // 0 unknown, 1 ok, -1 none
+  if( state == 1 ) { return RSGPU_OK; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount( &n );
+  if( e != cudaSuccess || n <= 0 )
+  {
+    cudaGetLastError();
+    return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" );
+  }
+  RS_CUDA( cudaSetDevice( rt().device ) );
+  state = 1;
+  return RSGPU_OK;
+}
+
+static void drain_pending()
+{
+  if( !g_pending ) { return; }
+  for( auto& p : *g_pending )
+  {
+    float ms = 0;
+    if( cudaEventSynchronize( p.b ) == cudaSuccess && cudaEventElapsedTime( &ms, p.a, p.b ) == cudaSuccess )
+    {
+      g_prof[p.name].ms += ms;
+      g_prof[p.name].launches += 1;
+    }
+    cudaEventDestroy( p.a ); cudaEventDestroy( p.b );
+  }
+  g_pending->clear();
+}
+
+ProfScope::ProfScope( const char* n ) : name( n )
+{
+  if( !rt().profile ) { return; }
+  cudaEventCreate( &a ); cudaEventCreate( &b );
+  cudaEventRecord( a, rt().stream );
+}
+ProfScope::~ProfScope()
+{
+  if( !a ) { return; }
+  cudaEventRecord( b, rt().stream );
+  std::lock_guard<std::mutex> lk( g_prof_mu );
+  if( !g_pending ) { g_pending = new std::vector<Pending>(); }
+  g_pending->push_back( Pending{ name, a, b } );
+}
+} // namespace rs
+
+using namespace rs;
+
+extern "C" {
+
+int rsgpu_device_count( void )
+{
+  int n = 0;
+  if( cudaGetDeviceCount( &n ) != cudaSuccess ) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int rsgpu_set_device( int device )
+{
+  rt().device = device;
+  int n = rsgpu_device_count();
+  if( n <= 0 ) { return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" ); }
+  if( device < 0 || device >= n ) { return fail( RSGPU_ERR_INVALID, "rsgpu_set_device: device index out of range" ); }
+  RS_CUDA( cudaSetDevice( device ) );
+  return RSGPU_OK;
+}
+
+int rsgpu_set_stream( void* s )
+{
+  rt().stream = (cudaStream_t)s;
+  return RSGPU_OK;
+}
+
+int rsgpu_synchronize( void )
+{
+  RS_TRY( ensure_device() );
+  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  return RSGPU_OK;
+}
+
+const char* rsgpu_last_error( void ) { return g_err.c_str(); }
+const char* rsgpu_version( void ) { return "rsgpu 0.1 (sm_100a)"; }
+
+int64_t rsgpu_launch_count( void ) { return (int64_t)rs::launches(); }
+
+int rsgpu_profile_enable( int on )
+{
+  rt().profile = on != 0;
+  return RSGPU_OK;
+}
+
+int rsgpu_profile_reset( void )
+{
+  std::lock_guard<std::mutex> lk( g_prof_mu );
+  drain_pending();
+  g_prof.clear();
+  return RSGPU_OK;
+}
+
+int rsgpu_profile_get( const char* name, double* ms, int64_t* launches )
+{
+  std::lock_guard<std::mutex> lk( g_prof_mu );
+  drain_pending();
+  auto it = g_prof.find( name );
+  if( ms ) { *ms = it == g_prof.end() ? 0.0 : it->second.ms; }
+  if( launches ) { *launches = it == g_prof.end() ? 0 : it->second.launches; }
+  return RSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- clouds
+int rsgpu_cloud_create( const float* pos, const float* nor, int32_t n, rsgpu_cloud_t** out )
+{
+  if( !out || n < 0 || ( n > 0 && ( !pos || !nor ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_cloud_create: bad argument" ); }
+  RS_TRY( ensure_device() );
+  rsgpu_cloud* c = new rsgpu_cloud();
+  c->n = n;
+  cudaError_t e = c->pos.alloc( (size_t)n * 3 );
+  if( e == cudaSuccess ) { e = c->nor.alloc( (size_t)n * 3 ); }
+  if( e == cudaSuccess && n ) { e = cudaMemcpyAsync( c->pos.p, pos, sizeof( float ) * 3 * n, cudaMemcpyHostToDevice, rt().stream ); }
+  if( e == cudaSuccess && n ) { e = cudaMemcpyAsync( c->nor.p, nor, sizeof( float ) * 3 * n, cudaMemcpyHostToDevice, rt().stream ); }
+  if( e == cudaSuccess ) { e = cudaStreamSynchronize( rt().stream ); }
+  if( e != cudaSuccess ) { delete c; return cuda_fail( e, "rsgpu_cloud_create", __FILE__, __LINE__ ); }
+  *out = c;
+  return RSGPU_OK;
+}
+
+void rsgpu_cloud_destroy( rsgpu_cloud_t* c ) { delete c; }
+int32_t rsgpu_cloud_size( const rsgpu_cloud_t* c ) { return c ? c->n : 0; }
+
+} // extern "C"

@@ -1,0 +1,406 @@
+// Fused batched pose scoring and the propose pipeline built on it.
+//
+// Replaces mgs_compute_object_alignment_score (reference apps/pose_proposal/pose_proposal.cpp:93-158),
+// the dense search loop of mgs__initial_pose_proposals (:170-254), mgs__pose_verification (:256-303) and the
+// survivor copy of mgs_propose_poses (:325-369).
+//
+// One warp per candidate pose.  For every object point the warp transforms it in registers (same float
+// evaluation order as msh_mat4_vec3_mul), asks the grid for the nearest normal-compatible scan point inside
+// the k-nearest list (nearest_compatible, rsgpu_internal.cuh) and accumulates the reference's score term in
+// fp64 in the reference's point order, so no k x N neighbour lists, no per-query sort and no scratch
+// storage exist on the GPU.  The fp64 exp/acos of 32 consecutive points are evaluated lane-parallel.
+#include "rsgpu_internal.cuh"
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+using namespace rs;
+
+namespace
+{
+struct PoseSource
+{
+  const float* __restrict__ xforms;  // explicit: n x 16
+  const float* __restrict__ rots;    // grid: n_rot x 16
+  const float* __restrict__ trans;   // grid: n_trans x 3
+  const float* __restrict__ gate;    // optional per-pose gate: poses with gate <= 0 are skipped (score untouched)
+  int n_rot;
+};
+
+struct ScoreParams
+{
+  double radius;     // search radius = sigma (double of the float literal)
+  float r2f;         // (float)(radius*radius)
+  float dot_thr;     // smallest float dot with acos((double)dot) - max_angle < 1e-6
+  double inv_two_sigma_sq_den; // 2.0*sigma*sigma
+  int k;
+};
+
+template <bool GRID, bool COUNT>
+__global__ void __launch_bounds__( 128 ) score_kernel( GridView g, const float* __restrict__ obj_pos, const float* __restrict__ obj_nor,
+                                                       int n_obj, PoseSource ps, long long n_poses, int n_split, int chunk,
+                                                       ScoreParams sp, double* __restrict__ partial,
+                                                       unsigned long long* __restrict__ counts )
+{
+  const int lane = threadIdx.x & 31;
+  long long warp = ( blockIdx.x * (long long)blockDim.x + threadIdx.x ) >> 5;
+  if( warp >= n_poses * n_split ) { return; }
+  long long pose = warp / n_split;
+  int split = (int)( warp % n_split );
+  if( ps.gate && !( __ldg( ps.gate + pose ) > 0.0f ) ) { return; }
+
+  float m[16];
+  if( GRID )
+  {
+    long long t = pose / ps.n_rot; int r = (int)( pose % ps.n_rot );
+#pragma unroll
+    for( int i = 0; i < 12; ++i ) { m[i] = __ldg( ps.rots + 16 * (size_t)r + i ); }
+    m[12] = __ldg( ps.trans + 3 * t ); m[13] = __ldg( ps.trans + 3 * t + 1 ); m[14] = __ldg( ps.trans + 3 * t + 2 ); m[15] = 1.0f;
+  }
+  else
+  {
+#pragma unroll
+    for( int i = 0; i < 16; ++i ) { m[i] = __ldg( ps.xforms + 16 * (size_t)pose + i ); }
+  }
+
+  const int i0 = split * chunk, i1 = min( n_obj, i0 + chunk );
+  double sum = 0.0;
+  float my_d2 = 0.f, my_dot = 0.f; bool my_found = false;
+  for( int i = i0; i < i1; ++i )
+  {
+    float px, py, pz, nx, ny, nz;
+    xf_apply( m, __ldg( obj_pos + 3 * (size_t)i ), __ldg( obj_pos + 3 * (size_t)i + 1 ), __ldg( obj_pos + 3 * (size_t)i + 2 ), 1.0f, px, py, pz );
+    xf_apply( m, __ldg( obj_nor + 3 * (size_t)i ), __ldg( obj_nor + 3 * (size_t)i + 1 ), __ldg( obj_nor + 3 * (size_t)i + 2 ), 0.0f, nx, ny, nz );
+    NearestHit h = nearest_compatible<COUNT>( g, px, py, pz, nx, ny, nz, sp.radius, sp.r2f, sp.dot_thr, sp.k, counts );
+    int slot = ( i - i0 ) & 31;
+    if( lane == slot ) { my_found = h.found; my_d2 = h.d2; my_dot = h.dot; }
+    if( slot == 31 || i == i1 - 1 )
+    {
+      // the reference's per-point term (:149-152), 32 points at a time, summed in point order
+      double term = 0.0;
+      if( my_found )
+      {
+        double angle = acos( (double)fmaxf( my_dot, 0.0f ) );
+        double nc = exp( -( angle * angle ) / ( 2.0 * 0.5 * 0.5 ) );
+        double dc = exp( -(double)my_d2 / sp.inv_two_sigma_sq_den );
+        term = 0.05 * nc + ( 1.0 - 0.05 ) * dc;
+      }
+      unsigned mask = __ballot_sync( RS_FULL, my_found );
+      while( mask )
+      {
+        int src = __ffs( mask ) - 1; mask &= mask - 1;
+        sum += __shfl_sync( RS_FULL, term, src );
+      }
+      my_found = false;
+    }
+  }
+  if( lane == 0 ) { partial[pose * n_split + split] = sum; }
+}
+
+__global__ void finalize_kernel( const double* __restrict__ partial, long long n_poses, int n_split, int n_obj,
+                                 const float* __restrict__ gate, float* __restrict__ scores )
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if( p >= n_poses ) { return; }
+  if( gate && !( gate[p] > 0.0f ) ) { return; }
+  double s = 0.0;
+  for( int j = 0; j < n_split; ++j ) { s += partial[p * n_split + j]; }
+  s /= (double)n_obj;  // (:156)
+  scores[p] = (float)s;
+}
+
+// smallest float dot in [0, 1] the reference accepts: acos((double)dot) - max_angle < 1e-6 (:141-142), evaluated
+// with the host libm the reference itself would use; acos is monotone, so the set of accepted dots is [thr, 1]
+float compat_threshold( double max_angle )
+{
+  auto ok = [&]( float d ) { return acos( (double)d ) - max_angle < 0.000001; };
+  if( ok( 0.0f ) ) { return -INFINITY; } // negative dots are clamped to 0 before the test (:139), so everything <= 1 passes
+  if( !ok( 1.0f ) ) { return 2.0f; } // nothing is ever accepted
+  uint32_t lo, hi; float f0 = 0.0f, f1 = 1.0f;
+  memcpy( &lo, &f0, 4 ); memcpy( &hi, &f1, 4 ); // !ok(lo), ok(hi); positive floats order like their bits
+  while( hi - lo > 1 )
+  {
+    uint32_t mid = lo + ( hi - lo ) / 2; float fm; memcpy( &fm, &mid, 4 );
+    if( ok( fm ) ) { hi = mid; } else { lo = mid; }
+  }
+  float out; memcpy( &out, &hi, 4 );
+  return out;
+}
+
+ScoreParams make_params( float radius, int k )
+{
+  ScoreParams sp;
+  double max_angle = 35.0 * 0.005555555556 * 3.1415926535897932384626433832; // msh_deg2rad(35.0), msh_std.h:618,625
+  double sigma = radius;
+  sp.radius = radius;
+  sp.r2f = (float)( sp.radius * sp.radius );
+  sp.dot_thr = compat_threshold( max_angle );
+  sp.inv_two_sigma_sq_den = 2.0 * sigma * sigma;
+  sp.k = k;
+  return sp;
+}
+
+// core launcher: scores (device) [n_poses]; gate may alias scores
+int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const PoseSource& ps, bool grid_mode, long long n_poses,
+                  int k, float radius, float* d_scores, unsigned long long* d_counts )
+{
+  if( n_poses <= 0 ) { return RSGPU_OK; }
+  if( !scene->has_normals ) { return fail( RSGPU_ERR_INVALID, "rsgpu score: the scene grid has no normals (rsgpu_grid_set_normals)" ); }
+  if( obj->n <= 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu score: empty object cloud" ); }
+  if( k <= 0 || !( radius > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu score: max_n_neigh and radius must be positive" ); }
+  cudaStream_t st = rt().stream;
+  ScoreParams sp = make_params( radius, k );
+  // few poses over many points (verification / rescoring): split the point range over several warps
+  int n_split = 1;
+  const long long want_warps = 148ll * 64;
+  if( n_poses < want_warps )
+  {
+    long long s = ( want_warps + n_poses - 1 ) / n_poses;
+    long long max_s = ( obj->n + 63 ) / 64;
+    n_split = (int)( s < max_s ? s : max_s );
+    if( n_split < 1 ) { n_split = 1; }
+  }
+  int chunk = ( ( obj->n + n_split - 1 ) / n_split + 31 ) / 32 * 32;
+  n_split = ( obj->n + chunk - 1 ) / chunk;
+  DevBuf<double> partial;
+  RS_CUDA( partial.alloc( (size_t)n_poses * n_split ) );
+  long long warps = n_poses * n_split;
+  long long blocks = ( warps + 3 ) / 4;
+  if( blocks > 2147483647ll ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu score: too many poses for one launch" ); }
+  GridView g = scene->view();
+  {
+    ProfScope prof( grid_mode ? "score_dense" : "score" );
+    if( d_counts )
+    {
+      if( grid_mode ) { score_kernel<true, true><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, d_counts ); }
+      else { score_kernel<false, true><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, d_counts ); }
+    }
+    else
+    {
+      if( grid_mode ) { score_kernel<true, false><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, nullptr ); }
+      else { score_kernel<false, false><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, nullptr ); }
+    }
+    RS_CHECK_LAUNCH();
+  }
+  finalize_kernel<<<(unsigned)( ( n_poses + 255 ) / 256 ), 256, 0, st>>>( partial.p, n_poses, n_split, obj->n, ps.gate, d_scores );
+  RS_CHECK_LAUNCH();
+  RS_CUDA( cudaStreamSynchronize( st ) ); // partial dies here
+  return RSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- propose
+// per translation: first strict maximum over rotations starting from 0, flagged iff > threshold (:217-243)
+__global__ void select_kernel( const float* __restrict__ scores, long long n_trans, int n_rot, float thr,
+                               int* __restrict__ flag, int* __restrict__ best_r, float* __restrict__ best_s )
+{
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if( t >= n_trans ) { return; }
+  float best = 0.f; int br = -1;
+  for( int r = 0; r < n_rot; ++r )
+  {
+    float s = scores[t * n_rot + r];
+    if( s > best ) { best = s; br = r; }
+  }
+  flag[t] = best > thr ? 1 : 0;
+  best_r[t] = br; best_s[t] = best;
+}
+
+// compact the flagged translations, in translation order, into pose_proposal_t records (16 + 1 floats)
+__global__ void emit_kernel( const int* __restrict__ flag, const int* __restrict__ offs, const int* __restrict__ best_r,
+                             const float* __restrict__ best_s, const float* __restrict__ rots, const float* __restrict__ trans,
+                             long long n_trans, int n_rot, float* __restrict__ xforms, float* __restrict__ scores,
+                             long long* __restrict__ pose_id )
+{
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if( t >= n_trans || !flag[t] ) { return; }
+  int o = offs[t], r = best_r[t];
+  for( int i = 0; i < 12; ++i ) { xforms[16 * (size_t)o + i] = rots[16 * (size_t)r + i]; }
+  xforms[16 * (size_t)o + 12] = trans[3 * t]; xforms[16 * (size_t)o + 13] = trans[3 * t + 1];
+  xforms[16 * (size_t)o + 14] = trans[3 * t + 2]; xforms[16 * (size_t)o + 15] = 1.0f;
+  scores[o] = best_s[t];
+  pose_id[o] = t * n_rot + r;
+}
+
+// verification outcome (:289-292): new score if above the level's threshold, else -1; gate <= 0 untouched
+__global__ void verify_kernel( float* __restrict__ scores, const float* __restrict__ fresh, int n, float thr )
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= n ) { return; }
+  if( !( scores[i] > 0.0f ) ) { return; }
+  scores[i] = fresh[i] > thr ? fresh[i] : -1.0f;
+}
+} // namespace
+
+extern "C" {
+
+int rsgpu_score_poses_dev( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const float* d_xforms, int64_t n_poses,
+                           int32_t k, float radius, float* d_scores )
+{
+  if( !obj || !scene || ( n_poses > 0 && ( !d_xforms || !d_scores ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_poses: NULL argument" ); }
+  RS_TRY( ensure_device() );
+  PoseSource ps; memset( &ps, 0, sizeof( ps ) ); ps.xforms = d_xforms;
+  return score_launch( obj, scene, ps, false, n_poses, k, radius, d_scores, nullptr );
+}
+
+int rsgpu_score_poses( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const float* xforms, int64_t n_poses, int32_t k,
+                       float radius, float* scores )
+{
+  if( !obj || !scene || ( n_poses > 0 && ( !xforms || !scores ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_poses: NULL argument" ); }
+  RS_TRY( ensure_device() );
+  if( n_poses <= 0 ) { return RSGPU_OK; }
+  DevBuf<float> dx, ds;
+  RS_CUDA( dx.alloc( (size_t)n_poses * 16 ) ); RS_CUDA( ds.alloc( (size_t)n_poses ) );
+  RS_CUDA( cudaMemcpyAsync( dx.p, xforms, sizeof( float ) * 16 * (size_t)n_poses, cudaMemcpyHostToDevice, rt().stream ) );
+  RS_TRY( rsgpu_score_poses_dev( obj, scene, dx.p, n_poses, k, radius, ds.p ) );
+  RS_CUDA( cudaMemcpyAsync( scores, ds.p, sizeof( float ) * (size_t)n_poses, cudaMemcpyDeviceToHost, rt().stream ) );
+  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  return RSGPU_OK;
+}
+
+int rsgpu_score_pose_grid_dev( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const float* d_rots, int32_t n_rot,
+                               const float* d_trans, int64_t n_trans, int32_t k, float radius, float* d_scores )
+{
+  if( !obj || !scene || n_rot < 0 || n_trans < 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_pose_grid: bad argument" ); }
+  if( (long long)n_rot * n_trans > 0 && ( !d_rots || !d_trans || !d_scores ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_pose_grid: NULL argument" ); }
+  RS_TRY( ensure_device() );
+  PoseSource ps; memset( &ps, 0, sizeof( ps ) ); ps.rots = d_rots; ps.trans = d_trans; ps.n_rot = n_rot;
+  return score_launch( obj, scene, ps, true, (long long)n_rot * n_trans, k, radius, d_scores, nullptr );
+}
+
+static int upload_pose_grid( const float* rots, int32_t n_rot, const float* trans, int64_t n_trans, DevBuf<float>& dr, DevBuf<float>& dt )
+{
+  RS_CUDA( dr.alloc( (size_t)n_rot * 16 ) ); RS_CUDA( dt.alloc( (size_t)n_trans * 3 ) );
+  if( n_rot ) { RS_CUDA( cudaMemcpyAsync( dr.p, rots, sizeof( float ) * 16 * (size_t)n_rot, cudaMemcpyHostToDevice, rt().stream ) ); }
+  if( n_trans ) { RS_CUDA( cudaMemcpyAsync( dt.p, trans, sizeof( float ) * 3 * (size_t)n_trans, cudaMemcpyHostToDevice, rt().stream ) ); }
+  return RSGPU_OK;
+}
+
+int rsgpu_score_pose_grid( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const float* rots, int32_t n_rot, const float* trans,
+                           int64_t n_trans, int32_t k, float radius, float* scores )
+{
+  if( !obj || !scene || n_rot < 0 || n_trans < 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_pose_grid: bad argument" ); }
+  long long n = (long long)n_rot * n_trans;
+  if( n > 0 && ( !rots || !trans || !scores ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_pose_grid: NULL argument" ); }
+  RS_TRY( ensure_device() );
+  if( n == 0 ) { return RSGPU_OK; }
+  DevBuf<float> dr, dt, ds;
+  RS_TRY( upload_pose_grid( rots, n_rot, trans, n_trans, dr, dt ) );
+  RS_CUDA( ds.alloc( (size_t)n ) );
+  RS_TRY( rsgpu_score_pose_grid_dev( obj, scene, dr.p, n_rot, dt.p, n_trans, k, radius, ds.p ) );
+  RS_CUDA( cudaMemcpyAsync( scores, ds.p, sizeof( float ) * (size_t)n, cudaMemcpyDeviceToHost, rt().stream ) );
+  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  return RSGPU_OK;
+}
+
+int rsgpu_score_pose_grid_count( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const float* rots, int32_t n_rot,
+                                 const float* trans, int64_t n_trans, int32_t k, float radius, int64_t counts[4] )
+{
+  if( !obj || !scene || !counts || n_rot < 0 || n_trans < 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu_score_pose_grid_count: bad argument" ); }
+  long long n = (long long)n_rot * n_trans;
+  RS_TRY( ensure_device() );
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  if( n == 0 ) { return RSGPU_OK; }
+  DevBuf<float> dr, dt, ds; DevBuf<unsigned long long> dc;
+  RS_TRY( upload_pose_grid( rots, n_rot, trans, n_trans, dr, dt ) );
+  RS_CUDA( ds.alloc( (size_t)n ) ); RS_CUDA( dc.alloc( 4 ) );
+  RS_CUDA( cudaMemsetAsync( dc.p, 0, 32, rt().stream ) );
+  PoseSource ps; memset( &ps, 0, sizeof( ps ) ); ps.rots = dr.p; ps.trans = dt.p; ps.n_rot = n_rot;
+  bool prof = rt().profile; rt().profile = false; // the counting pass is not a timed launch
+  int s = score_launch( obj, scene, ps, true, n, k, radius, ds.p, dc.p );
+  rt().profile = prof;
+  RS_TRY( s );
+  unsigned long long h[4];
+  RS_CUDA( cudaMemcpyAsync( h, dc.p, 32, cudaMemcpyDeviceToHost, rt().stream ) );
+  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  for( int i = 0; i < 4; ++i ) { counts[i] = (int64_t)h[i]; }
+  return RSGPU_OK;
+}
+
+void rsgpu_propose_default_opts( rsgpu_propose_opts_t* o )
+{
+  if( !o ) { return; }
+  o->max_n_neigh = 64; o->radius = 0.1f;
+  o->thresholds[0] = 0.25f; o->thresholds[1] = 0.35f; o->thresholds[2] = 0.40f;
+  o->top_k = 0;
+}
+
+int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const rsgpu_cloud_t* o2, const rsgpu_grid_t* scene,
+                         const float* rots, int32_t n_rot, const float* trans, int64_t n_trans, const rsgpu_propose_opts_t* opts_in,
+                         float* out, int64_t* out_pose_id, int64_t out_cap, int64_t* n_out )
+{
+  if( !o4 || !o3 || !o2 || !scene || !n_out || n_rot < 0 || n_trans < 0 || out_cap < 0 || ( out_cap > 0 && !out ) )
+  {
+    return fail( RSGPU_ERR_INVALID, "rsgpu_propose_poses: bad argument" );
+  }
+  RS_TRY( ensure_device() );
+  *n_out = 0;
+  rsgpu_propose_opts_t opts;
+  if( opts_in ) { opts = *opts_in; } else { rsgpu_propose_default_opts( &opts ); }
+  long long n = (long long)n_rot * n_trans;
+  if( n == 0 ) { return RSGPU_OK; }
+  if( n_trans > 2147483647ll ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_propose_poses: more than 2^31 translations" ); }
+  cudaStream_t st = rt().stream;
+  DevBuf<float> dr, dt, ds;
+  RS_TRY( upload_pose_grid( rots, n_rot, trans, n_trans, dr, dt ) );
+  RS_CUDA( ds.alloc( (size_t)n ) );
+  // level 4: dense search
+  RS_TRY( rsgpu_score_pose_grid_dev( o4, scene, dr.p, n_rot, dt.p, n_trans, opts.max_n_neigh, opts.radius, ds.p ) );
+  DevBuf<int> flag, offs, best_r; DevBuf<float> best_s;
+  RS_CUDA( flag.alloc( n_trans ) ); RS_CUDA( offs.alloc( n_trans ) ); RS_CUDA( best_r.alloc( n_trans ) ); RS_CUDA( best_s.alloc( n_trans ) );
+  unsigned tb = (unsigned)( ( n_trans + 255 ) / 256 );
+  select_kernel<<<tb, 256, 0, st>>>( ds.p, n_trans, n_rot, opts.thresholds[0], flag.p, best_r.p, best_s.p );
+  RS_CHECK_LAUNCH();
+  size_t scan_bytes = 0;
+  RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, scan_bytes, flag.p, offs.p, (int)n_trans, st ) );
+  DevBuf<unsigned char> tmp;
+  RS_CUDA( tmp.alloc( scan_bytes ) );
+  RS_CUDA( cub::DeviceScan::ExclusiveSum( tmp.p, scan_bytes, flag.p, offs.p, (int)n_trans, st ) );
+  int last_off = 0, last_flag = 0;
+  RS_CUDA( cudaMemcpyAsync( &last_off, offs.p + ( n_trans - 1 ), 4, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( &last_flag, flag.p + ( n_trans - 1 ), 4, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaStreamSynchronize( st ) );
+  int n_prop = last_off + last_flag;
+  if( n_prop == 0 ) { return RSGPU_OK; }
+  DevBuf<float> px, psc, fresh; DevBuf<long long> pid;
+  RS_CUDA( px.alloc( (size_t)n_prop * 16 ) ); RS_CUDA( psc.alloc( n_prop ) ); RS_CUDA( fresh.alloc( n_prop ) ); RS_CUDA( pid.alloc( n_prop ) );
+  emit_kernel<<<tb, 256, 0, st>>>( flag.p, offs.p, best_r.p, best_s.p, dr.p, dt.p, n_trans, n_rot, px.p, psc.p, pid.p );
+  RS_CHECK_LAUNCH();
+  // levels 3 and 2: verification of the survivors
+  const rsgpu_cloud_t* lv[2] = { o3, o2 };
+  for( int l = 0; l < 2; ++l )
+  {
+    PoseSource ps; memset( &ps, 0, sizeof( ps ) ); ps.xforms = px.p; ps.gate = psc.p;
+    RS_TRY( score_launch( lv[l], scene, ps, false, n_prop, opts.max_n_neigh, opts.radius, fresh.p, nullptr ) );
+    verify_kernel<<<( n_prop + 255 ) / 256, 256, 0, st>>>( psc.p, fresh.p, n_prop, opts.thresholds[1 + l] );
+    RS_CHECK_LAUNCH();
+  }
+  // survivor copy: |score| > 1e-6 (:352) — every entry here is either > threshold or -1, so all survive
+  std::vector<float> hx( (size_t)n_prop * 16 ), hs( n_prop ); std::vector<long long> hid( n_prop );
+  RS_CUDA( cudaMemcpyAsync( hx.data(), px.p, sizeof( float ) * 16 * (size_t)n_prop, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( hs.data(), psc.p, sizeof( float ) * (size_t)n_prop, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( hid.data(), pid.p, sizeof( long long ) * (size_t)n_prop, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaStreamSynchronize( st ) );
+  std::vector<int> order;
+  for( int i = 0; i < n_prop; ++i ) { if( fabsf( hs[i] ) > 0.000001f ) { order.push_back( i ); } }
+  if( opts.top_k > 0 )
+  {
+    std::stable_sort( order.begin(), order.end(), [&]( int a, int b ) { return hs[a] != hs[b] ? hs[a] > hs[b] : hid[a] < hid[b]; } );
+    if( (int)order.size() > opts.top_k ) { order.resize( opts.top_k ); }
+  }
+  int64_t w = 0;
+  for( int i : order )
+  {
+    if( w >= out_cap ) { break; }
+    memcpy( out + RSGPU_POSE_FLOATS * w, hx.data() + 16 * (size_t)i, 64 );
+    out[RSGPU_POSE_FLOATS * w + 16] = hs[i];
+    if( out_pose_id ) { out_pose_id[w] = hid[i]; }
+    ++w;
+  }
+  *n_out = (int64_t)order.size(); // may exceed out_cap: the caller then knows how much room a retry needs
+  return RSGPU_OK;
+}
+
+} // extern "C"

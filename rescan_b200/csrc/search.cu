@@ -1,0 +1,384 @@
+// Batched radius / k-NN search on the GPU hash grid: replaces msh_hash_grid_radius_search
+// (reference lib/msh/msh_hash_grid.h:1090-1259) and msh_hash_grid_knn_search (:1294-1450).
+//
+// One warp per query.  The 32 lanes first resolve the (up to 512, usually 27) cells of the query's window in
+// parallel — one coalesced pair of cell_start loads each instead of the reference's per-cell hash probe —
+// then sweep the cells nearest-first reading 32 consecutive 16-byte records per step (one 512-byte coalesced
+// request).  The k best are kept as a sorted list of 64-bit keys (dist^2 bits << 32 | original index) spread
+// over the warp's registers, so the reference's per-query heap and final sort (:796-824, :579-703) disappear:
+// rows come out ascending and ties are broken by the lower original index, deterministically.
+#include "rsgpu_internal.cuh"
+#include <cmath>
+
+using namespace rs;
+
+namespace
+{
+constexpr unsigned long long KEY_INF = 0xffffffffffffffffull;
+
+// sorted list of 32*EPL keys, element j lives in lane j / EPL, slot j % EPL
+template <int EPL>
+struct WarpList
+{
+  unsigned long long v[EPL];
+  __device__ __forceinline__ void init()
+  {
+#pragma unroll
+    for( int s = 0; s < EPL; ++s ) { v[s] = KEY_INF; }
+  }
+  // insert warp-uniform key x (drops the largest element)
+  __device__ __forceinline__ void insert( unsigned long long x, int lane )
+  {
+    unsigned long long up = __shfl_up_sync( RS_FULL, v[EPL - 1], 1 );
+    if( lane == 0 ) { up = 0ull; } // nothing precedes element 0: "previous <= x" always holds
+#pragma unroll
+    for( int s = EPL - 1; s >= 0; --s )
+    {
+      unsigned long long prev = s > 0 ? v[s - 1] : up;
+      v[s] = ( v[s] <= x ) ? v[s] : ( prev <= x ? x : prev );
+    }
+  }
+  __device__ __forceinline__ unsigned long long get( int j ) const
+  {
+    unsigned long long r = KEY_INF;
+    int src = j / EPL, slot = j % EPL;
+#pragma unroll
+    for( int s = 0; s < EPL; ++s ) { if( s == slot ) { r = v[s]; } }
+    return __shfl_sync( RS_FULL, r, src );
+  }
+};
+
+template <int EPL>
+__device__ __forceinline__ void sweep_cell( const GridView& g, uint32_t cs, uint32_t ce, float px, float py, float pz,
+                                            bool use_radius, float r2f, int k, int lane, WarpList<EPL>& list,
+                                            unsigned long long& thr, uint32_t& seen )
+{
+  for( uint32_t p0 = cs; p0 < ce; p0 += 32 )
+  {
+    uint32_t p = p0 + lane;
+    unsigned long long key = KEY_INF;
+    bool ok = false;
+    if( p < ce )
+    {
+      float4 rec = __ldg( g.recs + p );
+      float d2 = dist2_exact( rec, px, py, pz );
+      ok = !use_radius || d2 < r2f;
+      key = ( (unsigned long long)__float_as_uint( d2 ) << 32 ) | __float_as_uint( rec.w );
+    }
+    unsigned in_range = __ballot_sync( RS_FULL, ok );
+    seen += __popc( in_range );
+    unsigned m = __ballot_sync( RS_FULL, ok && key < thr );
+    while( m )
+    {
+      int src = __ffs( m ) - 1; m &= m - 1;
+      unsigned long long x = __shfl_sync( RS_FULL, key, src );
+      if( x < thr )
+      {
+        list.insert( x, lane );
+        thr = list.get( k - 1 );
+      }
+    }
+  }
+}
+
+template <int EPL>
+__device__ __forceinline__ void write_row( const WarpList<EPL>& list, int lane, uint32_t count, size_t row, int k,
+                                           float* __restrict__ out_d2, int32_t* __restrict__ out_idx )
+{
+#pragma unroll
+  for( int s = 0; s < EPL; ++s )
+  {
+    uint32_t j = lane * EPL + s;
+    if( j < count )
+    {
+      out_d2[row * k + j] = __uint_as_float( (uint32_t)( list.v[s] >> 32 ) );
+      out_idx[row * k + j] = (int32_t)(uint32_t)( list.v[s] & 0xffffffffull );
+    }
+  }
+}
+
+template <int EPL>
+__global__ void __launch_bounds__( 128 ) radius_search_kernel( GridView g, const float* __restrict__ q, size_t nq, double radius,
+                                                               float r2f, int k, float* __restrict__ out_d2,
+                                                               int32_t* __restrict__ out_idx, unsigned long long* __restrict__ out_nn,
+                                                               unsigned long long* __restrict__ total )
+{
+  const int lane = threadIdx.x & 31;
+  size_t warp = ( blockIdx.x * (size_t)blockDim.x + threadIdx.x ) >> 5;
+  size_t n_warps = ( gridDim.x * (size_t)blockDim.x ) >> 5;
+  unsigned long long local_total = 0;
+  for( size_t qi = warp; qi < nq; qi += n_warps )
+  {
+    float px = __ldg( q + 3 * qi ), py = __ldg( q + 3 * qi + 1 ), pz = __ldg( q + 3 * qi + 2 );
+    CellWindow w = make_window( g, px, py, pz, radius );
+    WarpList<EPL> list; list.init();
+    unsigned long long thr = KEY_INF;
+    uint32_t seen = 0;
+    for( int base = 0; base < w.n_cells; base += 32 )
+    {
+      uint32_t s, t; float gap2;
+      window_cell( g, w, base + lane, s, t, gap2 );
+      uint32_t gbits = ( s < t && gap2 < r2f ) ? __float_as_uint( gap2 ) : RS_INF_BITS;
+      while( true )
+      {
+        uint32_t gmin = __reduce_min_sync( RS_FULL, gbits );
+        // nothing left, or the list is full and no remaining cell can beat its last entry (:1232-1236)
+        if( gmin == RS_INF_BITS || ( thr != KEY_INF && gmin >= (uint32_t)( thr >> 32 ) ) ) { break; }
+        int src = __ffs( __ballot_sync( RS_FULL, gbits == gmin ) ) - 1;
+        uint32_t cs = __shfl_sync( RS_FULL, s, src ), ce = __shfl_sync( RS_FULL, t, src );
+        if( lane == src ) { gbits = RS_INF_BITS; }
+        sweep_cell<EPL>( g, cs, ce, px, py, pz, true, r2f, k, lane, list, thr, seen );
+      }
+    }
+    uint32_t count = seen < (uint32_t)k ? seen : (uint32_t)k;
+    write_row<EPL>( list, lane, count, qi, k, out_d2, out_idx );
+    if( lane == 0 && out_nn ) { out_nn[qi] = count; }
+    local_total += count;
+  }
+  if( lane == 0 && local_total ) { atomicAdd( total, local_total ); }
+}
+
+// msh_hash_grid_knn_search: shells of cells around the query's cell are opened layer by layer and the search
+// stops after the layer FOLLOWING the one that first filled the list (:1427-1429); cells pruned inside a
+// layer cannot hold a better point, so the result is the k nearest points of the cube of half-width L + 1
+// cells, L = first layer at which the cube holds >= k points.
+template <int EPL>
+__global__ void __launch_bounds__( 128 ) knn_search_kernel( GridView g, const float* __restrict__ q, size_t nq, int k,
+                                                            float* __restrict__ out_d2, int32_t* __restrict__ out_idx,
+                                                            unsigned long long* __restrict__ out_nn,
+                                                            unsigned long long* __restrict__ total )
+{
+  const int lane = threadIdx.x & 31;
+  size_t warp = ( blockIdx.x * (size_t)blockDim.x + threadIdx.x ) >> 5;
+  size_t n_warps = ( gridDim.x * (size_t)blockDim.x ) >> 5;
+  unsigned long long local_total = 0;
+  const int max_layer = g.W + g.H + g.D;
+  for( size_t qi = warp; qi < nq; qi += n_warps )
+  {
+    float px = __ldg( q + 3 * qi ), py = __ldg( q + 3 * qi + 1 ), pz = __ldg( q + 3 * qi + 2 );
+    long long c0[3];
+    c0[0] = __double2ll_rz( __dmul_rn( (double)__fsub_rn( px, g.mnx ), g.inv_cell ) );
+    c0[1] = __double2ll_rz( __dmul_rn( (double)__fsub_rn( py, g.mny ), g.inv_cell ) );
+    c0[2] = __double2ll_rz( __dmul_rn( (double)__fsub_rn( pz, g.mnz ), g.inv_cell ) );
+    const long long big = 1 << 28;
+    int cx = clamp_ll( c0[0], -big, big ), cy = clamp_ll( c0[1], -big, big ), cz = clamp_ll( c0[2], -big, big );
+    // find L: grow the cube until it holds k points (row ranges are contiguous in the dense table)
+    int L = 0;
+    for( ; L <= max_layer; ++L )
+    {
+      int x0 = max( cx - L, 0 ), x1 = min( cx + L, g.W - 1 ), y0 = max( cy - L, 0 ), y1 = min( cy + L, g.H - 1 ),
+          z0 = max( cz - L, 0 ), z1 = min( cz + L, g.D - 1 );
+      uint32_t cnt = 0;
+      if( x0 <= x1 && y0 <= y1 && z0 <= z1 )
+      {
+        int ny = y1 - y0 + 1, rows = ny * ( z1 - z0 + 1 );
+        for( int r = lane; r < rows; r += 32 )
+        {
+          size_t rowbase = ( (size_t)( z0 + r / ny ) * g.H + ( y0 + r % ny ) ) * g.W;
+          cnt += __ldg( g.cell_start + rowbase + x1 + 1 ) - __ldg( g.cell_start + rowbase + x0 );
+        }
+      }
+      cnt = __reduce_add_sync( RS_FULL, cnt );
+      if( cnt >= (uint32_t)k ) { break; }
+      if( x0 == 0 && y0 == 0 && z0 == 0 && x1 == g.W - 1 && y1 == g.H - 1 && z1 == g.D - 1 ) { break; } // whole grid seen
+    }
+    int R = L + 1; // the cube actually searched
+    WarpList<EPL> list; list.init();
+    unsigned long long thr = KEY_INF;
+    uint32_t seen = 0;
+    int x0 = max( cx - R, 0 ), x1 = min( cx + R, g.W - 1 ), y0 = max( cy - R, 0 ), y1 = min( cy + R, g.H - 1 ),
+        z0 = max( cz - R, 0 ), z1 = min( cz + R, g.D - 1 );
+    if( x0 <= x1 && y0 <= y1 && z0 <= z1 )
+    {
+      int ny = y1 - y0 + 1, rows = ny * ( z1 - z0 + 1 );
+      for( int r = 0; r < rows; ++r )
+      {
+        size_t rowbase = ( (size_t)( z0 + r / ny ) * g.H + ( y0 + r % ny ) ) * g.W;
+        uint32_t cs = __ldg( g.cell_start + rowbase + x0 ), ce = __ldg( g.cell_start + rowbase + x1 + 1 );
+        sweep_cell<EPL>( g, cs, ce, px, py, pz, false, 0.f, k, lane, list, thr, seen );
+      }
+    }
+    uint32_t count = seen < (uint32_t)k ? seen : (uint32_t)k;
+    write_row<EPL>( list, lane, count, qi, k, out_d2, out_idx );
+    if( lane == 0 && out_nn ) { out_nn[qi] = count; }
+    local_total += count;
+  }
+  if( lane == 0 && local_total ) { atomicAdd( total, local_total ); }
+}
+
+// rspf_compute_neighborhood's candidate edges (rs_pointcloud_filters.cpp:693-708): k <= 32 nearest within the
+// radius of every vertex plus the edge weight, one warp per vertex
+__global__ void __launch_bounds__( 128 ) neighborhood_kernel( GridView g, const float* __restrict__ pos, const float* __restrict__ nor, int n,
+                                                              double radius, float r2f, int k, float radius_sq, float dist_exp,
+                                                              float angle_exp, int32_t* __restrict__ nbr, float* __restrict__ wgt )
+{
+  const int lane = threadIdx.x & 31;
+  size_t warp = ( blockIdx.x * (size_t)blockDim.x + threadIdx.x ) >> 5;
+  size_t n_warps = ( gridDim.x * (size_t)blockDim.x ) >> 5;
+  for( size_t qi = warp; qi < (size_t)n; qi += n_warps )
+  {
+    float px = __ldg( pos + 3 * qi ), py = __ldg( pos + 3 * qi + 1 ), pz = __ldg( pos + 3 * qi + 2 );
+    CellWindow w = make_window( g, px, py, pz, radius );
+    WarpList<1> list; list.init();
+    unsigned long long thr = KEY_INF;
+    uint32_t seen = 0;
+    for( int base = 0; base < w.n_cells; base += 32 )
+    {
+      uint32_t s, t; float gap2;
+      window_cell( g, w, base + lane, s, t, gap2 );
+      uint32_t gbits = ( s < t && gap2 < r2f ) ? __float_as_uint( gap2 ) : RS_INF_BITS;
+      while( true )
+      {
+        uint32_t gmin = __reduce_min_sync( RS_FULL, gbits );
+        if( gmin == RS_INF_BITS || ( thr != KEY_INF && gmin >= (uint32_t)( thr >> 32 ) ) ) { break; }
+        int src = __ffs( __ballot_sync( RS_FULL, gbits == gmin ) ) - 1;
+        uint32_t cs = __shfl_sync( RS_FULL, s, src ), ce = __shfl_sync( RS_FULL, t, src );
+        if( lane == src ) { gbits = RS_INF_BITS; }
+        sweep_cell<1>( g, cs, ce, px, py, pz, true, r2f, k, lane, list, thr, seen );
+      }
+    }
+    uint32_t count = seen < (uint32_t)k ? seen : (uint32_t)k;
+    if( lane < k )
+    {
+      int32_t id = -1; float wv = 0.f;
+      if( (uint32_t)lane < count )
+      {
+        float d2 = __uint_as_float( (uint32_t)( list.v[0] >> 32 ) );
+        id = (int32_t)(uint32_t)( list.v[0] & 0xffffffffull );
+        float dot = dot3_exact( __ldg( nor + 3 * qi ), __ldg( nor + 3 * qi + 1 ), __ldg( nor + 3 * qi + 2 ),
+                                __ldg( nor + 3 * (size_t)id ), __ldg( nor + 3 * (size_t)id + 1 ), __ldg( nor + 3 * (size_t)id + 2 ) );
+        dot = dot < 0.0f ? 0.0f : ( dot > 1.0f ? 1.0f : dot ); // msh_clamp (:707)
+        float dist_cost = (float)( 1.0 - pow( (double)d2 / ( 4.0 * (double)radius_sq ), (double)dist_exp ) ); // (:706)
+        float norm_cost = (float)pow( (double)dot, (double)angle_exp ); // float pow overload (:707)
+        wv = __fmul_rn( dist_cost, norm_cost );
+      }
+      nbr[qi * k + lane] = id; wgt[qi * k + lane] = wv;
+    }
+  }
+}
+
+template <int EPL>
+int launch_search( bool knn, const GridView& g, const float* d_q, size_t nq, double radius, float r2f, int k, float* d_d2,
+                   int32_t* d_idx, unsigned long long* d_nn, unsigned long long* d_total )
+{
+  size_t warps = nq;
+  size_t blocks = ( warps + 3 ) / 4;
+  const size_t max_blocks = 148 * 64;
+  if( blocks > max_blocks ) { blocks = max_blocks; }
+  if( knn ) { knn_search_kernel<EPL><<<(unsigned)blocks, 128, 0, rt().stream>>>( g, d_q, nq, k, d_d2, d_idx, d_nn, d_total ); }
+  else { radius_search_kernel<EPL><<<(unsigned)blocks, 128, 0, rt().stream>>>( g, d_q, nq, radius, r2f, k, d_d2, d_idx, d_nn, d_total ); }
+  RS_CHECK_LAUNCH();
+  return RSGPU_OK;
+}
+
+int search_dev( bool knn, const rsgpu_grid_t* grid, const float* d_q, size_t nq, float radius, size_t k, float* d_d2,
+                int32_t* d_idx, unsigned long long* d_nn, size_t* total )
+{
+  if( k == 0 || k > RSGPU_MAX_K )
+  {
+    return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu search: k must be in [1, RSGPU_MAX_K]" );
+  }
+  if( !knn && !( radius > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_grid_radius_search: radius must be > 0" ); }
+  DevBuf<unsigned long long> d_total;
+  RS_CUDA( d_total.alloc( 1 ) );
+  RS_CUDA( cudaMemsetAsync( d_total.p, 0, 8, rt().stream ) );
+  if( nq > 0 && grid->info.n_pts > 0 )
+  {
+    ProfScope prof( "search" );
+    GridView g = grid->view();
+    double r = radius;
+    float r2f = (float)( r * r ); // double product narrowed when handed down (:1111, 828)
+    int kk = (int)k, s;
+    if( kk <= 32 ) { s = launch_search<1>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    else if( kk <= 64 ) { s = launch_search<2>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    else if( kk <= 128 ) { s = launch_search<4>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    else if( kk <= 256 ) { s = launch_search<8>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    else { s = launch_search<16>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    RS_TRY( s );
+  }
+  else if( d_nn && nq > 0 ) { RS_CUDA( cudaMemsetAsync( d_nn, 0, sizeof( unsigned long long ) * nq, rt().stream ) ); }
+  unsigned long long h = 0;
+  RS_CUDA( cudaMemcpyAsync( &h, d_total.p, 8, cudaMemcpyDeviceToHost, rt().stream ) );
+  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  if( total ) { *total = (size_t)h; }
+  return RSGPU_OK;
+}
+
+int search_host( bool knn, const rsgpu_grid_t* grid, rsgpu_search_desc_t* d, size_t* total )
+{
+  if( !grid || !d || !d->query_pts || !d->distances_sq || !d->indices )
+  {
+    return fail( RSGPU_ERR_INVALID, "rsgpu search: NULL grid / descriptor / buffer (the caller allocates every buffer)" );
+  }
+  RS_TRY( ensure_device() );
+  size_t nq = d->n_query_pts, k = d->k;
+  if( k == 0 || k > RSGPU_MAX_K ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu search: k must be in [1, RSGPU_MAX_K]" ); }
+  DevBuf<float> dq, dd; DevBuf<int32_t> di; DevBuf<unsigned long long> dn;
+  RS_CUDA( dq.alloc( nq * 3 ) ); RS_CUDA( dd.alloc( nq * k ) ); RS_CUDA( di.alloc( nq * k ) ); RS_CUDA( dn.alloc( nq ) );
+  cudaStream_t st = rt().stream;
+  if( nq ) { RS_CUDA( cudaMemcpyAsync( dq.p, d->query_pts, sizeof( float ) * 3 * nq, cudaMemcpyHostToDevice, st ) ); }
+  RS_TRY( search_dev( knn, grid, dq.p, nq, d->radius, k, dd.p, di.p, dn.p, total ) );
+  if( nq )
+  {
+    // rows are copied whole; entries past each row's count are unspecified in the reference as well
+    RS_CUDA( cudaMemcpyAsync( d->distances_sq, dd.p, sizeof( float ) * nq * k, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( cudaMemcpyAsync( d->indices, di.p, sizeof( int32_t ) * nq * k, cudaMemcpyDeviceToHost, st ) );
+    if( d->n_neighbors )
+    {
+      static_assert( sizeof( size_t ) == sizeof( unsigned long long ), "size_t must be 64-bit" );
+      RS_CUDA( cudaMemcpyAsync( d->n_neighbors, dn.p, sizeof( size_t ) * nq, cudaMemcpyDeviceToHost, st ) );
+    }
+    RS_CUDA( cudaStreamSynchronize( st ) );
+  }
+  return RSGPU_OK;
+}
+} // namespace
+
+extern "C" {
+
+int rsgpu_grid_radius_search( const rsgpu_grid_t* g, rsgpu_search_desc_t* d, size_t* total ) { return search_host( false, g, d, total ); }
+int rsgpu_grid_knn_search( const rsgpu_grid_t* g, rsgpu_search_desc_t* d, size_t* total ) { return search_host( true, g, d, total ); }
+
+int rsgpu_grid_radius_search_dev( const rsgpu_grid_t* g, rsgpu_search_desc_t* d, size_t* total )
+{
+  if( !g || !d || !d->query_pts || !d->distances_sq || !d->indices ) { return fail( RSGPU_ERR_INVALID, "rsgpu search: NULL argument" ); }
+  RS_TRY( ensure_device() );
+  return search_dev( false, g, d->query_pts, d->n_query_pts, d->radius, d->k, d->distances_sq, d->indices,
+                     (unsigned long long*)d->n_neighbors, total );
+}
+int rsgpu_grid_knn_search_dev( const rsgpu_grid_t* g, rsgpu_search_desc_t* d, size_t* total )
+{
+  if( !g || !d || !d->query_pts || !d->distances_sq || !d->indices ) { return fail( RSGPU_ERR_INVALID, "rsgpu search: NULL argument" ); }
+  RS_TRY( ensure_device() );
+  return search_dev( true, g, d->query_pts, d->n_query_pts, d->radius, d->k, d->distances_sq, d->indices,
+                     (unsigned long long*)d->n_neighbors, total );
+}
+
+int rsgpu_neighborhood( const rsgpu_grid_t* grid, const float* pos, const float* nor, int32_t n, int32_t max_nn, float radius_sq,
+                        float dist_exp, float angle_exp, int32_t* neighbors, float* weights )
+{
+  if( !grid || n < 0 || max_nn <= 0 || ( n > 0 && ( !pos || !nor || !neighbors || !weights ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_neighborhood: bad argument" ); }
+  if( max_nn > 32 ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_neighborhood: max_nn > 32" ); }
+  RS_TRY( ensure_device() );
+  if( n == 0 ) { return RSGPU_OK; }
+  cudaStream_t st = rt().stream;
+  DevBuf<float> dp, dn, dw; DevBuf<int32_t> di;
+  RS_CUDA( dp.alloc( (size_t)n * 3 ) ); RS_CUDA( dn.alloc( (size_t)n * 3 ) ); RS_CUDA( dw.alloc( (size_t)n * max_nn ) ); RS_CUDA( di.alloc( (size_t)n * max_nn ) );
+  RS_CUDA( cudaMemcpyAsync( dp.p, pos, sizeof( float ) * 3 * (size_t)n, cudaMemcpyHostToDevice, st ) );
+  RS_CUDA( cudaMemcpyAsync( dn.p, nor, sizeof( float ) * 3 * (size_t)n, cudaMemcpyHostToDevice, st ) );
+  float radius = (float)sqrt( radius_sq ); // search_opts.radius = sqrt(radius_sq) narrowed to float (:690)
+  double r = radius;
+  float r2f = (float)( r * r );
+  {
+    ProfScope prof( "edges" );
+    size_t blocks = ( (size_t)n + 3 ) / 4; if( blocks > 148 * 64 ) { blocks = 148 * 64; }
+    neighborhood_kernel<<<(unsigned)blocks, 128, 0, st>>>( grid->view(), dp.p, dn.p, n, r, r2f, max_nn, radius_sq, dist_exp, angle_exp, di.p, dw.p );
+    RS_CHECK_LAUNCH();
+  }
+  RS_CUDA( cudaMemcpyAsync( neighbors, di.p, sizeof( int32_t ) * (size_t)n * max_nn, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( weights, dw.p, sizeof( float ) * (size_t)n * max_nn, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaStreamSynchronize( st ) );
+  return RSGPU_OK;
+}
+
+} // extern "C"

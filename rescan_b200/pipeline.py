@@ -1,0 +1,159 @@
+"""The pose_proposal hot path end to end on the GPU, as one "step" (used by bench.py, __graft_entry__.smoke()
+and the pipeline tests).
+
+One step = what reference apps/pose_proposal/main.cpp:118-206 does between loading and saving, minus the host
+stages that stay reference code (NMS, sorting, .rsdb / .bin I/O):
+
+  1. build the scan's level-1 grid (scoring) and level-2 grid (ICP)           rs_pointcloud.h:849-863
+  2. per dynamic object: dense pose search at level 4 + verification at 3, 2   pose_proposal.cpp:325-369
+  3. ICP refinement of the per-object survivors at level 2                    main.cpp:175-197
+  4. rescoring of the refined poses at object level 1 with k = 32             main.cpp:199-201
+
+Multi-GPU: translations are sharded over ranks in contiguous blocks (the per-translation arg-max over rotations
+stays rank-local); the only exchange is one all-gather of the per-object top-k proposals, after which every
+rank refines an interleaved share of the merged list and a second small all-gather returns the refined poses.
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+from . import api, synth
+
+
+@dataclasses.dataclass
+class ObjectModel:
+    uidx: int
+    class_idx: int
+    is_static: bool
+    levels: dict  # lvl -> api.PointCloud
+
+
+@dataclasses.dataclass
+class StepResult:
+    proposals: list          # per dynamic object: float32 [n, 17] (xform + rescored score), descending score
+    pose_ids: list           # per dynamic object: int64 [n] dense pose ids (t * n_rot + r)
+    n_evaluations: int       # mgs_compute_object_alignment_score call-equivalents done by THIS rank
+    n_queries: int           # object points searched by THIS rank
+    h2d_bytes: int
+    d2h_bytes: int
+
+
+def upload_objects(objects, levels=(4, 3, 2, 1)):
+    out = []
+    for o in objects:
+        out.append(ObjectModel(o.uidx, o.class_idx, o.is_static,
+                               {l: api.PointCloud(o.cloud.pos(l), o.cloud.nor(l)) for l in levels}))
+    return out
+
+
+def shard_range(n, rank, world):
+    """contiguous block [lo, hi) of n items for `rank` of `world` (sizes differ by at most one)"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_topk(per_rank_props, per_rank_ids, top_k):
+    """deterministic merge of per-rank proposal lists: descending score, ties by pose id (identical on every rank)"""
+    props = np.concatenate(per_rank_props) if per_rank_props else np.zeros((0, api.POSE_FLOATS), np.float32)
+    ids = np.concatenate(per_rank_ids) if per_rank_ids else np.zeros(0, np.int64)
+    order = np.lexsort((ids, -props[:, 16].astype(np.float64)))
+    if top_k > 0:
+        order = order[:top_k]
+    return props[order], ids[order]
+
+
+def _allgather_var(arr, dist, device):
+    """all-gather of variable-length float32/int64 rows via torch.distributed (NCCL on GPU, gloo on CPU)"""
+    import torch
+    world = dist.get_world_size()
+    n = torch.tensor([arr.shape[0]], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    width = int(np.prod(arr.shape[1:])) if arr.ndim > 1 else 1
+    buf = torch.zeros((cap, width), dtype=torch.from_numpy(arr[:0]).dtype, device=device)
+    if arr.shape[0]:
+        buf[: arr.shape[0]] = torch.from_numpy(np.ascontiguousarray(arr).reshape(arr.shape[0], width)).to(device)
+    outs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return [o[:c].cpu().numpy().reshape((c,) + arr.shape[1:]) for o, c in zip(outs, counts)]
+
+
+def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, icp_max_dist=0.10,
+             icp_max_angle=np.float32(np.deg2rad(60.0)), rank=0, world=1, dist=None, device=None,
+             scan_dev=None, do_icp=True):
+    """scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
+    {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead."""
+    h2d = d2h = 0
+    p1, n1 = scan_lvl1
+    p2, n2 = scan_lvl2
+    if scan_dev is None:
+        g1 = api.HashGrid(p1, 0.05, normals=n1)
+        g2 = api.HashGrid(p2, 0.05, normals=n2) if do_icp else None
+        h2d += p1.nbytes + n1.nbytes + (p2.nbytes + n2.nbytes if do_icp else 0)
+    else:
+        g1 = api.HashGrid(device_ptr=scan_dev["p1"], n_pts=len(p1), radius=0.05)
+        api._check(api.lib().rsgpu_grid_set_normals_dev(g1.h, scan_dev["n1"]))
+        g2 = None
+        if do_icp:
+            g2 = api.HashGrid(device_ptr=scan_dev["p2"], n_pts=len(p2), radius=0.05)
+            api._check(api.lib().rsgpu_grid_set_normals_dev(g2.h, scan_dev["n2"]))
+    n_rot = len(rotations)
+    lo, hi = shard_range(len(translations), rank, world)
+    my_trans = np.ascontiguousarray(translations[lo:hi])
+    h2d += rotations.nbytes + my_trans.nbytes
+    n_eval = n_query = 0
+    out_props, out_ids = [], []
+    for m in models:
+        if m.is_static:  # pose_proposal.cpp:198
+            continue
+        props, ids = api.propose_poses(m.levels[4], m.levels[3], m.levels[2], g1, rotations, my_trans, top_k=top_k)
+        ids = ids + lo * n_rot
+        d2h += props.nbytes + ids.nbytes
+        n_eval += n_rot * len(my_trans)
+        n_query += n_rot * len(my_trans) * len(m.levels[4])
+        if world > 1:
+            gp = _allgather_var(props, dist, device)
+            gi = _allgather_var(ids, dist, device)
+            props, ids = merge_topk(gp, gi, top_k)
+        if do_icp and len(props):
+            good = props[:, 16] > 0
+            mine = np.nonzero(good)[0][rank::world]  # interleaved share of the merged list
+            if len(mine):
+                T, err, it = api.icp_align(m.levels[2], g2, props[mine, :16], icp_max_dist, icp_max_angle)
+                sc = api.compute_object_alignment_scores(m.levels[1], g1, T, 32, 0.10)  # main.cpp:199
+                h2d += 2 * T.nbytes
+                d2h += T.nbytes + err.nbytes + it.nbytes + sc.nbytes
+                n_eval += len(mine)
+                n_query += len(mine) * len(m.levels[1])
+                upd = np.concatenate([T, sc[:, None]], axis=1).astype(np.float32)
+            else:
+                upd = np.zeros((0, api.POSE_FLOATS), np.float32)
+            if world > 1:
+                gu = _allgather_var(upd, dist, device)
+                gm = _allgather_var(mine.astype(np.int64), dist, device)
+                for u, mi in zip(gu, gm):
+                    props[mi] = u
+            else:
+                props[mine] = upd
+            order = np.lexsort((ids, -props[:, 16].astype(np.float64)))  # mgs_sort_poses: descending score
+            props, ids = props[order], ids[order]
+        out_props.append(props)
+        out_ids.append(ids)
+    g1.close()
+    if g2 is not None:
+        g2.close()
+    return StepResult(out_props, out_ids, n_eval, n_query, h2d, d2h)
+
+
+def make_workload(name):
+    """synthetic scene + pose grid of a named config (rescan_b200.synth.CONFIGS)"""
+    cfg = synth.CONFIGS[name]
+    scene = synth.make_scene(**cfg["scene"])
+    from . import posegrid
+    rotations = posegrid.rotation_xforms(cfg["n_rot"])
+    translations = synth.translation_seeds(scene.scan, cfg["n_seeds"])
+    return scene, rotations, translations

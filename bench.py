@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — pose evaluations/s of the GPU pose_proposal hot path (BASELINE.json metric) on synthetic scans.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one scan (rescan_b200.pipeline.run_step): grid builds, dense pose
+search (level 4) + verification (levels 3, 2) for every dynamic object, ICP refinement of the per-object top-k
+and rescoring at level 1.  `value` times it with the scan resident in HBM; `e2e` times the same step through the
+host-buffer C ABI (scan uploaded from pinned host memory and proposals read back every step).  N > 1 is weak
+scaling: every rank gets its own `n_seeds` translation seeds of the same scan; the only exchanges are the
+all-gathers of per-object top-k lists.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pose_evaluations_per_sec"
+UNIT = "pose evaluations/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def workload_config(name, world):
+    from rescan_b200 import synth
+    cfg = synth.CONFIGS[name]
+    sc = cfg["scene"]
+    return {"workload": f"{name}: pose_proposal on one synthetic scene pair", "scan_points_target": sc.get("target_points"),
+            "objects": sc["n_objects"], "static_objects": sc["n_static"], "rotations": cfg["n_rot"],
+            "translation_seeds_per_gpu": cfg["n_seeds"], "translation_seeds_total": cfg["n_seeds"] * world,
+            "top_k": 64, "parallelism": f"pose-sharded x{world}",
+            "l2": "flushed between steps (256 MiB write inside the timed region); working set is L2-resident within a step"}
+
+
+def build_workload(name, world):
+    from rescan_b200 import synth, posegrid
+    cfg = synth.CONFIGS[name]
+    scene = synth.make_scene(**cfg["scene"])
+    rotations = posegrid.rotation_xforms(cfg["n_rot"])
+    translations = synth.translation_seeds(scene.scan, cfg["n_seeds"] * world)
+    return scene, rotations, translations
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_rate(scene, rotations, translations, target_seconds, threads=None, steps=1, warmup=0):
+    """the reference's own mgs_compute_object_alignment_score (oracle/_ref, compiled from /root/reference) — or the
+    oracle port when that library is absent — over a bounded, strided sample of the dense level-4 pose grid, with
+    every host core (OpenMP over poses in the harness).  Returns (evals/s, info dict, per-step seconds)."""
+    from oracle import refbind, orcbind
+    from rescan_b200 import posegrid
+    threads = threads or os.cpu_count() or 1
+    dyn = [o for o in scene.objects if not o.is_static]
+    grid = posegrid.pose_grid(rotations, translations).reshape(-1, 16)
+    use_ref = refbind.available(openmp=True)
+    if use_ref:
+        scan = refbind.RefCloud.from_levels({l: (scene.scan.pos(l), scene.scan.nor(l)) for l in range(5)}, openmp=True)
+        objs = [refbind.RefCloud.from_levels({l: (o.cloud.pos(l), o.cloud.nor(l)) for l in range(5)}, openmp=True) for o in dyn]
+
+        def run(oi, x):
+            return refbind.score_batch(objs[oi], scan, x, query_lvl=4, search_lvl=1, k=64, n_threads=threads)[1]
+    else:
+        og = orcbind.OrcGrid(scene.scan.pos(1), 0.05)
+
+        def run(oi, x):
+            return orcbind.score_poses(dyn[oi].cloud.pos(4), dyn[oi].cloud.nor(4), og, scene.scan.nor(1), x, 64, 0.10, threads)[1]
+    # pilot to size the sample
+    pilot = grid[:: max(1, len(grid) // 64)][:64]
+    t = sum(run(oi, pilot) for oi in range(len(dyn)))
+    rate = len(pilot) * len(dyn) / max(t, 1e-6)
+    per_obj = int(min(len(grid), max(64, rate * target_seconds / len(dyn))))
+    stride = max(1, len(grid) // per_obj)
+    sample = np.ascontiguousarray(grid[::stride][:per_obj])
+    times = []
+    for s in range(warmup + steps):
+        t = sum(run(oi, sample) for oi in range(len(dyn)))
+        if s >= warmup:
+            times.append(t)
+    n_eval = len(sample) * len(dyn)
+    info = {"cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": f"every {stride}th pose of the dense level-4 grid ({len(sample)} poses) x {len(dyn)} dynamic objects per step, "
+                      f"mgs_compute_object_alignment_score with OpenMP over poses"}
+    return n_eval / (sum(times) / len(times)), info, times
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    scene, rotations, translations = build_workload(args.workload, 1)
+    rate, info, times = cpu_reference_rate(scene, rotations, translations, target_seconds=8.0, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, 1),
+            "cpu_baseline": dict(info, value=rate, unit=UNIT),
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rescan_b200 import api, pipeline
+
+    if not torch.cuda.is_available() or api.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    api.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    scene, rotations, translations = build_workload(args.workload, world)
+    models = pipeline.upload_objects(scene.objects)
+    p1, n1 = scene.scan.pos(1), scene.scan.nor(1)
+    p2, n2 = scene.scan.pos(2), scene.scan.nor(2)
+    # HBM-resident copy for `value`, pinned host copy for `e2e`
+    dev = {k: torch.from_numpy(v).to(device) for k, v in dict(p1=p1, n1=n1, p2=p2, n2=n2).items()}
+    scan_dev = {k: v.data_ptr() for k, v in dev.items()}
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in dict(p1=p1, n1=n1, p2=p2, n2=n2).items()}
+    hp = {k: v.numpy() for k, v in pinned.items()}
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+
+    def step(resident):
+        flush.zero_()
+        return pipeline.run_step((hp["p1"], hp["n1"]), (hp["p2"], hp["n2"]), models, rotations, translations, top_k=64, rank=rank,
+                                 world=world, dist=dist if world > 1 else None, device=device, scan_dev=scan_dev if resident else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = [step(resident) for _ in range(k)]
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    # algorithmic bytes of the dominant kernel (dense level-4 scoring), exact census on this rank's shard, untimed
+    lo, hi = pipeline.shard_range(len(translations), rank, world)
+    g1 = api.HashGrid(p1, 0.05, normals=n1)
+    census = [api.score_pose_grid_count(m.levels[4], g1, rotations, translations[lo:hi]) for m in models if not m.is_static]
+    g1.close()
+    dense_bytes = sum(c["bytes"] for c in census)
+    dense_queries = sum(c["queries"] for c in census)
+
+    for _ in range(args.warmup):
+        step(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    api.profile_reset()
+    api.profile_enable(True)
+    l0 = api.launch_count()
+    ms_value, res = timed(True, args.steps)
+    launches = api.launch_count() - l0
+    api.profile_enable(False)
+    dense_ms, dense_launches = api.profile_get("score_dense")
+    prof = {n: api.profile_get(n) for n in ("grid_build", "score_dense", "score", "icp")}
+    for _ in range(1):
+        step(False)
+    ms_e2e, res_e2e = timed(False, args.steps)
+    clk = clocks.stop()
+
+    def total(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    evals = total(sum(r.n_evaluations for r in res))
+    queries = total(sum(r.n_queries for r in res))
+    evals_e2e = total(sum(r.n_evaluations for r in res_e2e))
+    h2d = total(sum(r.h2d_bytes for r in res_e2e)) / args.steps
+    d2h = total(sum(r.d2h_bytes for r in res_e2e)) / args.steps
+    launches_all = total(launches)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        steps_dense_bytes = dense_bytes * args.steps
+        achieved = steps_dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
+        line = {"metric": METRIC, "value": evals / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world),
+                "nn_queries_per_sec": queries / (ms_value * 1e-3),
+                "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches_all),
+                "roofline": {"bound": "hbm", "kernel": "score_kernel<GRID> (dense level-4 pose scoring)", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": dense_bytes / max(len(census), 1),
+                             "launches_timed": dense_launches, "avg_launch_ms": dense_ms / max(dense_launches, 1),
+                             "dense_nn_queries_per_sec": dense_queries * args.steps / (dense_ms * 1e-3) if dense_ms > 0 else 0.0,
+                             "note": "algorithmic bytes = 8B/cell + 16B/point + 12B/normal per query + 68B/pose (SURVEY.md 8d), rank 0 shard; "
+                                     "the working set is L2-resident, so achieved may exceed the HBM peak"},
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                "clocks": clk}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, info, _ = cpu_reference_rate(scene, rotations, translations, target_seconds=15.0)
+            line["cpu_baseline"] = dict(info, value=rate, unit=UNIT)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,18 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* object_lvl4, const rsgpu_cloud_t* 
    estimation steps taken. */
 int rsgpu_icp_align_batch( const rsgpu_cloud_t* object, const rsgpu_grid_t* scan, float* T1, int32_t n_batch,
                            const float* T2, float max_dist, float max_angle, float* errs, int32_t* iters );
+/* several objects against the same scan in ONE launch (one thread block per starting pose), e.g. all the
+   proposals main.cpp:175-204 refines for one scan */
+typedef struct rsgpu_icp_job
+{
+  const rsgpu_cloud_t* object; /* pts1 / nor1 */
+  float* T1;                   /* n_batch x 16, in/out */
+  int32_t n_batch;
+  float* errs;                 /* n_batch */
+  int32_t* iters;              /* n_batch, may be NULL */
+} rsgpu_icp_job_t;
+int rsgpu_icp_align_multi( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* scan, const float* T2,
+                           float max_dist, float max_angle );
 /* same with the iteration cap exposed (the reference hard-codes max_iter = 100, icp.h:443); <= 0 means 100 */
 int rsgpu_icp_align_batch_ex( const rsgpu_cloud_t* object, const rsgpu_grid_t* scan, float* T1, int32_t n_batch,
                               const float* T2, float max_dist, float max_angle, int32_t max_iter, float* errs,

@@ -52,6 +52,10 @@ class SearchDesc(C.Structure):
                 ("k", C.c_size_t), ("sort", C.c_int)]
 
 
+class IcpJob(C.Structure):
+    _fields_ = [("object", C.c_void_p), ("T1", C.c_void_p), ("n_batch", C.c_int32), ("errs", C.c_void_p), ("iters", C.c_void_p)]
+
+
 class ProposeOpts(C.Structure):
     _fields_ = [("max_n_neigh", C.c_int32), ("radius", C.c_float), ("thresholds", C.c_float * 3), ("top_k", C.c_int32)]
 
@@ -94,6 +98,7 @@ SIGNATURES = {
     "rsgpu_propose_poses": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(ProposeOpts), _vp, _vp, _i64,
                                    C.POINTER(_i64)]),
     "rsgpu_icp_align_batch": (_int, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _vp, _vp]),
+    "rsgpu_icp_align_multi": (_int, [C.POINTER(IcpJob), _i32, _vp, _vp, _f32, _f32]),
     "rsgpu_icp_align_batch_ex": (_int, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _vp, _vp]),
     "rsgpu_assign_labels": (_int, [_vp, _vp, _i32, _vp, C.POINTER(_vp), _i32, _i32, _f32, _vp, _vp]),
     "rsgpu_unary_costs": (_int, [_vp, _vp, _i32, _i32, _vp]),
@@ -295,6 +300,21 @@ def icp_align(obj: PointCloud, scan: HashGrid, T1, max_dist, max_angle, T2=None,
     _check(lib().rsgpu_icp_align_batch_ex(obj.h, scan.h, _ptr(T), len(T), _ptr(T2), max_dist, max_angle, max_iter,
                                           _ptr(err), _ptr(it)))
     return T, err, it
+
+
+def icp_align_multi(objects, scan: HashGrid, T1_list, max_dist, max_angle, T2=None):
+    """icp_align for several objects against one scan in a single launch -> list of (T1 [B,16], err [B], iters [B])"""
+    T2 = _f32(T2 if T2 is not None else np.eye(4).reshape(16)).reshape(16)
+    outs = []
+    jobs = (IcpJob * len(objects))()
+    for j, (o, T1) in enumerate(zip(objects, T1_list)):
+        T = _f32(T1).reshape(-1, 16).copy()
+        err = np.zeros(len(T), np.float32)
+        it = np.zeros(len(T), np.int32)
+        outs.append((T, err, it))
+        jobs[j] = IcpJob(o.h.value, T.ctypes.data, len(T), err.ctypes.data, it.ctypes.data)
+    _check(lib().rsgpu_icp_align_multi(jobs, len(objects), scan.h, _ptr(T2), max_dist, max_angle))
+    return outs
 
 
 def assign_labels(scan_pos, scan_nor, poses, object_grids, first, last, radius, labels, min_dists):

@@ -84,6 +84,25 @@ __global__ void relay_kernel( const float* __restrict__ pts, int n, const uint32
   }
 }
 
+// occ27[c] = number of points in the (clipped) 3x3x3 block of cells around c; rows along x are contiguous
+// in the dense table, so a block is 9 range lookups
+__global__ void occ27_kernel( const uint32_t* __restrict__ cell_start, int W, int H, int D, uint32_t* __restrict__ occ )
+{
+  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t n = (size_t)W * H * D;
+  if( c >= n ) { return; }
+  int x = (int)( c % W ); size_t r = c / W; int y = (int)( r % H ); int z = (int)( r / H );
+  int x0 = x > 0 ? x - 1 : 0, x1 = x < W - 1 ? x + 1 : W - 1;
+  uint32_t total = 0;
+  for( int zz = ( z > 0 ? z - 1 : 0 ); zz <= ( z < D - 1 ? z + 1 : D - 1 ); ++zz )
+    for( int yy = ( y > 0 ? y - 1 : 0 ); yy <= ( y < H - 1 ? y + 1 : H - 1 ); ++yy )
+    {
+      size_t rowbase = ( (size_t)zz * H + yy ) * W;
+      total += cell_start[rowbase + x1 + 1] - cell_start[rowbase + x0];
+    }
+  occ[c] = total;
+}
+
 __global__ void relay_normals_kernel( const float* __restrict__ nor, int n, const float4* __restrict__ recs, float4* __restrict__ out )
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,6 +186,8 @@ int build_from_device( const float* d_pts, int32_t n, float radius, rsgpu_grid_t
   if( n <= 0 )
   {
     RS_CUDA( cudaMemsetAsync( g->cell_start.p, 0, sizeof( uint32_t ) * ( n_cells + 1 ), st ) );
+    RS_CUDA( g->occ27.alloc( n_cells ) );
+    RS_CUDA( cudaMemsetAsync( g->occ27.p, 0, sizeof( uint32_t ) * n_cells, st ) );
   }
   else
   {
@@ -192,6 +213,9 @@ int build_from_device( const float* d_pts, int32_t n, float radius, rsgpu_grid_t
     DevBuf<unsigned char> tmp2;
     RS_CUDA( tmp2.alloc( scan_bytes ) );
     RS_CUDA( cub::DeviceScan::InclusiveSum( tmp2.p, scan_bytes, g->cell_start.p, g->cell_start.p, (int64_t)( n_cells + 1 ), st ) );
+    RS_CUDA( g->occ27.alloc( n_cells ) );
+    occ27_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->cell_start.p, (int)dim[0], (int)dim[1], (int)dim[2], g->occ27.p );
+    RS_CHECK_LAUNCH();
     RS_CUDA( cudaStreamSynchronize( st ) ); // temporaries die here
   }
   uint32_t hs[2] = { 0, 0 };

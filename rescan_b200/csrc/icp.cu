@@ -14,15 +14,17 @@
 // are formed in float exactly as the reference forms them and summed in fp64.  Results agree to the
 // tolerance stated in tests (1e-5 m / 1e-5 rad), not bit for bit.
 #include "rsgpu_internal.cuh"
+#include "nearest.cuh"
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 
 using namespace rs;
 
 namespace
 {
-constexpr int ICP_THREADS = 512;
+constexpr int ICP_THREADS = 256;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int ICP_MAX_NV = 32;
 
@@ -179,20 +181,33 @@ __device__ __forceinline__ void ordered_sums( int n, TermFn term_fn, float* tile
   __syncthreads();
 }
 
+// one entry per thread block (= per starting pose): which object it aligns and where its scratch lives
+struct IcpBlock
+{
+  const float* p1;
+  const float* n1;
+  int n;
+  unsigned long long scratch_off;
+};
+
 template <bool EXACT>
-__global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const float* __restrict__ p1, const float* __restrict__ n1, int c1n,
+__global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const IcpBlock* __restrict__ blocks,
                                                              float* __restrict__ T1_io, const float* __restrict__ T2i, float max_dist0,
                                                              float dot_thr, int max_iter, float4* __restrict__ scratch_q,
                                                              uint2* __restrict__ scratch_m, float* __restrict__ errs,
                                                              int* __restrict__ iters )
 {
+  const IcpBlock blk = blocks[blockIdx.x];
+  const float* __restrict__ p1 = blk.p1;
+  const float* __restrict__ n1 = blk.n1;
+  const int c1n = blk.n;
   __shared__ IcpShared sh;
   extern __shared__ float tile[]; // EXACT: ICP_THREADS * TILE_LD floats
   __shared__ float fout[32];
   __shared__ double dout[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float4* cq = scratch_q + (size_t)b * c1n;  // {q, d2}
-  uint2* cm = scratch_m + (size_t)b * c1n;   // {recs position or ~0, dot bits}
+  float4* cq = scratch_q + blk.scratch_off;  // {q, d2}
+  uint2* cm = scratch_m + blk.scratch_off;   // {recs position or ~0, dot bits}
   if( tid < 16 ) { sh.T[tid] = T1_io[16 * (size_t)b + tid]; sh.M[tid] = T2i[tid]; }
   if( tid == 0 ) { sh.max_dist = max_dist0; sh.prev_err = 1e6f; sh.err = 1e6f; sh.stop = 0; sh.steps = 0; }
   __syncthreads();
@@ -204,17 +219,23 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const f
     const double radius = (double)max_dist;
     const float r2f = (float)__dmul_rn( radius, radius );
     // ---- (A) correspondences (icp.h:339-391): one warp per object point
-    for( int i = warp; i < c1n; i += ICP_WARPS )
+    for( int ib = warp * 32; ib < c1n; ib += ICP_WARPS * 32 )
     {
-      float ax, ay, az, bx, by, bz, qx, qy, qz, mx, my, mz;
-      xf_apply( sh.T, __ldg( p1 + 3 * (size_t)i ), __ldg( p1 + 3 * (size_t)i + 1 ), __ldg( p1 + 3 * (size_t)i + 2 ), 1.0f, ax, ay, az );
-      xf_apply( sh.T, __ldg( n1 + 3 * (size_t)i ), __ldg( n1 + 3 * (size_t)i + 1 ), __ldg( n1 + 3 * (size_t)i + 2 ), 0.0f, bx, by, bz );
-      xf_apply( sh.M, ax, ay, az, 1.0f, qx, qy, qz );
-      xf_apply( sh.M, bx, by, bz, 0.0f, mx, my, mz );
-      NearestHit h = nearest_compatible<false>( g, qx, qy, qz, mx, my, mz, radius, r2f, dot_thr, 16, nullptr );
-      if( lane == 0 )
+      const int i = ib + lane;
+      const bool valid = i < c1n;
+      LaneQuery q;
+      if( valid )
       {
-        cq[i] = make_float4( qx, qy, qz, h.d2 );
+        float ax, ay, az, bx, by, bz;
+        xf_apply( sh.T, __ldg( p1 + 3 * (size_t)i ), __ldg( p1 + 3 * (size_t)i + 1 ), __ldg( p1 + 3 * (size_t)i + 2 ), 1.0f, ax, ay, az );
+        xf_apply( sh.T, __ldg( n1 + 3 * (size_t)i ), __ldg( n1 + 3 * (size_t)i + 1 ), __ldg( n1 + 3 * (size_t)i + 2 ), 0.0f, bx, by, bz );
+        xf_apply( sh.M, ax, ay, az, 1.0f, q.px, q.py, q.pz );
+        xf_apply( sh.M, bx, by, bz, 0.0f, q.nx, q.ny, q.nz );
+      }
+      NearestHit h = nearest_compatible_batch<false>( g, q, valid, radius, r2f, dot_thr, 16, nullptr );
+      if( valid )
+      {
+        cq[i] = make_float4( q.px, q.py, q.pz, h.d2 );
         float dot = h.dot > 0.0f ? h.dot : 0.0f;
         cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
       }
@@ -472,32 +493,49 @@ float compat_threshold_acosf( float max_angle )
 }
 } // namespace rs
 
-extern "C" int rsgpu_icp_align_batch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scan, float* T1, int32_t n_batch, const float* T2,
-                                      float max_dist, float max_angle, float* errs, int32_t* iters )
+namespace
 {
-  return rsgpu_icp_align_batch_ex( obj, scan, T1, n_batch, T2, max_dist, max_angle, 100, errs, iters );
-}
-
-extern "C" int rsgpu_icp_align_batch_ex( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scan, float* T1, int32_t n_batch, const float* T2,
-                                         float max_dist, float max_angle, int32_t max_iter, float* errs, int32_t* iters )
+int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* scan, const float* T2, float max_dist, float max_angle,
+             int32_t max_iter )
 {
+  if( n_jobs < 0 || ( n_jobs > 0 && !jobs ) || !scan ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align: bad argument" ); }
+  RS_TRY( ensure_device() );
+  size_t total = 0, scratch = 0;
+  for( int j = 0; j < n_jobs; ++j )
+  {
+    const rsgpu_icp_job_t& J = jobs[j];
+    if( !J.object || J.n_batch < 0 || ( J.n_batch > 0 && ( !J.T1 || !J.errs ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align: bad job" ); }
+    total += (size_t)J.n_batch; scratch += (size_t)J.n_batch * (size_t)( J.object->n > 0 ? J.object->n : 1 );
+  }
+  if( total == 0 ) { return RSGPU_OK; }
+  if( total > 2147483647u ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_icp_align: too many poses" ); }
+  if( !scan->has_normals ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align: the scan grid has no normals" ); }
+  if( !( max_dist > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align: max_dist must be > 0" ); }
   if( max_iter <= 0 ) { max_iter = 100; }
   // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
   const char* mode = getenv( "RSGPU_ICP_SUMS" );
   const bool exact = !( mode && strcmp( mode, "fp64" ) == 0 );
-  if( !obj || !scan || n_batch < 0 || ( n_batch > 0 && ( !T1 || !errs ) ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align_batch: bad argument" ); }
-  RS_TRY( ensure_device() );
-  if( n_batch == 0 ) { return RSGPU_OK; }
-  if( !scan->has_normals ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align_batch: the scan grid has no normals" ); }
-  if( !( max_dist > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align_batch: max_dist must be > 0" ); }
   cudaStream_t st = rt().stream;
   float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
   mat4_inverse_ref( T2 ? T2 : ident, T2i );
-  const int n = obj->n;
-  DevBuf<float> dT, dT2i, derr; DevBuf<int> dit; DevBuf<float4> sq; DevBuf<uint2> sm;
-  RS_CUDA( dT.alloc( (size_t)n_batch * 16 ) ); RS_CUDA( dT2i.alloc( 16 ) ); RS_CUDA( derr.alloc( n_batch ) ); RS_CUDA( dit.alloc( n_batch ) );
-  RS_CUDA( sq.alloc( (size_t)n_batch * ( n > 0 ? n : 1 ) ) ); RS_CUDA( sm.alloc( (size_t)n_batch * ( n > 0 ? n : 1 ) ) );
-  RS_CUDA( cudaMemcpyAsync( dT.p, T1, sizeof( float ) * 16 * (size_t)n_batch, cudaMemcpyHostToDevice, st ) );
+  std::vector<IcpBlock> hb( total );
+  std::vector<float> hT( total * 16 );
+  size_t bi = 0, off = 0;
+  for( int j = 0; j < n_jobs; ++j )
+  {
+    const rsgpu_icp_job_t& J = jobs[j];
+    for( int b = 0; b < J.n_batch; ++b, ++bi )
+    {
+      hb[bi].p1 = J.object->pos.p; hb[bi].n1 = J.object->nor.p; hb[bi].n = J.object->n; hb[bi].scratch_off = off;
+      memcpy( &hT[bi * 16], J.T1 + 16 * (size_t)b, 64 );
+      off += (size_t)( J.object->n > 0 ? J.object->n : 1 );
+    }
+  }
+  DevBuf<IcpBlock> dB; DevBuf<float> dT, dT2i, derr; DevBuf<int> dit; DevBuf<float4> sq; DevBuf<uint2> sm;
+  RS_CUDA( dB.alloc( total ) ); RS_CUDA( dT.alloc( total * 16 ) ); RS_CUDA( dT2i.alloc( 16 ) ); RS_CUDA( derr.alloc( total ) ); RS_CUDA( dit.alloc( total ) );
+  RS_CUDA( sq.alloc( scratch ) ); RS_CUDA( sm.alloc( scratch ) );
+  RS_CUDA( cudaMemcpyAsync( dB.p, hb.data(), sizeof( IcpBlock ) * total, cudaMemcpyHostToDevice, st ) );
+  RS_CUDA( cudaMemcpyAsync( dT.p, hT.data(), sizeof( float ) * 16 * total, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemcpyAsync( dT2i.p, T2i, 64, cudaMemcpyHostToDevice, st ) );
   {
     ProfScope prof( "icp" );
@@ -505,19 +543,52 @@ extern "C" int rsgpu_icp_align_batch_ex( const rsgpu_cloud_t* obj, const rsgpu_g
     if( exact )
     {
       RS_CUDA( cudaFuncSetAttribute( icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
-      icp_kernel<true><<<n_batch, ICP_THREADS, tile_bytes, st>>>( scan->view(), obj->pos.p, obj->nor.p, n, dT.p, dT2i.p, max_dist,
-                                                                   compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
+      icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist,
+                                                                          compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
     }
     else
     {
-      icp_kernel<false><<<n_batch, ICP_THREADS, 0, st>>>( scan->view(), obj->pos.p, obj->nor.p, n, dT.p, dT2i.p, max_dist,
-                                                           compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
+      icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist,
+                                                                  compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
     }
     RS_CHECK_LAUNCH();
   }
-  RS_CUDA( cudaMemcpyAsync( T1, dT.p, sizeof( float ) * 16 * (size_t)n_batch, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaMemcpyAsync( errs, derr.p, sizeof( float ) * (size_t)n_batch, cudaMemcpyDeviceToHost, st ) );
-  if( iters ) { RS_CUDA( cudaMemcpyAsync( iters, dit.p, sizeof( int32_t ) * (size_t)n_batch, cudaMemcpyDeviceToHost, st ) ); }
+  std::vector<float> herr( total ); std::vector<int> hit( total );
+  RS_CUDA( cudaMemcpyAsync( hT.data(), dT.p, sizeof( float ) * 16 * total, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( herr.data(), derr.p, sizeof( float ) * total, cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaMemcpyAsync( hit.data(), dit.p, sizeof( int ) * total, cudaMemcpyDeviceToHost, st ) );
   RS_CUDA( cudaStreamSynchronize( st ) );
+  bi = 0;
+  for( int j = 0; j < n_jobs; ++j )
+  {
+    const rsgpu_icp_job_t& J = jobs[j];
+    for( int b = 0; b < J.n_batch; ++b, ++bi )
+    {
+      memcpy( J.T1 + 16 * (size_t)b, &hT[bi * 16], 64 );
+      J.errs[b] = herr[bi];
+      if( J.iters ) { J.iters[b] = hit[bi]; }
+    }
+  }
   return RSGPU_OK;
+}
+} // namespace
+
+extern "C" int rsgpu_icp_align_multi( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* scan, const float* T2,
+                                      float max_dist, float max_angle )
+{
+  return icp_run( jobs, n_jobs, scan, T2, max_dist, max_angle, 100 );
+}
+
+extern "C" int rsgpu_icp_align_batch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scan, float* T1, int32_t n_batch, const float* T2,
+                                      float max_dist, float max_angle, float* errs, int32_t* iters )
+{
+  rsgpu_icp_job_t job = { obj, T1, n_batch, errs, iters };
+  return icp_run( &job, 1, scan, T2, max_dist, max_angle, 100 );
+}
+
+extern "C" int rsgpu_icp_align_batch_ex( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scan, float* T1, int32_t n_batch, const float* T2,
+                                         float max_dist, float max_angle, int32_t max_iter, float* errs, int32_t* iters )
+{
+  rsgpu_icp_job_t job = { obj, T1, n_batch, errs, iters };
+  return icp_run( &job, 1, scan, T2, max_dist, max_angle, max_iter );
 }

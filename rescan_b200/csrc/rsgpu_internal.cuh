@@ -28,7 +28,8 @@ int cuda_fail( cudaError_t e, const char* what, const char* file, int line );
 int ensure_device();
 void count_launch(); // one of OUR kernels was launched (library kernels such as CUB are not counted)
 
-// RAII device buffer
+// RAII device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are enqueued on the
+// library stream, so per-call temporaries cost no device synchronisation (cudaFree would)
 template <typename T>
 struct DevBuf
 {
@@ -40,14 +41,14 @@ struct DevBuf
   ~DevBuf() { release(); }
   void release()
   {
-    if( p ) { cudaFree( p ); }
+    if( p ) { cudaFreeAsync( p, rt().stream ); }
     p = nullptr; n = 0;
   }
   cudaError_t alloc( size_t count )
   {
     release();
     n = count;
-    return cudaMalloc( (void**)&p, sizeof( T ) * ( count ? count : 1 ) );
+    return cudaMallocAsync( (void**)&p, sizeof( T ) * ( count ? count : 1 ), rt().stream );
   }
 };
 
@@ -80,6 +81,7 @@ struct GridView
   const float4* __restrict__ recs;
   const float4* __restrict__ nrm;
   const uint32_t* __restrict__ cell_start;
+  const uint32_t* __restrict__ occ27; // points in the 3x3x3 block of cells centred on each cell (0 = a query there sees nothing)
   float mnx, mny, mnz;
   int W, H, D;
   double cell, inv_cell;
@@ -91,12 +93,13 @@ struct rsgpu_grid
   rs::DevBuf<float4> recs;
   rs::DevBuf<float4> nrm;
   rs::DevBuf<uint32_t> cell_start;
+  rs::DevBuf<uint32_t> occ27;
   bool has_normals = false;
   rsgpu_grid_info_t info;
   GridView view() const
   {
     GridView v;
-    v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p;
+    v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p; v.occ27 = occ27.p;
     v.mnx = info.min_pt[0]; v.mny = info.min_pt[1]; v.mnz = info.min_pt[2];
     v.W = (int)info.width; v.H = (int)info.height; v.D = (int)info.depth;
     v.cell = info.cell_size; v.inv_cell = info.inv_cell_size; v.n_pts = (int)info.n_pts;
@@ -199,103 +202,4 @@ __device__ __forceinline__ void window_cell( const GridView& g, const CellWindow
   gap2 = __fadd_rn( __fadd_rn( __fmul_rn( gz, gz ), __fmul_rn( gy, gy ) ), __fmul_rn( gx, gx ) );
 }
 
-// ---------------------------------------------------------------------------------------------- nearest compatible
-// What both mgs_compute_object_alignment_score (pose_proposal.cpp:124-148) and icp_find_corrs
-// (icp.h:349-380) ask of the grid, without materialising the k-list: the nearest point within `radius`
-// whose normal is compatible (dot in [dot_thr, 1]), accepted only when fewer than k points are strictly
-// closer (= it would have been inside the reference's k-nearest list).  Warp-cooperative: all 32 lanes
-// call it with the same arguments.  Returns found; d2 / dot / pos (index into recs) of the accepted point.
-struct NearestHit
-{
-  float d2, dot;
-  uint32_t pos;
-  bool found;
-};
-
-template <bool COUNT>
-__device__ __forceinline__ NearestHit nearest_compatible( const GridView& g, float px, float py, float pz,
-                                                          float nx, float ny, float nz, double radius, float r2f,
-                                                          float dot_thr, int k, unsigned long long* counts )
-{
-  const int lane = threadIdx.x & 31;
-  NearestHit hit; hit.found = false; hit.d2 = 0.f; hit.dot = 0.f; hit.pos = 0;
-  CellWindow w = make_window( g, px, py, pz, radius );
-  if( w.n_cells == 0 ) { return hit; }
-  const uint32_t r2bits = __float_as_uint( r2f );
-
-  // ---- phase 1: nearest compatible point, cells visited nearest-first and pruned by the running best
-  uint32_t best = r2bits;          // lane-local best d2 (as ordered bits; d2 >= 0)
-  uint32_t best_pos = 0xffffffffu; float best_dot = 0.f;
-  uint32_t dc = r2bits;            // warp-uniform bound: nothing at or beyond it can win
-  unsigned long long nB = 0, nC = 0, nHits = 0;
-  for( int base = 0; base < w.n_cells; base += 32 )
-  {
-    uint32_t s, t; float gap2;
-    window_cell( g, w, base + lane, s, t, gap2 );
-    if( COUNT ) { nB += __popc( __ballot_sync( RS_FULL, s < t ) ); nC += __reduce_add_sync( RS_FULL, t - s ); }
-    uint32_t gbits = ( s < t ) ? __float_as_uint( gap2 ) : RS_INF_BITS;
-    while( true )
-    {
-      uint32_t gmin = __reduce_min_sync( RS_FULL, gbits );
-      if( !COUNT && gmin >= dc ) { break; }
-      if( COUNT && gmin == RS_INF_BITS ) { break; }
-      int src = __ffs( __ballot_sync( RS_FULL, gbits == gmin ) ) - 1;
-      uint32_t cs = __shfl_sync( RS_FULL, s, src ), ce = __shfl_sync( RS_FULL, t, src );
-      if( lane == src ) { gbits = RS_INF_BITS; }
-      for( uint32_t p = cs + lane; p < ce; p += 32 )
-      {
-        float4 rec = __ldg( g.recs + p );
-        float d2 = dist2_exact( rec, px, py, pz );
-        uint32_t db = __float_as_uint( d2 );
-        if( COUNT && d2 < r2f ) { nHits++; }
-        if( d2 < r2f && db < best && db < dc )
-        {
-          float4 m = __ldg( g.nrm + p );
-          float dot = dot3_exact( m.x, m.y, m.z, nx, ny, nz );
-          if( dot >= dot_thr && dot <= 1.0f ) { best = db; best_pos = p; best_dot = dot; }
-        }
-      }
-      dc = __reduce_min_sync( RS_FULL, best );
-    }
-  }
-  if( COUNT ) { nHits = __reduce_add_sync( RS_FULL, (unsigned)nHits ); }
-  bool any = dc < r2bits;
-  uint32_t cnt = 0;
-  if( any )
-  {
-    // winner: smallest recs position among the lanes holding dc (deterministic tie-break)
-    uint32_t wpos = __reduce_min_sync( RS_FULL, best == dc ? best_pos : 0xffffffffu );
-    int src = __ffs( __ballot_sync( RS_FULL, best == dc && best_pos == wpos ) ) - 1;
-    hit.d2 = __uint_as_float( dc ); hit.pos = wpos; hit.dot = __shfl_sync( RS_FULL, best_dot, src );
-    // ---- phase 2: rank of the winner = number of points strictly closer; k or more => it is not in the k-list
-    const float dcf = hit.d2;
-    for( int base = 0; base < w.n_cells && cnt < (uint32_t)k; base += 32 )
-    {
-      uint32_t s, t; float gap2;
-      window_cell( g, w, base + lane, s, t, gap2 );
-      unsigned todo = __ballot_sync( RS_FULL, s < t && gap2 < dcf );
-      while( todo && cnt < (uint32_t)k )
-      {
-        int src2 = __ffs( todo ) - 1; todo &= todo - 1;
-        uint32_t cs = __shfl_sync( RS_FULL, s, src2 ), ce = __shfl_sync( RS_FULL, t, src2 );
-        for( uint32_t p0 = cs; p0 < ce && cnt < (uint32_t)k; p0 += 32 )
-        {
-          uint32_t p = p0 + lane;
-          bool closer = false;
-          if( p < ce ) { float4 rec = __ldg( g.recs + p ); closer = dist2_exact( rec, px, py, pz ) < dcf; }
-          cnt += __popc( __ballot_sync( RS_FULL, closer ) );
-        }
-      }
-    }
-    hit.found = cnt < (uint32_t)k;
-  }
-  if( COUNT && lane == 0 && counts )
-  {
-    // normals the reference fetches: up to and including the accepted neighbour, else the whole k-list
-    unsigned long long kk = (unsigned long long)k;
-    unsigned long long T = hit.found ? (unsigned long long)cnt + 1 : ( nHits < kk ? nHits : kk );
-    atomicAdd( counts + 0, 1ull ); atomicAdd( counts + 1, nB ); atomicAdd( counts + 2, nC ); atomicAdd( counts + 3, T );
-  }
-  return hit;
-}
 #endif // __CUDACC__

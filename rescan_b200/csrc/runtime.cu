@@ -43,6 +43,18 @@ int cuda_fail( cudaError_t e, const char* what, const char* file, int line )
   return fail( code, buf );
 }
 
+// keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
+static void configure_pool( int device )
+{
+  cudaMemPool_t pool;
+  if( cudaDeviceGetDefaultMemPool( &pool, device ) == cudaSuccess )
+  {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &keep );
+  }
+  cudaGetLastError();
+}
+
 int ensure_device()
 {
   static int state = 0; // 0 unknown, 1 ok, -1 none
@@ -55,6 +67,7 @@ int ensure_device()
     return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" );
   }
   RS_CUDA( cudaSetDevice( rt().device ) );
+  configure_pool( rt().device );
   state = 1;
   return RSGPU_OK;
 }
@@ -109,6 +122,7 @@ int rsgpu_set_device( int device )
   if( n <= 0 ) { return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" ); }
   if( device < 0 || device >= n ) { return fail( RSGPU_ERR_INVALID, "rsgpu_set_device: device index out of range" ); }
   RS_CUDA( cudaSetDevice( device ) );
+  configure_pool( device );
   return RSGPU_OK;
 }
 

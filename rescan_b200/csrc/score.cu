@@ -10,6 +10,7 @@
 // fp64 in the reference's point order, so no k x N neighbour lists, no per-query sort and no scratch
 // storage exist on the GPU.  The fp64 exp/acos of 32 consecutive points are evaluated lane-parallel.
 #include "rsgpu_internal.cuh"
+#include "nearest.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -68,33 +69,33 @@ __global__ void __launch_bounds__( 128 ) score_kernel( GridView g, const float* 
 
   const int i0 = split * chunk, i1 = min( n_obj, i0 + chunk );
   double sum = 0.0;
-  float my_d2 = 0.f, my_dot = 0.f; bool my_found = false;
-  for( int i = i0; i < i1; ++i )
+  for( int ib = i0; ib < i1; ib += 32 )
   {
-    float px, py, pz, nx, ny, nz;
-    xf_apply( m, __ldg( obj_pos + 3 * (size_t)i ), __ldg( obj_pos + 3 * (size_t)i + 1 ), __ldg( obj_pos + 3 * (size_t)i + 2 ), 1.0f, px, py, pz );
-    xf_apply( m, __ldg( obj_nor + 3 * (size_t)i ), __ldg( obj_nor + 3 * (size_t)i + 1 ), __ldg( obj_nor + 3 * (size_t)i + 2 ), 0.0f, nx, ny, nz );
-    NearestHit h = nearest_compatible<COUNT>( g, px, py, pz, nx, ny, nz, sp.radius, sp.r2f, sp.dot_thr, sp.k, counts );
-    int slot = ( i - i0 ) & 31;
-    if( lane == slot ) { my_found = h.found; my_d2 = h.d2; my_dot = h.dot; }
-    if( slot == 31 || i == i1 - 1 )
+    // 32 object points per batch, one per lane: transform in registers (pose_proposal.cpp:106-112) ...
+    const int i = ib + lane;
+    const bool valid = i < i1;
+    LaneQuery q;
+    if( valid )
     {
-      // the reference's per-point term (:149-152), 32 points at a time, summed in point order
-      double term = 0.0;
-      if( my_found )
-      {
-        double angle = acos( (double)fmaxf( my_dot, 0.0f ) );
-        double nc = exp( -( angle * angle ) / ( 2.0 * 0.5 * 0.5 ) );
-        double dc = exp( -(double)my_d2 / sp.inv_two_sigma_sq_den );
-        term = 0.05 * nc + ( 1.0 - 0.05 ) * dc;
-      }
-      unsigned mask = __ballot_sync( RS_FULL, my_found );
-      while( mask )
-      {
-        int src = __ffs( mask ) - 1; mask &= mask - 1;
-        sum += __shfl_sync( RS_FULL, term, src );
-      }
-      my_found = false;
+      xf_apply( m, __ldg( obj_pos + 3 * (size_t)i ), __ldg( obj_pos + 3 * (size_t)i + 1 ), __ldg( obj_pos + 3 * (size_t)i + 2 ), 1.0f, q.px, q.py, q.pz );
+      xf_apply( m, __ldg( obj_nor + 3 * (size_t)i ), __ldg( obj_nor + 3 * (size_t)i + 1 ), __ldg( obj_nor + 3 * (size_t)i + 2 ), 0.0f, q.nx, q.ny, q.nz );
+    }
+    // ... search (:115-148) ...
+    NearestHit h = nearest_compatible_batch<COUNT>( g, q, valid, sp.radius, sp.r2f, sp.dot_thr, sp.k, counts );
+    // ... and the reference's per-point term (:149-152), lane-parallel in fp64, summed in point order
+    double term = 0.0;
+    if( h.found )
+    {
+      double angle = acos( (double)fmaxf( h.dot, 0.0f ) );
+      double nc = exp( -( angle * angle ) / ( 2.0 * 0.5 * 0.5 ) );
+      double dc = exp( -(double)h.d2 / sp.inv_two_sigma_sq_den );
+      term = 0.05 * nc + ( 1.0 - 0.05 ) * dc;
+    }
+    unsigned mask = __ballot_sync( RS_FULL, h.found );
+    while( mask )
+    {
+      int src = __ffs( mask ) - 1; mask &= mask - 1;
+      sum += __shfl_sync( RS_FULL, term, src );
     }
   }
   if( lane == 0 ) { partial[pose * n_split + split] = sum; }

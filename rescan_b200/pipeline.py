@@ -106,10 +106,10 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     my_trans = np.ascontiguousarray(translations[lo:hi])
     h2d += rotations.nbytes + my_trans.nbytes
     n_eval = n_query = 0
+    dyn = [m for m in models if not m.is_static]  # pose_proposal.cpp:198
     out_props, out_ids = [], []
-    for m in models:
-        if m.is_static:  # pose_proposal.cpp:198
-            continue
+    # ---- dense search + verification per object (+ all-gather of the per-object top-k)
+    for m in dyn:
         props, ids = api.propose_poses(m.levels[4], m.levels[3], m.levels[2], g1, rotations, my_trans, top_k=top_k)
         ids = ids + lo * n_rot
         d2h += props.nbytes + ids.nbytes
@@ -119,11 +119,18 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
             gp = _allgather_var(props, dist, device)
             gi = _allgather_var(ids, dist, device)
             props, ids = merge_topk(gp, gi, top_k)
-        if do_icp and len(props):
-            good = props[:, 16] > 0
-            mine = np.nonzero(good)[0][rank::world]  # interleaved share of the merged list
+        out_props.append(props)
+        out_ids.append(ids)
+    # ---- ICP refinement of every surviving proposal of every object in ONE launch, then rescoring
+    if do_icp:
+        shares = [np.nonzero(p[:, 16] > 0)[0][rank::world] if len(p) else np.zeros(0, np.int64) for p in out_props]
+        jobs = [(m, p[s, :16]) for m, p, s in zip(dyn, out_props, shares) if len(s)]
+        refined = api.icp_align_multi([m.levels[2] for m, _ in jobs], g2, [t for _, t in jobs], icp_max_dist, icp_max_angle) if jobs else []
+        ri = 0
+        for k, (m, props, ids, mine) in enumerate(zip(dyn, out_props, out_ids, shares)):
             if len(mine):
-                T, err, it = api.icp_align(m.levels[2], g2, props[mine, :16], icp_max_dist, icp_max_angle)
+                T, err, it = refined[ri]
+                ri += 1
                 sc = api.compute_object_alignment_scores(m.levels[1], g1, T, 32, 0.10)  # main.cpp:199
                 h2d += 2 * T.nbytes
                 d2h += T.nbytes + err.nbytes + it.nbytes + sc.nbytes
@@ -137,12 +144,10 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
                 gm = _allgather_var(mine.astype(np.int64), dist, device)
                 for u, mi in zip(gu, gm):
                     props[mi] = u
-            else:
+            elif len(mine):
                 props[mine] = upd
             order = np.lexsort((ids, -props[:, 16].astype(np.float64)))  # mgs_sort_poses: descending score
-            props, ids = props[order], ids[order]
-        out_props.append(props)
-        out_ids.append(ids)
+            out_props[k], out_ids[k] = props[order], ids[order]
     g1.close()
     if g2 is not None:
         g2.close()

@@ -111,6 +111,37 @@ __global__ void relay_normals_kernel( const float* __restrict__ nor, int n, cons
   out[i] = make_float4( nor[3 * (size_t)src], nor[3 * (size_t)src + 1], nor[3 * (size_t)src + 2], 0.f );
 }
 
+// per-cell normal cone (see ConeCull in nearest.cuh): unit mean normal and the cosine of the widest angle to it,
+// shrunk by a safety margin; flags[0] is raised when some normal is not unit length to 1e-4
+__global__ void cone_kernel( const float4* __restrict__ nrm, const uint32_t* __restrict__ cell_start, size_t n_cells,
+                             float4* __restrict__ cone, uint32_t* __restrict__ flags )
+{
+  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if( c >= n_cells ) { return; }
+  uint32_t s = cell_start[c], t = cell_start[c + 1];
+  float4 out = make_float4( 0.f, 0.f, 0.f, -1.f );
+  if( s < t )
+  {
+    float sx = 0.f, sy = 0.f, sz = 0.f; bool unit = true;
+    for( uint32_t p = s; p < t; ++p )
+    {
+      float4 m = nrm[p];
+      sx += m.x; sy += m.y; sz += m.z;
+      float l2 = m.x * m.x + m.y * m.y + m.z * m.z;
+      if( !( fabsf( l2 - 1.0f ) < 2e-4f ) ) { unit = false; }
+    }
+    if( !unit ) { atomicOr( flags, 1u ); }
+    float len = sqrtf( sx * sx + sy * sy + sz * sz );
+    if( unit && len > 1e-3f )
+    {
+      float ux = sx / len, uy = sy / len, uz = sz / len, cmin = 1.0f;
+      for( uint32_t p = s; p < t; ++p ) { float4 m = nrm[p]; cmin = fminf( cmin, m.x * ux + m.y * uy + m.z * uz ); }
+      out = make_float4( ux, uy, uz, cmin - 1e-4f );
+    }
+  }
+  cone[c] = out;
+}
+
 __global__ void unpack_recs_kernel( const float4* __restrict__ recs, int n, float* __restrict__ xyz, int32_t* __restrict__ idx )
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,6 +294,22 @@ int rsgpu_grid_set_normals_dev( rsgpu_grid_t* g, const float* d_nor )
     RS_CHECK_LAUNCH();
   }
   g->has_normals = true;
+  // normal cones per cell for the compatible-neighbour searches
+  size_t n_cells = (size_t)( g->info.width * g->info.height * g->info.depth );
+  g->has_cone = false;
+  if( n > 0 )
+  {
+    DevBuf<uint32_t> flag;
+    RS_CUDA( flag.alloc( 1 ) );
+    RS_CUDA( cudaMemsetAsync( flag.p, 0, 4, rt().stream ) );
+    RS_CUDA( g->cone.alloc( n_cells ) );
+    cone_kernel<<<(unsigned)( ( n_cells + 127 ) / 128 ), 128, 0, rt().stream>>>( g->nrm.p, g->cell_start.p, n_cells, g->cone.p, flag.p );
+    RS_CHECK_LAUNCH();
+    uint32_t h = 0;
+    RS_CUDA( cudaMemcpyAsync( &h, flag.p, 4, cudaMemcpyDeviceToHost, rt().stream ) );
+    RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+    g->has_cone = h == 0; // any non-unit normal disables the culling for this grid
+  }
   return RSGPU_OK;
 }
 

@@ -13,9 +13,9 @@
 //   stage 2 (warp-cooperative, one query at a time)  lane l owns cell l of the (<= 27 cell) window: two
 //            cell_start loads resolve its point range; cells are swept nearest-first, 32 consecutive 16-byte
 //            records per step (one coalesced 512-byte request), pruned by the running best distance;
-//   the k-cap is exploited twice: (a) checkpoints — once k points are known inside a threshold distance, every
-//            cell farther away than that threshold is irrelevant; (b) the final rank count stops at k.  Windows
-//            holding fewer than k points skip both (the cap cannot bind).
+//            cells whose normal cone cannot contain a compatible normal are not swept at all (ConeCull below);
+//   the rank test (fewer than k points strictly closer) is a second, counting-only sweep over the cells nearer
+//            than the winner that stops at k; windows holding fewer than k points skip it (the cap cannot bind).
 // All pruning is conservative, so results equal the brute-force definition above (exact distance ties excepted).
 #pragma once
 #include "rsgpu_internal.cuh"
@@ -84,22 +84,19 @@ struct SweepState
 {
   uint32_t best, best_pos; float best_dot; // lane-local nearest compatible so far (d2 as ordered bits)
   uint32_t dc;                              // warp-uniform bound = min over lanes of best
-  uint32_t c0, c1;                          // lane-local counts of scanned points inside the two checkpoints
   unsigned nHits;                           // COUNT only
 };
 
 // sweep one cell's records [cs, ce): 32 consecutive 16-byte records per step
-template <bool CAP, bool COUNT>
+template <bool COUNT>
 __device__ __forceinline__ void sweep_cell_nc( const GridView& g, uint32_t cs, uint32_t ce, int lane, float px, float py, float pz,
-                                               float nx, float ny, float nz, float dot_thr, uint32_t r2bits, uint32_t tb0,
-                                               uint32_t tb1, SweepState& st )
+                                               float nx, float ny, float nz, float dot_thr, uint32_t r2bits, SweepState& st )
 {
   uint32_t lim = st.best < st.dc ? st.best : st.dc;
   for( uint32_t p = cs + lane; p < ce; p += 32 )
   {
     float4 rec = __ldg( g.recs + p );
     uint32_t db = __float_as_uint( dist2_exact( rec, px, py, pz ) );
-    if( CAP ) { st.c0 += db < tb0; st.c1 += db < tb1; }
     if( COUNT ) { st.nHits += db < r2bits; }
     if( db < lim )
     {
@@ -110,40 +107,27 @@ __device__ __forceinline__ void sweep_cell_nc( const GridView& g, uint32_t cs, u
   }
 }
 
-// phase 1 over one chunk of <= 32 cells (lane l holds cell l: range [s, t), squared gap gap2)
-template <bool CAP, bool COUNT>
-__device__ __forceinline__ bool phase1_chunk( const GridView& g, uint32_t s, uint32_t t, float gap2, int lane, float px, float py, float pz,
-                                              float nx, float ny, float nz, float dot_thr, uint32_t r2bits, uint32_t tb0, uint32_t tb1,
-                                              uint32_t uk, bool sorted_globally, SweepState& st )
+// phase 1 over one chunk of <= 32 cells (lane l holds cell l: range [s, t), squared gap gap2; `possible` false
+// when the cell's normal cone proves that none of its points can be compatible)
+template <bool COUNT>
+__device__ __forceinline__ void phase1_chunk( const GridView& g, uint32_t s, uint32_t t, float gap2, bool possible, int lane, float px,
+                                              float py, float pz, float nx, float ny, float nz, float dot_thr, uint32_t r2bits,
+                                              SweepState& st )
 {
   // key = gap bits with the lane in the low 5 bits: one redux gives the nearest unvisited cell and its owner
   // (dropping 5 mantissa bits only makes the pruning test marginally more conservative)
-  uint32_t key = ( s < t ) ? ( ( __float_as_uint( gap2 ) & 0xffffffe0u ) | (uint32_t)lane ) : 0xffffffffu;
-  int next_cp = ( CAP && sorted_globally ) ? 0 : 2;
+  uint32_t key = ( s < t && possible ) ? ( ( __float_as_uint( gap2 ) & 0xffffffe0u ) | (uint32_t)lane ) : 0xffffffffu;
   while( true )
   {
     uint32_t kmin = __reduce_min_sync( RS_FULL, key );
     if( kmin == 0xffffffffu ) { break; }
-    uint32_t gmin = kmin & 0xffffffe0u;
-    if( !COUNT )
-    {
-      if( gmin >= st.dc ) { break; }
-      if( CAP && next_cp < 2 && gmin >= ( next_cp == 0 ? tb0 : tb1 ) )
-      {
-        // every unvisited cell is at least this far away: if k scanned points are closer, nothing farther matters
-        bool capped = false;
-        if( next_cp == 0 ) { capped = __reduce_add_sync( RS_FULL, st.c0 ) >= uk; next_cp = 1; }
-        if( !capped && next_cp == 1 && gmin >= tb1 ) { capped = __reduce_add_sync( RS_FULL, st.c1 ) >= uk; next_cp = 2; }
-        if( capped ) { return true; }
-      }
-    }
+    if( !COUNT && ( kmin & 0xffffffe0u ) >= st.dc ) { break; }
     int src = (int)( kmin & 31u );
     uint32_t cs = __shfl_sync( RS_FULL, s, src ), ce = __shfl_sync( RS_FULL, t, src );
     if( lane == src ) { key = 0xffffffffu; }
-    sweep_cell_nc<CAP, COUNT>( g, cs, ce, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, tb0, tb1, st );
+    sweep_cell_nc<COUNT>( g, cs, ce, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, st );
     st.dc = __reduce_min_sync( RS_FULL, st.best );
   }
-  return false;
 }
 
 // phase 2 over one chunk: count points strictly closer than dcf, stop at k
@@ -165,6 +149,40 @@ __device__ __forceinline__ void phase2_chunk( const GridView& g, uint32_t s, uin
   }
 }
 
+// Normal-cone culling.  Each non-empty cell stores the unit mean u of its normals and cos(alpha), alpha = the
+// largest angle between u and a normal of the cell.  A point of the cell can only be compatible with the query
+// normal n (dot >= dot_thr = cos(beta)) if angle(n, u) <= alpha + beta, so a cell with
+//   dot(n, u) < cos(alpha + beta')      (beta' = beta widened by a safety margin)
+// is skipped when looking for the nearest compatible point.  Only used when all normals involved are unit
+// length to 1e-4 (checked at rsgpu_grid_set_normals / per query); planar regions (floors, walls) — where the
+// reference wastes its whole k-list on incompatible points — have cones of a few degrees.
+struct ConeCull
+{
+  bool on;
+  float cb, sb; // cos / sin of beta'
+};
+__device__ __forceinline__ ConeCull make_cull( const GridView& g, float dot_thr, float nx, float ny, float nz )
+{
+  ConeCull c; c.on = false; c.cb = 0.f; c.sb = 1.f;
+  float n2 = nx * nx + ny * ny + nz * nz;
+  if( g.cone && dot_thr >= 1e-3f && dot_thr <= 1.0f && fabsf( n2 - 1.0f ) < 2e-4f )
+  {
+    c.on = true;
+    c.cb = dot_thr - 1e-3f;
+    c.sb = sqrtf( fmaxf( 0.0f, 1.0f - c.cb * c.cb ) ) ;
+  }
+  return c;
+}
+__device__ __forceinline__ bool cone_possible( const GridView& g, const ConeCull& c, size_t cell_id, float nx, float ny, float nz )
+{
+  if( !c.on ) { return true; }
+  float4 u = __ldg( g.cone + cell_id ); // {ux, uy, uz, cos(alpha)} (cos(alpha) < 0: no usable cone)
+  if( !( u.w > 0.0f ) ) { return true; }
+  float sa = sqrtf( fmaxf( 0.0f, 1.0f - u.w * u.w ) ) + 1e-5f;
+  float ct = u.x * nx + u.y * ny + u.z * nz;
+  return !( ct < u.w * c.cb - sa * c.sb );
+}
+
 // stage 2: all 32 lanes call this with the same (broadcast) query.  FAST: the window is a subset of the
 // 3x3x3 block around the query's own cell (always the case when radius <= cell size) and lane l < 27 owns block
 // cell (l % 3, l / 3 % 3, l / 9) relative to (lox, loy, loz); otherwise the generic enumeration in chunks of 32.
@@ -179,13 +197,12 @@ __device__ __forceinline__ NearestHit nearest_compatible_w( const GridView& g, c
   if( w.n_cells == 0 ) { return hit; }
   const uint32_t r2bits = __float_as_uint( r2f );
   const uint32_t uk = (uint32_t)k;
-  // checkpoint thresholds of the k-cap (fractions of r^2; any values are valid)
-  const uint32_t tb0 = __float_as_uint( 0.2f * r2f ), tb1 = __float_as_uint( 0.5f * r2f );
-  SweepState st; st.best = r2bits; st.best_pos = 0xffffffffu; st.best_dot = 0.f; st.dc = r2bits; st.c0 = st.c1 = 0; st.nHits = 0;
+  SweepState st; st.best = r2bits; st.best_pos = 0xffffffffu; st.best_dot = 0.f; st.dc = r2bits; st.nHits = 0;
   unsigned long long nB = 0, nC = 0;
   uint32_t s0 = 0, t0 = 0; float gap0 = __int_as_float( RS_INF_BITS );
-  bool cap = false;
-  const bool single = w.n_cells <= 32;
+  bool possible0 = true;
+  ConeCull cull = make_cull( g, dot_thr, nx, ny, nz );
+  if( COUNT ) { cull.on = false; }
   if( fast )
   {
     const int ix = lane % 3, iy = ( lane / 3 ) % 3, iz = lane / 9;
@@ -198,25 +215,22 @@ __device__ __forceinline__ NearestHit nearest_compatible_w( const GridView& g, c
       const float gy = cy < w.c0y ? gly : ( cy > w.c0y ? ghy : 0.0f );
       const float gz = cz < w.c0z ? glz : ( cz > w.c0z ? ghz : 0.0f );
       gap0 = __fadd_rn( __fadd_rn( __fmul_rn( gz, gz ), __fmul_rn( gy, gy ) ), __fmul_rn( gx, gx ) );
+      if( s0 < t0 && gap0 < r2f ) { possible0 = cone_possible( g, cull, id, nx, ny, nz ); }
     }
   }
   else { window_cell( g, w, lane, s0, t0, gap0 ); }
-  {
-    // the cap can only bind when the window holds at least k points
-    uint32_t npts = __reduce_add_sync( RS_FULL, t0 - s0 );
-    cap = !single || npts >= uk;
-    if( COUNT ) { nB += __popc( __ballot_sync( RS_FULL, s0 < t0 ) ); nC += npts; }
-  }
+  // the k-cap can only bind when the window holds at least k points
+  const uint32_t npts = __reduce_add_sync( RS_FULL, t0 - s0 );
+  const bool cap = w.n_cells > 32 || npts >= uk;
+  if( COUNT ) { nB += __popc( __ballot_sync( RS_FULL, s0 < t0 ) ); nC += npts; }
   // ---- phase 1: nearest compatible point, cells visited nearest-first and pruned by the running best
-  bool capped;
-  if( cap ) { capped = phase1_chunk<true, COUNT>( g, s0, t0, gap0, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, tb0, tb1, uk, single, st ); }
-  else { capped = phase1_chunk<false, COUNT>( g, s0, t0, gap0, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, tb0, tb1, uk, single, st ); }
-  for( int base = 32; base < w.n_cells && !capped; base += 32 )
+  phase1_chunk<COUNT>( g, s0, t0, gap0, possible0, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, st );
+  for( int base = 32; base < w.n_cells; base += 32 )
   {
     uint32_t s, t; float gap2;
     window_cell( g, w, base + lane, s, t, gap2 );
     if( COUNT ) { nB += __popc( __ballot_sync( RS_FULL, s < t ) ); nC += __reduce_add_sync( RS_FULL, t - s ); }
-    phase1_chunk<true, COUNT>( g, s, t, gap2, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, tb0, tb1, uk, false, st );
+    phase1_chunk<COUNT>( g, s, t, gap2, true, lane, px, py, pz, nx, ny, nz, dot_thr, r2bits, st );
   }
   uint32_t cnt = 0;
   if( st.dc < r2bits )
@@ -226,21 +240,8 @@ __device__ __forceinline__ NearestHit nearest_compatible_w( const GridView& g, c
     int src = __ffs( __ballot_sync( RS_FULL, st.best == st.dc && st.best_pos == wpos ) ) - 1;
     hit.d2 = __uint_as_float( st.dc ); hit.pos = wpos; hit.dot = __shfl_sync( RS_FULL, st.best_dot, src );
     const float dcf = hit.d2;
-    bool decided = false;
-    if( !COUNT )
-    {
-      if( !cap ) { decided = true; hit.found = true; } // fewer than k points in the whole window
-      else if( single )
-      {
-        // every point closer than dc sits in a visited cell, so the scanned-point count inside a threshold >= dc
-        // bounds the rank from above: if that bound is already < k the exact count is not needed
-        uint32_t bound = 0xffffffffu;
-        if( st.dc <= tb0 ) { bound = __reduce_add_sync( RS_FULL, st.c0 ); }
-        else if( st.dc <= tb1 ) { bound = __reduce_add_sync( RS_FULL, st.c1 ); }
-        if( bound < uk ) { decided = true; hit.found = true; }
-      }
-    }
-    if( !decided )
+    if( !cap && !COUNT ) { hit.found = true; } // fewer than k points in the whole window: the rank cannot reach k
+    else
     {
       // ---- phase 2: rank of the winner = number of points strictly closer; k or more => it is not in the k-list
       phase2_chunk( g, s0, t0, gap0, lane, px, py, pz, dcf, uk, cnt );

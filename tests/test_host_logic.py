@@ -1,0 +1,77 @@
+"""CPU: host-side logic of the product (pose grids, sharding, merging) and the C-ABI surface of librsgpu.so."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import orcbind as O
+from rescan_b200 import api, pipeline, posegrid, synth
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """the C-ABI library loads and exports every function include/rsgpu.h declares (no compute call is made)"""
+    hdr = open(os.path.join(ROOT, "include", "rsgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rsgpu_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(api.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"librsgpu.so does not export {name}"
+    assert declared == set(api.SIGNATURES), declared ^ set(api.SIGNATURES)
+
+
+def test_no_device_fails_loudly():
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.RsgpuError, match="no CUDA device"):
+        api.HashGrid(np.zeros((4, 3), np.float32), 0.05)
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "rescan_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                bad = re.search(r"^\s*(from|import)\s+oracle\b|orcbind|refbind|librescan_oracle|librescan_ref|rescan_oracle\.c", src, flags=re.M)
+                assert bad is None, f"{f} references the oracle: {bad.group(0)}"
+
+
+def test_posegrid_matches_reference_arithmetic():
+    rng = np.random.default_rng(0)
+    for a in list(posegrid.rotation_angles(36)) + list(rng.uniform(-7, 7, 500).astype(np.float32)):
+        assert (posegrid.make_pose(a, 1.5, 0.0, -2.25) == O.make_pose(a, 1.5, 0.0, -2.25)).all()
+    assert len(posegrid.rotation_angles(10)) == 10  # the reference's own setting (pose_proposal.cpp:28)
+    assert posegrid.rotation_xforms(36).shape == (36, 16) and posegrid.rotation_xforms(72).shape == (72, 16)
+    z, scan, _ = common.golden()
+    t = posegrid.reference_translation_grid(z["scan_bbox"][:3], z["scan_bbox"][3:], 0.10)
+    assert (t == synth.reference_translation_grid(type("C", (), {"bbox_min": z["scan_bbox"][:3], "bbox_max": z["scan_bbox"][3:]})(), 0.10)).all()
+    g = posegrid.pose_grid(posegrid.rotation_xforms(4), t[:5])
+    assert g.shape == (5, 4, 16) and (g[3, 2, 12:15] == t[3]).all() and (g[:, :, 15] == 1).all()
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 2048, 20000):
+        for world in (1, 2, 3, 8):
+            spans = [pipeline.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_merge_topk_is_deterministic_and_order_independent():
+    rng = np.random.default_rng(1)
+    props = rng.uniform(0, 1, (40, 17)).astype(np.float32)
+    props[5, 16] = props[9, 16] = props[30, 16] = 0.75  # ties broken by pose id
+    ids = rng.permutation(1000)[:40].astype(np.int64)
+    a = pipeline.merge_topk([props[:13], props[13:]], [ids[:13], ids[13:]], 10)
+    b = pipeline.merge_topk([props[25:], props[:25]], [ids[25:], ids[:25]], 10)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    assert (np.diff(a[0][:, 16]) <= 0).all()
+    full = pipeline.merge_topk([props], [ids], 0)
+    assert len(full[0]) == 40

@@ -1,0 +1,79 @@
+"""CPU: the oracle against the UNMODIFIED reference compiled in place (oracle/_ref/librescan_ref.so) on denser seeded
+data than the golden fixture.  Skipped where that library does not exist (it is built only where /root/reference is)."""
+import numpy as np
+import pytest
+
+from oracle import orcbind as O, refbind as R
+from rescan_b200 import synth
+from tests import common
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/librescan_ref.so not built (no /root/reference here)")
+
+
+@pytest.fixture(scope="module")
+def S():
+    scene = common.tiny_scene()
+    scan = R.RefCloud.from_levels({l: (scene.scan.pos(l), scene.scan.nor(l)) for l in range(5)})
+    objs = [R.RefCloud.from_levels({l: (o.cloud.pos(l), o.cloud.nor(l)) for l in range(5)}) for o in scene.objects]
+    return scene, scan, objs
+
+
+def test_sizeof_and_levels(S):
+    scene, scan, _ = S
+    assert R.load().ref_sizeof_hash_grid() == 120
+    assert scan.n(1) == scene.scan.n(1)
+
+
+@pytest.mark.parametrize("radius,k", [(0.10, 64), (0.05, 16), (0.05, 1), (0.075, 8), (0.2, 32)])
+def test_radius_search(S, radius, k):
+    scene, scan, _ = S
+    p = scene.scan.pos(1)
+    rng = np.random.default_rng(7)
+    q = np.ascontiguousarray(p[rng.choice(len(p), 1500)] + rng.uniform(-0.03, 0.03, (1500, 3)).astype(np.float32), np.float32)
+    og, rg = O.OrcGrid(p, 0.05), scan.grid(1)
+    a, b = og.radius_search(q, radius, k), rg.radius_search(q, radius, k)
+    assert a[3] == b[3]
+    common.check_rows(a[0], a[1], a[2], b[0], b[1], b[2], k)
+
+
+def test_radius_search_cell_cap(S):
+    """more than 512 cells in range: the reference stops enumerating (msh_hash_grid.h:1213)"""
+    scene, _, _ = S
+    p = scene.scan.pos(3)
+    og, rg = O.OrcGrid(p, 0.02), R.RefGrid(p, 0.02)
+    rng = np.random.default_rng(8)
+    q = np.ascontiguousarray(p[rng.choice(len(p), 200)], np.float32)
+    a, b = og.radius_search(q, 0.25, 8), rg.radius_search(q, 0.25, 8)
+    common.check_rows(a[0], a[1], a[2], b[0], b[1], b[2], 8)
+
+
+def test_knn_search(S):
+    scene, scan, _ = S
+    p = scene.scan.pos(1)
+    rng = np.random.default_rng(9)
+    q = np.ascontiguousarray(p[rng.choice(len(p), 1000)] + rng.uniform(-0.005, 0.005, (1000, 3)).astype(np.float32), np.float32)
+    a, b = O.OrcGrid(p, 0.05).knn_search(q, 8), scan.grid(1).knn_search(q, 8)
+    common.check_rows(a[0], a[1], a[2], b[0], b[1], b[2], 8)
+
+
+@pytest.mark.parametrize("lvl", [4, 3])
+def test_scores(S, lvl):
+    scene, scan, objs = S
+    og = O.OrcGrid(scene.scan.pos(1), 0.05)
+    rng = np.random.default_rng(10 + lvl)
+    for o, ro in zip(scene.objects, objs):
+        xs = np.stack([common.colmajor(m) for _, m in common.perturbed_poses(rng, type("X", (), {"objects": [o]})(), 12)])
+        got, _ = O.score_poses(o.cloud.pos(lvl), o.cloud.nor(lvl), og, scene.scan.nor(1), xs, 64, 0.10)
+        want, _ = R.score_batch(ro, scan, xs, query_lvl=lvl)
+        assert (got == want).all()
+
+
+def test_icp_align(S):
+    scene, _, _ = S
+    o = scene.objects[-1]
+    rng = np.random.default_rng(12)
+    s = common.colmajor(common.perturbed_poses(rng, type("X", (), {"objects": [o]})(), 1, 0.03, 0.08)[0][1])
+    ang = np.float32(np.deg2rad(60.0))
+    To, eo, _ = O.icp_align(o.cloud.pos(2), o.cloud.nor(2), scene.scan.pos(2), scene.scan.nor(2), s, 0.10, ang)
+    Tr, er = R.icp_align(o.cloud.pos(2), o.cloud.nor(2), scene.scan.pos(2), scene.scan.nor(2), s, 0.10, ang)
+    assert (To == Tr).all() and np.float32(eo) == np.float32(er)

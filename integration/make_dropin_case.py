@@ -1,0 +1,40 @@
+"""Writes the file set of the drop-in test (a first-scan database + a rescan PLY) into a directory.  With --golden it
+also runs the pure-CPU reference build (integration/_build/pose_proposal_ref) on it and stores the resulting proposal
+.bin as tests/golden/dropin_pp.bin (build container only)."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rescan_b200 import rsio, synth  # noqa: E402
+
+
+def write_case(folder):
+    os.makedirs(folder, exist_ok=True)
+    scan0 = synth.make_scene(n_objects=3, n_static=1, room=(3.2, 1.6, 2.8), spacing=0.035, seed=synth.SEED + 99)
+    scan1 = synth.make_scene(n_objects=3, n_static=1, room=(3.2, 1.6, 2.8), spacing=0.035, seed=synth.SEED + 100, objects=scan0.objects)
+    p0 = os.path.join(folder, "scan0.ply")
+    p1 = os.path.join(folder, "scan1.ply")
+    rsio.write_ply(p0, scan0.scan.pos(0), scan0.scan.nor(0), scan0.scan_class, scan0.scan_instance)
+    rsio.write_ply(p1, scan1.scan.pos(0), scan1.scan.nor(0), scan1.scan_class, scan1.scan_instance)
+    db = rsio.write_database(folder, "scan0", scan0, p0, [(i, o.pose) for i, o in enumerate(scan0.objects)])
+    return db, p1, os.path.join(folder, "scan1_pp.rsdb"), scan1
+
+
+def main():
+    folder = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "/tmp/rsgpu_dropin_case"
+    db, scan, out, _ = write_case(folder)
+    print(db, scan, out)
+    if "--golden" in sys.argv:
+        exe = os.path.join(ROOT, "integration", "_build", "pose_proposal_ref")
+        subprocess.check_call([exe, db, scan, out, "-v"], stdout=subprocess.DEVNULL)
+        shutil.copy(os.path.join(folder, "scan1_pp", "scan1_pp.bin"), os.path.join(ROOT, "tests", "golden", "dropin_pp.bin"))
+        print("wrote tests/golden/dropin_pp.bin", os.path.getsize(os.path.join(ROOT, "tests", "golden", "dropin_pp.bin")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

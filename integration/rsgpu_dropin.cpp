@@ -1,0 +1,157 @@
+// Drop-in replacement of the hot-path symbols of mhalber/Rescan's pose_proposal executable, on top of the
+// rsgpu C ABI (include/rsgpu.h).  Linked together with the reference's UNMODIFIED apps/pose_proposal/main.cpp
+// (see integration/Makefile and INTEGRATION.md) it gives a `pose_proposal` binary whose dense pose search,
+// verification, ICP refinement and rescoring run on the GPU while loading, NMS, sorting and saving stay
+// reference host code.  Nothing here is copied from the reference: the reference headers are included in place
+// for their TYPES only (no *_IMPLEMENTATION define), exactly like apps/pose_proposal/pose_proposal.cpp:1-17 does.
+//
+//   replaces                                   (reference)                               with
+//   mgs_propose_poses                          apps/pose_proposal/pose_proposal.cpp:325  rsgpu_propose_poses
+//   mgs_compute_object_alignment_score         apps/pose_proposal/pose_proposal.cpp:93   rsgpu_score_poses
+//   icp_align                                  lib/rs/icp.h:416                          rsgpu_icp_align_batch
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <cassert>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "msh/msh_std.h"
+#include "msh/msh_vec_math.h"
+#include "msh/msh_geometry.h"
+#include "msh/msh_hash_grid.h"
+#include "mg/hashtable.h"
+#include "msh/msh_ply.h"
+#include "rs_pointcloud.h"
+#include "rs_distance_function.h"
+#include "rs_database.h"
+#include "pose_proposal.h"
+
+#include "rsgpu.h"
+
+namespace
+{
+void die( const char* what )
+{
+  // the reference reports errors with printf + exit(-1) (main.cpp:141, 153); there is no CPU fallback to take
+  fprintf( stderr, "rsgpu drop-in: %s failed: %s\n", what, rsgpu_last_error() );
+  exit( -1 );
+}
+#define RSGPU_OR_DIE( call ) do { if( ( call ) != RSGPU_OK ) { die( #call ); } } while( 0 )
+
+typedef std::pair<const void*, size_t> key_t;
+std::map<key_t, rsgpu_grid_t*> g_grids;    // grids over (positions pointer, count): the scan levels never change in a run
+std::map<key_t, rsgpu_cloud_t*> g_clouds;
+
+rsgpu_grid_t* grid_for( const msh_vec3_t* pos, const msh_vec3_t* nor, size_t n )
+{
+  key_t k( pos, n );
+  std::map<key_t, rsgpu_grid_t*>::iterator it = g_grids.find( k );
+  if( it != g_grids.end() ) { return it->second; }
+  rsgpu_grid_t* g = NULL;
+  // rs_pointcloud_compute_search_grid builds every level's grid with radius 0.05 (rs_pointcloud.h:849-863)
+  RSGPU_OR_DIE( rsgpu_grid_create( &pos[0].x, (int32_t)n, 0.05f, &g ) );
+  RSGPU_OR_DIE( rsgpu_grid_set_normals( g, &nor[0].x ) );
+  g_grids[k] = g;
+  return g;
+}
+
+rsgpu_cloud_t* cloud_for( const msh_vec3_t* pos, const msh_vec3_t* nor, size_t n )
+{
+  key_t k( pos, n );
+  std::map<key_t, rsgpu_cloud_t*>::iterator it = g_clouds.find( k );
+  if( it != g_clouds.end() ) { return it->second; }
+  rsgpu_cloud_t* c = NULL;
+  RSGPU_OR_DIE( rsgpu_cloud_create( &pos[0].x, &nor[0].x, (int32_t)n, &c ) );
+  g_clouds[k] = c;
+  return c;
+}
+} // namespace
+
+float
+mgs_compute_object_alignment_score( rs_pointcloud_t* object, rs_pointcloud_t* scene, int search_lvl, int query_lvl,
+                                    msh_mat4_t xform, tmp_score_calc_storage_t* storage )
+{
+  static const float search_radii[5] = { 0.05f, 0.1f, 0.15f, 0.2f, 0.25f }; // pose_proposal.cpp:98
+  rsgpu_cloud_t* obj = cloud_for( object->positions[query_lvl], object->normals[query_lvl], object->n_pts[query_lvl] );
+  rsgpu_grid_t* scn = grid_for( scene->positions[search_lvl], scene->normals[search_lvl], scene->n_pts[search_lvl] );
+  float score = 0.0f;
+  RSGPU_OR_DIE( rsgpu_score_poses( obj, scn, xform.data, 1, storage->max_n_neigh, search_radii[search_lvl], &score ) );
+  return score;
+}
+
+void
+mgs_propose_poses( rsdb_t* rsdb, rs_pointcloud_t* input_scan, msh_array( msh_array( pose_proposal_t ) ) * proposed_poses,
+                   const mgs_opts_t* opts, int verbose )
+{
+  uint64_t t0 = msh_time_now();
+  const int32_t search_lvl = 1; // pose_proposal.cpp:178
+  rsgpu_grid_t* scn = grid_for( input_scan->positions[search_lvl], input_scan->normals[search_lvl], input_scan->n_pts[search_lvl] );
+
+  // the candidate lattice of mgs__initial_pose_proposals (pose_proposal.cpp:203-222), same float loop counters
+  float spacing = opts->search_grid_spacing;
+  float y_angle_inc = opts->search_grid_angle_delta;
+  msh_vec3_t origin = input_scan->bbox.min_p;
+  float length_x = input_scan->bbox.max_p.x - input_scan->bbox.min_p.x;
+  float length_z = input_scan->bbox.max_p.z - input_scan->bbox.min_p.z;
+  float height = 0.0f;
+  std::vector<float> rotations, translations;
+  for( float y_angle = 0.0f; y_angle < MSH_TWO_PI; y_angle += y_angle_inc )
+  {
+    msh_mat4_t r = msh_rotate( msh_mat4_identity(), y_angle, msh_vec3( 0.0f, 1.0f, 0.0f ) );
+    rotations.insert( rotations.end(), r.data, r.data + 16 );
+  }
+  for( float ox = -spacing; ox < length_x + spacing; ox += spacing )
+  {
+    for( float oz = -spacing; oz < length_z + spacing; oz += spacing )
+    {
+      translations.push_back( origin.x + ox ); translations.push_back( height ); translations.push_back( origin.z + oz );
+    }
+  }
+  const int32_t n_rot = (int32_t)( rotations.size() / 16 );
+  const int64_t n_trans = (int64_t)( translations.size() / 3 );
+
+  rsgpu_propose_opts_t po;
+  rsgpu_propose_default_opts( &po ); // k = 64, r = 0.10, thresholds 0.25 / 0.35 / 0.40, every survivor kept
+  std::vector<float> out( (size_t)( n_trans > 0 ? n_trans : 1 ) * RSGPU_POSE_FLOATS );
+  int32_t n_objects = (int32_t)msh_array_len( rsdb->objects );
+  for( int32_t i = 0; i < n_objects; ++i )
+  {
+    msh_array( pose_proposal_t ) cur = NULL;
+    if( !rsdb_is_object_static( rsdb, i ) ) // pose_proposal.cpp:198
+    {
+      rs_pointcloud_t* shape = rsdb->objects[i].shape;
+      rsgpu_cloud_t* lv[3];
+      for( int l = 0; l < 3; ++l ) { lv[l] = cloud_for( shape->positions[4 - l], shape->normals[4 - l], shape->n_pts[4 - l] ); }
+      int64_t n_out = 0;
+      RSGPU_OR_DIE( rsgpu_propose_poses( lv[0], lv[1], lv[2], scn, rotations.data(), n_rot, translations.data(), n_trans, &po,
+                                         out.data(), NULL, n_trans, &n_out ) );
+      for( int64_t j = 0; j < n_out; ++j )
+      {
+        pose_proposal_t p;
+        memcpy( p.xform.data, &out[(size_t)j * RSGPU_POSE_FLOATS], 64 );
+        p.score = out[(size_t)j * RSGPU_POSE_FLOATS + 16];
+        msh_array_push( cur, p );
+      }
+      msh_cprintf( verbose, "POSE_PROPOSAL:      object %d: %d potential poses (GPU)\n", i, (int)n_out );
+    }
+    msh_array_push( *proposed_poses, cur );
+  }
+  msh_cprintf( verbose, "POSE PROPOSAL: Done in %fs (rsgpu: %d rotations x %d translations per object)\n",
+               msh_time_diff_sec( msh_time_now(), t0 ), (int)n_rot, (int)n_trans );
+}
+
+extern "C" float
+icp_align( msh_vec3_t* pts1, msh_vec3_t* nor1, int32_t n_pts1, msh_vec3_t* pts2, msh_vec3_t* nor2, int32_t n_pts2,
+           msh_mat4_t* T1, msh_mat4_t T2, float max_dist, float max_angle, bool verbose )
+{
+  (void)verbose;
+  rsgpu_cloud_t* obj = cloud_for( pts1, nor1, (size_t)n_pts1 );
+  rsgpu_grid_t* scn = grid_for( pts2, nor2, (size_t)n_pts2 ); // any cell size gives the same (exact) correspondences
+  float err = 1e6f;
+  RSGPU_OR_DIE( rsgpu_icp_align_batch( obj, scn, T1->data, 1, T2.data, max_dist, max_angle, &err, NULL ) );
+  return err;
+}

@@ -1,0 +1,75 @@
+"""Writers / readers for the reference's on-disk formats, so that synthetic scenes can be handed to the reference's
+own executables (and to the drop-in build of integration/): binary PLY clouds with the 12 vertex properties
+rs_pointcloud__load_ply reads (reference lib/rs/rs_pointcloud.h:598-781), the `.rsdb` text database
+(lib/rs/rs_database.h:291-441 parser, :532-611 writer) and the proposal `.bin` (apps/pose_proposal/main.cpp:61-89).
+Host-side only: numpy, no GPU, no oracle.
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+from . import synth
+
+
+def write_ply(path, pos, nor, class_idx=0, instance_idx=0, radius=0.01):
+    """face-less binary little-endian PLY: level 0 is then exactly these points (no area resampling, :1268-1281)"""
+    pos, nor = np.asarray(pos, np.float32), np.asarray(nor, np.float32)
+    n = len(pos)
+    dt = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                   ("red", "u1"), ("green", "u1"), ("blue", "u1"), ("radius", "<f4"), ("class_idx", "<i4"), ("instance_idx", "<i4")])
+    v = np.zeros(n, dt)
+    v["x"], v["y"], v["z"] = pos[:, 0], pos[:, 1], pos[:, 2]
+    v["nx"], v["ny"], v["nz"] = nor[:, 0], nor[:, 1], nor[:, 2]
+    v["red"] = v["green"] = v["blue"] = 128
+    v["radius"] = radius
+    v["class_idx"] = class_idx
+    v["instance_idx"] = instance_idx
+    hdr = ["ply", "format binary_little_endian 1.0", f"element vertex {n}",
+           "property float x", "property float y", "property float z",
+           "property float nx", "property float ny", "property float nz",
+           "property uchar red", "property uchar green", "property uchar blue",
+           "property float radius", "property int class_idx", "property int instance_idx", "end_header"]
+    with open(path, "wb") as f:
+        f.write(("\n".join(hdr) + "\n").encode("ascii"))
+        f.write(v.tobytes())
+
+
+def pose_to_rsdb_row_major(m4):
+    """the 16 numbers of a `pose` line: row-major although msh_mat4_t is column-major in memory (rs_database.h:601-606)"""
+    return " ".join(f"{float(x):.9g}" for x in np.asarray(m4, np.float32).reshape(4, 4).reshape(-1))
+
+
+def write_database(folder, name, scene: synth.Scene, scan_ply, placements=None):
+    """`<folder>/<name>.rsdb` + `<folder>/<name>/obj_XXX.ply` object models; returns the .rsdb path.
+    placements: optional list of (object_idx, 4x4 pose) forming arrangement 0 (the previous scan's arrangement)."""
+    model_folder = os.path.join(folder, name)
+    os.makedirs(model_folder, exist_ok=True)
+    lines = ["rsdb 1.0", f"model_folder {model_folder}"]
+    for i, c in enumerate(synth.CLASS_NAMES):
+        lines.append(f"class {c} {i}")
+    lines.append(f"scene 0 0 {scan_ply} none")
+    for i, o in enumerate(scene.objects):
+        fn = f"obj_{o.uidx:03d}.ply"
+        write_ply(os.path.join(model_folder, fn), o.cloud.pos(0), o.cloud.nor(0), o.class_idx, o.uidx)
+        lines.append(f"object {fn} {o.uidx} {o.class_idx}")
+    lines.append("n_arrangements 1")
+    for k, (oi, pose) in enumerate(placements or []):
+        lines.append(f"pose {k} 0 {oi} 1.0  {pose_to_rsdb_row_major(pose)}")
+    path = os.path.join(folder, name + ".rsdb")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
+
+
+def read_proposals(path):
+    """proposal .bin -> list (per object) of float32 [n, 17] (column-major xform + score), as written (descending score)"""
+    raw = np.fromfile(path, np.uint8)
+    n_obj = int(raw[:4].view("<i4")[0])
+    counts = raw[4:4 + 4 * n_obj].view("<i4")
+    body = raw[4 + 4 * n_obj:].view("<f4").reshape(-1, 17)
+    out, o = [], 0
+    for c in counts:
+        out.append(body[o:o + c].copy())
+        o += c
+    return out

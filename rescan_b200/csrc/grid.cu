@@ -142,6 +142,48 @@ __global__ void cone_kernel( const float4* __restrict__ nrm, const uint32_t* __r
   cone[c] = out;
 }
 
+// cone enclosing every normal of the 3x3x3 block of cells around c: axis = count-weighted mean of the cells' axes,
+// half-angle = max over cells of (angle between axes + the cell's own half-angle), all rounded outwards
+__global__ void ncone_kernel( const float4* __restrict__ cone, const uint32_t* __restrict__ cell_start, int W, int H, int D,
+                              float4* __restrict__ ncone )
+{
+  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t n = (size_t)W * H * D;
+  if( c >= n ) { return; }
+  int x = (int)( c % W ); size_t r = c / W; int y = (int)( r % H ); int z = (int)( r / H );
+  float sx = 0.f, sy = 0.f, sz = 0.f; bool usable = true; int filled = 0;
+  for( int zz = max( z - 1, 0 ); zz <= min( z + 1, D - 1 ); ++zz )
+    for( int yy = max( y - 1, 0 ); yy <= min( y + 1, H - 1 ); ++yy )
+      for( int xx = max( x - 1, 0 ); xx <= min( x + 1, W - 1 ); ++xx )
+      {
+        size_t id = ( (size_t)zz * H + yy ) * W + xx;
+        uint32_t cnt = cell_start[id + 1] - cell_start[id];
+        if( !cnt ) { continue; }
+        float4 u = cone[id];
+        if( !( u.w > 0.0f ) ) { usable = false; }
+        sx += u.x * (float)cnt; sy += u.y * (float)cnt; sz += u.z * (float)cnt; ++filled;
+      }
+  float4 out = make_float4( 0.f, 0.f, 0.f, -1.f );
+  float len = sqrtf( sx * sx + sy * sy + sz * sz );
+  if( usable && filled && len > 1e-3f )
+  {
+    float ux = sx / len, uy = sy / len, uz = sz / len, worst = 0.0f; // worst = largest (axis angle + half-angle), radians
+    for( int zz = max( z - 1, 0 ); zz <= min( z + 1, D - 1 ); ++zz )
+      for( int yy = max( y - 1, 0 ); yy <= min( y + 1, H - 1 ); ++yy )
+        for( int xx = max( x - 1, 0 ); xx <= min( x + 1, W - 1 ); ++xx )
+        {
+          size_t id = ( (size_t)zz * H + yy ) * W + xx;
+          if( cell_start[id + 1] == cell_start[id] ) { continue; }
+          float4 u = cone[id];
+          float a = acosf( fminf( 1.0f, fmaxf( -1.0f, u.x * ux + u.y * uy + u.z * uz ) ) ) + acosf( fminf( 1.0f, u.w ) );
+          worst = fmaxf( worst, a );
+        }
+    worst += 2e-3f;
+    if( worst < 1.5f ) { out = make_float4( ux, uy, uz, cosf( worst ) ); }
+  }
+  ncone[c] = out;
+}
+
 __global__ void unpack_recs_kernel( const float4* __restrict__ recs, int n, float* __restrict__ xyz, int32_t* __restrict__ idx )
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,6 +346,10 @@ int rsgpu_grid_set_normals_dev( rsgpu_grid_t* g, const float* d_nor )
     RS_CUDA( cudaMemsetAsync( flag.p, 0, 4, rt().stream ) );
     RS_CUDA( g->cone.alloc( n_cells ) );
     cone_kernel<<<(unsigned)( ( n_cells + 127 ) / 128 ), 128, 0, rt().stream>>>( g->nrm.p, g->cell_start.p, n_cells, g->cone.p, flag.p );
+    RS_CHECK_LAUNCH();
+    RS_CUDA( g->ncone.alloc( n_cells ) );
+    ncone_kernel<<<(unsigned)( ( n_cells + 127 ) / 128 ), 128, 0, rt().stream>>>( g->cone.p, g->cell_start.p, (int)g->info.width, (int)g->info.height,
+                                                                                   (int)g->info.depth, g->ncone.p );
     RS_CHECK_LAUNCH();
     uint32_t h = 0;
     RS_CUDA( cudaMemcpyAsync( &h, flag.p, 4, cudaMemcpyDeviceToHost, rt().stream ) );

@@ -37,8 +37,42 @@ struct LaneQuery
   bool active, fast;
 };
 
+// Normal-cone culling.  Each non-empty cell stores the unit mean u of its normals and cos(alpha), alpha = the
+// largest angle between u and a normal of the cell.  A point of the cell can only be compatible with the query
+// normal n (dot >= dot_thr = cos(beta)) if angle(n, u) <= alpha + beta, so a cell with
+//   dot(n, u) < cos(alpha + beta')      (beta' = beta widened by a safety margin)
+// is skipped when looking for the nearest compatible point.  Only used when all normals involved are unit
+// length to 1e-4 (checked at rsgpu_grid_set_normals / per query); planar regions (floors, walls) — where the
+// reference wastes its whole k-list on incompatible points — have cones of a few degrees.
+struct ConeCull
+{
+  bool on;
+  float cb, sb; // cos / sin of beta'
+};
+__device__ __forceinline__ ConeCull make_cull( const GridView& g, float dot_thr, float nx, float ny, float nz )
+{
+  ConeCull c; c.on = false; c.cb = 0.f; c.sb = 1.f;
+  float n2 = nx * nx + ny * ny + nz * nz;
+  if( g.cone && dot_thr >= 1e-3f && dot_thr <= 1.0f && fabsf( n2 - 1.0f ) < 2e-4f )
+  {
+    c.on = true;
+    c.cb = dot_thr - 1e-3f;
+    c.sb = sqrtf( fmaxf( 0.0f, 1.0f - c.cb * c.cb ) ) ;
+  }
+  return c;
+}
+__device__ __forceinline__ bool cone_possible( const float4* __restrict__ cones, const ConeCull& c, size_t cell_id, float nx, float ny, float nz )
+{
+  if( !c.on ) { return true; }
+  float4 u = __ldg( cones + cell_id ); // {ux, uy, uz, cos(alpha)} (cos(alpha) <= 0: no usable cone)
+  if( !( u.w > 0.0f ) ) { return true; }
+  float sa = sqrtf( fmaxf( 0.0f, 1.0f - u.w * u.w ) ) + 1e-5f;
+  float ct = u.x * nx + u.y * ny + u.z * nz;
+  return !( ct < u.w * c.cb - sa * c.sb );
+}
+
 // stage 1: window + occupancy filter for this lane's own query
-__device__ __forceinline__ void lane_query_setup( const GridView& g, double radius, LaneQuery& q, bool valid )
+__device__ __forceinline__ void lane_query_setup( const GridView& g, double radius, float dot_thr, bool allow_cull, LaneQuery& q, bool valid )
 {
   q.active = false; q.fast = false;
   q.glx = q.ghx = q.gly = q.ghy = q.glz = q.ghz = 0.f;
@@ -51,8 +85,16 @@ __device__ __forceinline__ void lane_query_setup( const GridView& g, double radi
   if( inside && within1 && g.occ27 )
   {
     // the window is a subset of the 3x3x3 block around the query's own cell: one load decides emptiness
-    q.active = __ldg( g.occ27 + ( ( (size_t)q.w.c0z * g.H + q.w.c0y ) * g.W + q.w.c0x ) ) != 0;
+    const size_t c0id = ( (size_t)q.w.c0z * g.H + q.w.c0y ) * g.W + q.w.c0x;
+    q.active = __ldg( g.occ27 + c0id ) != 0;
     q.fast = true;
+    if( q.active && allow_cull && g.ncone )
+    {
+      // one more load: the cone of ALL normals in that block; most surface-adjacent queries of a wrong pose face a
+      // single plane whose normals cannot be compatible, and end here as well
+      ConeCull cull = make_cull( g, dot_thr, q.nx, q.ny, q.nz );
+      q.active = cone_possible( g.ncone, cull, c0id, q.nx, q.ny, q.nz );
+    }
     if( q.active )
     {
       // gaps of msh_hash_grid.h:1196-1198 for the cells below (c0 - 1) and above (c0 + 1) the query's own
@@ -149,40 +191,6 @@ __device__ __forceinline__ void phase2_chunk( const GridView& g, uint32_t s, uin
   }
 }
 
-// Normal-cone culling.  Each non-empty cell stores the unit mean u of its normals and cos(alpha), alpha = the
-// largest angle between u and a normal of the cell.  A point of the cell can only be compatible with the query
-// normal n (dot >= dot_thr = cos(beta)) if angle(n, u) <= alpha + beta, so a cell with
-//   dot(n, u) < cos(alpha + beta')      (beta' = beta widened by a safety margin)
-// is skipped when looking for the nearest compatible point.  Only used when all normals involved are unit
-// length to 1e-4 (checked at rsgpu_grid_set_normals / per query); planar regions (floors, walls) — where the
-// reference wastes its whole k-list on incompatible points — have cones of a few degrees.
-struct ConeCull
-{
-  bool on;
-  float cb, sb; // cos / sin of beta'
-};
-__device__ __forceinline__ ConeCull make_cull( const GridView& g, float dot_thr, float nx, float ny, float nz )
-{
-  ConeCull c; c.on = false; c.cb = 0.f; c.sb = 1.f;
-  float n2 = nx * nx + ny * ny + nz * nz;
-  if( g.cone && dot_thr >= 1e-3f && dot_thr <= 1.0f && fabsf( n2 - 1.0f ) < 2e-4f )
-  {
-    c.on = true;
-    c.cb = dot_thr - 1e-3f;
-    c.sb = sqrtf( fmaxf( 0.0f, 1.0f - c.cb * c.cb ) ) ;
-  }
-  return c;
-}
-__device__ __forceinline__ bool cone_possible( const GridView& g, const ConeCull& c, size_t cell_id, float nx, float ny, float nz )
-{
-  if( !c.on ) { return true; }
-  float4 u = __ldg( g.cone + cell_id ); // {ux, uy, uz, cos(alpha)} (cos(alpha) < 0: no usable cone)
-  if( !( u.w > 0.0f ) ) { return true; }
-  float sa = sqrtf( fmaxf( 0.0f, 1.0f - u.w * u.w ) ) + 1e-5f;
-  float ct = u.x * nx + u.y * ny + u.z * nz;
-  return !( ct < u.w * c.cb - sa * c.sb );
-}
-
 // stage 2: all 32 lanes call this with the same (broadcast) query.  FAST: the window is a subset of the
 // 3x3x3 block around the query's own cell (always the case when radius <= cell size) and lane l < 27 owns block
 // cell (l % 3, l / 3 % 3, l / 9) relative to (lox, loy, loz); otherwise the generic enumeration in chunks of 32.
@@ -215,7 +223,7 @@ __device__ __forceinline__ NearestHit nearest_compatible_w( const GridView& g, c
       const float gy = cy < w.c0y ? gly : ( cy > w.c0y ? ghy : 0.0f );
       const float gz = cz < w.c0z ? glz : ( cz > w.c0z ? ghz : 0.0f );
       gap0 = __fadd_rn( __fadd_rn( __fmul_rn( gz, gz ), __fmul_rn( gy, gy ) ), __fmul_rn( gx, gx ) );
-      if( s0 < t0 && gap0 < r2f ) { possible0 = cone_possible( g, cull, id, nx, ny, nz ); }
+      if( s0 < t0 && gap0 < r2f ) { possible0 = cone_possible( g.cone, cull, id, nx, ny, nz ); }
     }
   }
   else { window_cell( g, w, lane, s0, t0, gap0 ); }
@@ -272,7 +280,7 @@ __device__ __forceinline__ NearestHit nearest_compatible_batch( const GridView& 
                                                                 float dot_thr, int k, unsigned long long* counts )
 {
   const int lane = threadIdx.x & 31;
-  lane_query_setup( g, radius, q, valid );
+  lane_query_setup( g, radius, dot_thr, !COUNT, q, valid );
   NearestHit mine; mine.found = false; mine.d2 = 0.f; mine.dot = 0.f; mine.pos = 0;
   if( COUNT )
   {

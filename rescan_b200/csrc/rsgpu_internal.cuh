@@ -83,6 +83,7 @@ struct GridView
   const uint32_t* __restrict__ cell_start;
   const uint32_t* __restrict__ occ27; // points in the 3x3x3 block of cells centred on each cell (0 = a query there sees nothing)
   const float4* __restrict__ cone;    // per cell {unit mean normal, cos(max angle to it)}; nullptr when normals are not unit
+  const float4* __restrict__ ncone;   // the same for all normals in the 3x3x3 block around each cell
   float mnx, mny, mnz;
   int W, H, D;
   double cell, inv_cell;
@@ -96,13 +97,14 @@ struct rsgpu_grid
   rs::DevBuf<uint32_t> cell_start;
   rs::DevBuf<uint32_t> occ27;
   rs::DevBuf<float4> cone;
+  rs::DevBuf<float4> ncone;
   bool has_cone = false;
   bool has_normals = false;
   rsgpu_grid_info_t info;
   GridView view() const
   {
     GridView v;
-    v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p; v.occ27 = occ27.p; v.cone = ( has_normals && has_cone ) ? cone.p : nullptr;
+    v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p; v.occ27 = occ27.p; v.cone = ( has_normals && has_cone ) ? cone.p : nullptr; v.ncone = v.cone ? ncone.p : nullptr;
     v.mnx = info.min_pt[0]; v.mny = info.min_pt[1]; v.mnz = info.min_pt[2];
     v.W = (int)info.width; v.H = (int)info.height; v.D = (int)info.depth;
     v.cell = info.cell_size; v.inv_cell = info.inv_cell_size; v.n_pts = (int)info.n_pts;

@@ -15,6 +15,7 @@
 // tolerance stated in tests (1e-5 m / 1e-5 rad), not bit for bit.
 #include "rsgpu_internal.cuh"
 #include "nearest.cuh"
+#include "nearest_group.cuh"
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -27,6 +28,7 @@ namespace
 constexpr int ICP_THREADS = 256;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int ICP_MAX_NV = 32;
+constexpr int ICP_G = 4;       // lanes per correspondence search (nearest_group.cuh)
 
 struct IcpShared
 {
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
   __shared__ IcpShared sh;
   extern __shared__ float tile[]; // EXACT: ICP_THREADS * TILE_LD floats
   __shared__ float fout[32];
+  __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
+  __shared__ unsigned char s_slot[ICP_WARPS][32];
   __shared__ double dout[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* cq = scratch_q + blk.scratch_off;  // {q, d2}
@@ -218,12 +222,13 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
     const float max_dist = sh.max_dist;
     const double radius = (double)max_dist;
     const float r2f = (float)__dmul_rn( radius, radius );
-    // ---- (A) correspondences (icp.h:339-391): one warp per object point
+    // ---- (A) correspondences (icp.h:339-391): 32 object points per warp batch, searched 8 at a time by 4-lane groups
     for( int ib = warp * 32; ib < c1n; ib += ICP_WARPS * 32 )
     {
       const int i = ib + lane;
       const bool valid = i < c1n;
       LaneQuery q;
+      q.px = q.py = q.pz = q.nx = q.ny = q.nz = 0.f;
       if( valid )
       {
         float ax, ay, az, bx, by, bz;
@@ -232,13 +237,35 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
         xf_apply( sh.M, ax, ay, az, 1.0f, q.px, q.py, q.pz );
         xf_apply( sh.M, bx, by, bz, 0.0f, q.nx, q.ny, q.nz );
       }
-      NearestHit h = nearest_compatible_batch<false>( g, q, valid, radius, r2f, dot_thr, 16, nullptr );
+      const rsg::Stage1 s1 = rsg::stage1_test( g, radius, dot_thr, true, q.px, q.py, q.pz, q.nx, q.ny, q.nz, valid );
+      const bool fastq = s1.active && s1.fast, slowq = s1.active && !s1.fast;
+      const unsigned fastm = __ballot_sync( RS_FULL, fastq );
+      const int rank = __popc( fastm & ( ( 1u << lane ) - 1u ) );
+      if( fastq ) { s_slot[warp][rank] = (unsigned char)lane; }
+      __syncwarp();
+      auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz ) -> bool {
+        const int src = s_slot[warp][r];
+        px = __shfl_sync( RS_FULL, q.px, src ); py = __shfl_sync( RS_FULL, q.py, src ); pz = __shfl_sync( RS_FULL, q.pz, src );
+        nx = __shfl_sync( RS_FULL, q.nx, src ); ny = __shfl_sync( RS_FULL, q.ny, src ); nz = __shfl_sync( RS_FULL, q.nz, src );
+        return true;
+      };
+      const NearestHit hr = rsg::group_round<ICP_G>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, s_cand[warp] );
+      // lane L of the round holds the result of the query with rank L
+      NearestHit h;
+      h.d2 = __shfl_sync( RS_FULL, hr.d2, rank ); h.dot = __shfl_sync( RS_FULL, hr.dot, rank );
+      h.pos = __shfl_sync( RS_FULL, hr.pos, rank ); h.found = __shfl_sync( RS_FULL, (int)hr.found, rank ) != 0 && fastq;
+      if( __any_sync( RS_FULL, slowq ) )
+      {
+        NearestHit hs = nearest_compatible_batch<false>( g, q, slowq, radius, r2f, dot_thr, 16, nullptr );
+        if( slowq ) { h = hs; }
+      }
       if( valid )
       {
         cq[i] = make_float4( q.px, q.py, q.pz, h.d2 );
         float dot = h.dot > 0.0f ? h.dot : 0.0f;
         cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
       }
+      __syncwarp();
     }
     __syncthreads();
     // ---- (B1) statistics of the squared distances (icp.h:394-396; msh_std.h:1778-1824)

@@ -11,11 +11,13 @@
 // storage exist on the GPU.  The fp64 exp/acos of 32 consecutive points are evaluated lane-parallel.
 #include "rsgpu_internal.cuh"
 #include "nearest.cuh"
+#include "nearest_group.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 using namespace rs;
@@ -101,6 +103,114 @@ __global__ void __launch_bounds__( 128 ) score_kernel( GridView g, const float* 
   if( lane == 0 ) { partial[pose * n_split + split] = sum; }
 }
 
+// ---------------------------------------------------------------------------------------------- group kernel
+// The production scorer.  One warp per (pose, point chunk), three passes over its points:
+//   A  lane-parallel: transform, cell window, 3x3x3 occupancy + block normal-cone test (rsg::stage1_test); the points
+//      that can have a compatible neighbour at all are compacted, in point order, into a per-warp list in shared memory;
+//   B  the listed points are searched 8 at a time by 4-lane groups (nearest_group.cuh), 32 per round;
+//   C  per round the fp64 acos / exp terms of the 32 results are evaluated lane-parallel and summed in point order.
+// Bound pruning (prune_cnt >= 0, propose only): every term is <= 1, so a pose whose number of still-possible
+// contributions is below threshold * N can never be emitted by mgs__initial_pose_proposals (its score is reported
+// as 0, which never wins the per-translation arg-max and never passes the threshold: pose_proposal.cpp:217-243).
+constexpr int SC_WARPS = 4;
+constexpr int SC_LIST_CAP = 1024;
+
+template <bool GRID, int SC_G, int MINB>
+__global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridView g, const float* __restrict__ obj_pos, const float* __restrict__ obj_nor,
+                                                                   int n_obj, PoseSource ps, long long n_poses, int n_split, int chunk,
+                                                                   ScoreParams sp, double prune_cnt, double* __restrict__ partial )
+{
+  __shared__ uint4 s_cand[SC_WARPS][rsg::GroupCfg<SC_G>::CAND_WORDS];
+  __shared__ uint16_t s_list[SC_WARPS][SC_LIST_CAP];
+  __shared__ float s_m[SC_WARPS][16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long warp = ( blockIdx.x * (long long)blockDim.x + threadIdx.x ) >> 5;
+  if( warp >= n_poses * n_split ) { return; }
+  long long pose = warp / n_split;
+  int split = (int)( warp % n_split );
+  if( ps.gate && !( __ldg( ps.gate + pose ) > 0.0f ) ) { return; }
+
+  // the pose lives in shared memory (16 registers less per thread; reads are warp broadcasts)
+  float* m = s_m[wib];
+  if( lane < 16 )
+  {
+    if( GRID )
+    {
+      long long t = pose / ps.n_rot; int r = (int)( pose % ps.n_rot );
+      m[lane] = lane < 12 ? __ldg( ps.rots + 16 * (size_t)r + lane ) : ( lane < 15 ? __ldg( ps.trans + 3 * t + ( lane - 12 ) ) : 1.0f );
+    }
+    else { m[lane] = __ldg( ps.xforms + 16 * (size_t)pose + lane ); }
+  }
+  __syncwarp();
+  uint16_t* list = s_list[wib];
+  uint4* cand = s_cand[wib];
+  const int i0 = split * chunk, i1 = min( n_obj, i0 + chunk );
+
+  // ---- pass A: which points can contribute at all (pose_proposal.cpp:106-112 + the search's cell window)
+  int n_list = 0;
+  for( int ib = i0; ib < i1; ib += 32 )
+  {
+    const int i = ib + lane;
+    const bool valid = i < i1;
+    float px = 0.f, py = 0.f, pz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+    if( valid )
+    {
+      xf_apply( m, __ldg( obj_pos + 3 * (size_t)i ), __ldg( obj_pos + 3 * (size_t)i + 1 ), __ldg( obj_pos + 3 * (size_t)i + 2 ), 1.0f, px, py, pz );
+      xf_apply( m, __ldg( obj_nor + 3 * (size_t)i ), __ldg( obj_nor + 3 * (size_t)i + 1 ), __ldg( obj_nor + 3 * (size_t)i + 2 ), 0.0f, nx, ny, nz );
+    }
+    const rsg::Stage1 s1 = rsg::stage1_test( g, sp.radius, sp.dot_thr, true, px, py, pz, nx, ny, nz, valid );
+    const unsigned bal = __ballot_sync( RS_FULL, s1.active );
+    if( s1.active ) { list[n_list + __popc( bal & ( ( 1u << lane ) - 1u ) )] = (uint16_t)( ( i - i0 ) | ( s1.fast ? 0 : 0x8000 ) ); }
+    n_list += __popc( bal );
+  }
+  __syncwarp();
+
+  double sum = 0.0;
+  bool pruned = prune_cnt >= 0.0 && (double)n_list < prune_cnt;
+  int n_found = 0;
+  for( int base = 0; base < n_list && !pruned; base += 32 )
+  {
+    // every remaining listed point contributes at most 1
+    if( prune_cnt >= 0.0 && (double)( n_found + ( n_list - base ) ) < prune_cnt ) { pruned = true; break; }
+    const int n_round = min( 32, n_list - base );
+    // ---- pass B: the searches of this round (:115-148)
+    auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz ) -> bool {
+      const int e = list[base + r];
+      const int i = i0 + ( e & 0x7fff );
+      xf_apply( m, __ldg( obj_pos + 3 * (size_t)i ), __ldg( obj_pos + 3 * (size_t)i + 1 ), __ldg( obj_pos + 3 * (size_t)i + 2 ), 1.0f, px, py, pz );
+      xf_apply( m, __ldg( obj_nor + 3 * (size_t)i ), __ldg( obj_nor + 3 * (size_t)i + 1 ), __ldg( obj_nor + 3 * (size_t)i + 2 ), 0.0f, nx, ny, nz );
+      return ( e & 0x8000 ) == 0;
+    };
+    NearestHit h = rsg::group_round<SC_G>( g, n_round, query_of, sp.radius, sp.r2f, sp.dot_thr, sp.k, cand );
+    // windows the group path cannot take (last-bit cases, radius > cell size): generic warp-cooperative search
+    const bool slow = lane < n_round && ( list[base + lane] & 0x8000 ) != 0;
+    if( __any_sync( RS_FULL, slow ) )
+    {
+      LaneQuery q;
+      if( slow ) { query_of( lane, q.px, q.py, q.pz, q.nx, q.ny, q.nz ); }
+      NearestHit hs = nearest_compatible_batch<false>( g, q, slow, sp.radius, sp.r2f, sp.dot_thr, sp.k, nullptr );
+      if( slow ) { h = hs; }
+    }
+    // ---- pass C: the reference's per-point term (:149-152), lane-parallel in fp64, summed in point order
+    double term = 0.0;
+    if( h.found )
+    {
+      double angle = acos( (double)fmaxf( h.dot, 0.0f ) );
+      double nc = exp( -( angle * angle ) / ( 2.0 * 0.5 * 0.5 ) );
+      double dc = exp( -(double)h.d2 / sp.inv_two_sigma_sq_den );
+      term = 0.05 * nc + ( 1.0 - 0.05 ) * dc;
+    }
+    unsigned mask = __ballot_sync( RS_FULL, h.found );
+    n_found += __popc( mask );
+    while( mask )
+    {
+      int src = __ffs( mask ) - 1; mask &= mask - 1;
+      sum += __shfl_sync( RS_FULL, term, src );
+    }
+  }
+  if( lane == 0 ) { partial[pose * n_split + split] = pruned ? 0.0 : sum; }
+}
+
 __global__ void finalize_kernel( const double* __restrict__ partial, long long n_poses, int n_split, int n_obj,
                                  const float* __restrict__ gate, float* __restrict__ scores )
 {
@@ -145,8 +255,9 @@ ScoreParams make_params( float radius, int k )
 }
 
 // core launcher: scores (device) [n_poses]; gate may alias scores
+// prune_thr > 0 (propose only): poses that provably cannot score above prune_thr are reported as 0
 int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const PoseSource& ps, bool grid_mode, long long n_poses,
-                  int k, float radius, float* d_scores, unsigned long long* d_counts )
+                  int k, float radius, float* d_scores, unsigned long long* d_counts, float prune_thr = 0.0f )
 {
   if( n_poses <= 0 ) { return RSGPU_OK; }
   if( !scene->has_normals ) { return fail( RSGPU_ERR_INVALID, "rsgpu score: the scene grid has no normals (rsgpu_grid_set_normals)" ); }
@@ -164,8 +275,13 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
     n_split = (int)( s < max_s ? s : max_s );
     if( n_split < 1 ) { n_split = 1; }
   }
+  // RSGPU_SCORE_IMPL=coop selects the warp-per-query kernel (the census pass always uses it)
+  static const bool coop_env = []() { const char* e = getenv( "RSGPU_SCORE_IMPL" ); return e && strcmp( e, "coop" ) == 0; }();
+  const bool group_impl = !d_counts && !coop_env;
+  if( group_impl && n_split < ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP ) { n_split = ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP; }
   int chunk = ( ( obj->n + n_split - 1 ) / n_split + 31 ) / 32 * 32;
   n_split = ( obj->n + chunk - 1 ) / chunk;
+  const double prune_cnt = ( prune_thr > 0.0f && n_split == 1 ) ? (double)prune_thr * (double)obj->n / 1.000001 : -1.0;
   DevBuf<double> partial;
   RS_CUDA( partial.alloc( (size_t)n_poses * n_split ) );
   long long warps = n_poses * n_split;
@@ -174,7 +290,23 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
   GridView g = scene->view();
   {
     ProfScope prof( grid_mode ? "score_dense" : "score" );
-    if( d_counts )
+    if( group_impl )
+    {
+      // lanes per query and resident blocks per SM (register cap) of the group kernel; the defaults are the measured best
+      static const int cfg_g = []() { const char* e = getenv( "RSGPU_SCORE_G" ); return e ? atoi( e ) : 4; }();
+      static const int cfg_b = []() { const char* e = getenv( "RSGPU_SCORE_MINB" ); return e ? atoi( e ) : 6; }();
+#define RS_SCORE_G_LAUNCH( GRIDM, GG, MB ) \
+      score_kernel_g<GRIDM, GG, MB><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p )
+#define RS_SCORE_G_PICK( GRIDM ) \
+      do { \
+        if( cfg_g == 8 ) { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 8 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 6 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 8, 4 ); } } \
+        else { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 8 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 4 ); } } \
+      } while( 0 )
+      if( grid_mode ) { RS_SCORE_G_PICK( true ); } else { RS_SCORE_G_PICK( false ); }
+#undef RS_SCORE_G_PICK
+#undef RS_SCORE_G_LAUNCH
+    }
+    else if( d_counts )
     {
       if( grid_mode ) { score_kernel<true, true><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, d_counts ); }
       else { score_kernel<false, true><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, d_counts ); }
@@ -347,8 +479,13 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   DevBuf<float> dr, dt, ds;
   RS_TRY( upload_pose_grid( rots, n_rot, trans, n_trans, dr, dt ) );
   RS_CUDA( ds.alloc( (size_t)n ) );
-  // level 4: dense search
-  RS_TRY( rsgpu_score_pose_grid_dev( o4, scene, dr.p, n_rot, dt.p, n_trans, opts.max_n_neigh, opts.radius, ds.p ) );
+  // level 4: dense search.  Scores that provably cannot exceed the level's threshold are not resolved (reported as
+  // 0): they can neither be emitted nor change which rotation is emitted (RSGPU_PRUNE=0 resolves every score).
+  {
+    static const bool no_prune = []() { const char* e = getenv( "RSGPU_PRUNE" ); return e && strcmp( e, "0" ) == 0; }();
+    PoseSource ps; memset( &ps, 0, sizeof( ps ) ); ps.rots = dr.p; ps.trans = dt.p; ps.n_rot = n_rot;
+    RS_TRY( score_launch( o4, scene, ps, true, n, opts.max_n_neigh, opts.radius, ds.p, nullptr, no_prune ? 0.0f : opts.thresholds[0] ) );
+  }
   DevBuf<int> flag, offs, best_r; DevBuf<float> best_s;
   RS_CUDA( flag.alloc( n_trans ) ); RS_CUDA( offs.alloc( n_trans ) ); RS_CUDA( best_r.alloc( n_trans ) ); RS_CUDA( best_s.alloc( n_trans ) );
   unsigned tb = (unsigned)( ( n_trans + 255 ) / 256 );

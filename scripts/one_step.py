@@ -1,6 +1,11 @@
-"""one (or a few) pose_proposal steps of a named workload, for ncu captures:  python scripts/one_step.py [C2] [n_steps]"""
+"""a few pose_proposal steps of a named workload (ncu captures, A/B runs of kernel variants via RSGPU_* env vars):
+   python scripts/one_step.py [C2] [n_steps]   -> per-kernel ms/step and a digest of the proposals"""
+import hashlib
 import os
 import sys
+import time
+
+import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rescan_b200 import api, pipeline  # noqa: E402
@@ -10,7 +15,20 @@ n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 api.set_device(0)
 scene, rotations, translations = pipeline.make_workload(name)
 models = pipeline.upload_objects(scene.objects)
+args = ((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rotations, translations)
+if n_steps > 1:
+    pipeline.run_step(*args, top_k=64)  # warm-up
+api.profile_reset()
+api.profile_enable(True)
+t0 = time.perf_counter()
 for _ in range(n_steps):
-    res = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rotations,
-                            translations, top_k=64)
-print("evaluations", res.n_evaluations, "launches", api.launch_count())
+    res = pipeline.run_step(*args, top_k=64)
+dt = (time.perf_counter() - t0) / n_steps
+api.profile_enable(False)
+h = hashlib.sha1()
+for p, i in zip(res.proposals, res.pose_ids):
+    h.update(np.ascontiguousarray(p).tobytes())
+    h.update(np.ascontiguousarray(i).tobytes())
+prof = {n: round(api.profile_get(n)[0] / n_steps, 3) for n in ("grid_build", "score_dense", "score", "icp")}
+env = {k: v for k, v in os.environ.items() if k.startswith("RSGPU_")}
+print(f"env {env} wall {dt * 1e3:.2f} ms/step kernels {prof} evaluations {res.n_evaluations} launches {api.launch_count()} digest {h.hexdigest()[:12]}")

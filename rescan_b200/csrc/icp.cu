@@ -20,6 +20,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 
 using namespace rs;
 
@@ -152,7 +153,7 @@ __device__ void ldlt_solve6( double A[6][6], const double* b, double* x )
 // correspondence hold zeros, which leave a float sum unchanged.
 constexpr int TILE_LD = 33;
 
-template <int NV, class TermFn>
+template <int NV, bool WITH_F64, class TermFn>
 __device__ __forceinline__ void ordered_sums( int n, TermFn term_fn, float* tile, float* fout, double* dout )
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,24 +167,26 @@ __device__ __forceinline__ void ordered_sums( int n, TermFn term_fn, float* tile
 #pragma unroll
     for( int v = 0; v < NV; ++v ) { tile[tid * TILE_LD + v] = t[v]; }
     __syncthreads();
+    const int rows = min( ICP_THREADS, n - base );
     if( warp == 0 && lane < NV )
     {
-      const int rows = min( ICP_THREADS, n - base );
 #pragma unroll 8
-      for( int r = 0; r < rows; ++r )
-      {
-        float x = tile[r * TILE_LD + lane];
-        fa = __fadd_rn( fa, x );
-        da = __dadd_rn( da, (double)x );
-      }
+      for( int r = 0; r < rows; ++r ) { fa = __fadd_rn( fa, tile[r * TILE_LD + lane] ); }
+    }
+    else if( WITH_F64 && warp == 1 && lane < 2 )
+    {
+      // the two fp64 sums of the error term (icp.h:250-253: columns NV-2, NV-1) run beside the float sums on another warp
+#pragma unroll 8
+      for( int r = 0; r < rows; ++r ) { da = __dadd_rn( da, (double)tile[r * TILE_LD + ( NV - 2 + lane )] ); }
     }
     __syncthreads();
   }
-  if( warp == 0 ) { fout[lane] = fa; dout[lane] = da; }
+  if( warp == 0 ) { fout[lane] = fa; }
+  if( WITH_F64 && warp == 1 && lane < 2 ) { dout[NV - 2 + lane] = da; }
   __syncthreads();
 }
 
-// one entry per thread block (= per starting pose): which object it aligns and where its scratch lives
+// what one alignment needs: which object it aligns and where its scratch lives
 struct IcpBlock
 {
   const float* p1;
@@ -192,6 +195,243 @@ struct IcpBlock
   unsigned long long scratch_off;
 };
 
+// (A) correspondences of one batch of 32 object points (icp.h:339-391), searched 8 at a time by 4-lane groups
+__device__ __forceinline__ void icp_correspond_batch( const GridView& g, const float* __restrict__ T, const float* __restrict__ M,
+                                                      const float* __restrict__ p1, const float* __restrict__ n1, int c1n, int ib,
+                                                      double radius, float r2f, float dot_thr, float4* __restrict__ cq, uint2* __restrict__ cm,
+                                                      uint4* __restrict__ cand, unsigned char* __restrict__ slot )
+{
+  const int lane = threadIdx.x & 31;
+  const int i = ib + lane;
+  const bool valid = i < c1n;
+  LaneQuery q;
+  q.px = q.py = q.pz = q.nx = q.ny = q.nz = 0.f;
+  if( valid )
+  {
+    float ax, ay, az, bx, by, bz;
+    xf_apply( T, __ldg( p1 + 3 * (size_t)i ), __ldg( p1 + 3 * (size_t)i + 1 ), __ldg( p1 + 3 * (size_t)i + 2 ), 1.0f, ax, ay, az );
+    xf_apply( T, __ldg( n1 + 3 * (size_t)i ), __ldg( n1 + 3 * (size_t)i + 1 ), __ldg( n1 + 3 * (size_t)i + 2 ), 0.0f, bx, by, bz );
+    xf_apply( M, ax, ay, az, 1.0f, q.px, q.py, q.pz );
+    xf_apply( M, bx, by, bz, 0.0f, q.nx, q.ny, q.nz );
+  }
+  const rsg::Stage1 s1 = rsg::stage1_test( g, radius, dot_thr, true, q.px, q.py, q.pz, q.nx, q.ny, q.nz, valid );
+  const bool fastq = s1.active && s1.fast, slowq = s1.active && !s1.fast;
+  const unsigned fastm = __ballot_sync( RS_FULL, fastq );
+  const int rank = __popc( fastm & ( ( 1u << lane ) - 1u ) );
+  if( fastq ) { slot[rank] = (unsigned char)lane; }
+  __syncwarp();
+  auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz ) -> bool {
+    const int src = slot[r];
+    px = __shfl_sync( RS_FULL, q.px, src ); py = __shfl_sync( RS_FULL, q.py, src ); pz = __shfl_sync( RS_FULL, q.pz, src );
+    nx = __shfl_sync( RS_FULL, q.nx, src ); ny = __shfl_sync( RS_FULL, q.ny, src ); nz = __shfl_sync( RS_FULL, q.nz, src );
+    return true;
+  };
+  const NearestHit hr = rsg::group_round<ICP_G>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, cand );
+  // lane L of the round holds the result of the query with rank L
+  NearestHit h;
+  h.d2 = __shfl_sync( RS_FULL, hr.d2, rank ); h.dot = __shfl_sync( RS_FULL, hr.dot, rank );
+  h.pos = __shfl_sync( RS_FULL, hr.pos, rank ); h.found = __shfl_sync( RS_FULL, (int)hr.found, rank ) != 0 && fastq;
+  if( __any_sync( RS_FULL, slowq ) )
+  {
+    NearestHit hs = nearest_compatible_batch<false>( g, q, slowq, radius, r2f, dot_thr, 16, nullptr );
+    if( slowq ) { h = hs; }
+  }
+  if( valid )
+  {
+    cq[i] = make_float4( q.px, q.py, q.pz, h.d2 );
+    float dot = h.dot > 0.0f ? h.dot : 0.0f;
+    cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
+  }
+  __syncwarp();
+}
+
+// (B) + (C) of one iteration for the block's alignment: statistics, centroids, normal equations, solve, compose.
+// Returns false when the reference leaves its loop before the update (no correspondences / no weight, icp.h:453-468);
+// otherwise sh.T, sh.err, sh.steps, sh.max_dist are updated and sh.stop is set when the stopping rule fires.
+template <bool EXACT>
+__device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const float4* __restrict__ cq, const uint2* __restrict__ cm, int it,
+                                            IcpShared& sh, float* tile, float* fout, double* dout )
+{
+  const int tid = threadIdx.x;
+  const float max_dist = sh.max_dist;
+  // ---- (B1) statistics of the squared distances (icp.h:394-396; msh_std.h:1778-1824)
+  int nc; float sum_d, sum_dd;
+  if( EXACT )
+  {
+    int mine = 0;
+    for( int i = tid; i < c1n; i += ICP_THREADS ) { mine += cm[i].x != 0xffffffffu; }
+    {
+      double v[1] = { (double)mine };
+      block_reduce<1>( v, sh );
+      nc = (int)sh.out[0];
+    }
+    ordered_sums<2, false>( c1n, [&]( int i, float* t ) {
+      if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; t[0] = d; t[1] = __fmul_rn( d, d ); }
+    }, tile, fout, dout );
+    sum_d = fout[0]; sum_dd = fout[1];
+  }
+  else
+  {
+    double v[3] = { 0, 0, 0 };
+    for( int i = tid; i < c1n; i += ICP_THREADS )
+    {
+      if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; v[0] += 1.0; v[1] += (double)d; v[2] += (double)__fmul_rn( d, d ); }
+    }
+    block_reduce<3>( v, sh );
+    nc = (int)sh.out[0]; sum_d = (float)sh.out[1]; sum_dd = (float)sh.out[2];
+  }
+  if( nc == 0 ) { return false; } // (icp.h:453-457)
+  const float mean = __fdiv_rn( sum_d, (float)nc );
+  const float sd = (float)sqrt( (double)__fsub_rn( __fdiv_rn( sum_dd, (float)nc ), __fmul_rn( mean, mean ) ) );
+  const bool reject = (double)sd > 0.000001;
+  const float cut = __fmul_rn( 2.5f, sd );
+  __syncthreads();
+  // weight of correspondence i (icp.h:387, 397-402)
+  auto weight = [&]( const float4& q, const uint2& m ) {
+    float w = __fmul_rn( __fsub_rn( 1.0f, __fdiv_rn( q.w, max_dist ) ), __uint_as_float( m.y ) );
+    if( reject && q.w > cut ) { w = 0.0f; }
+    return w;
+  };
+  // ---- (B2) weighted centroids (icp.h:137-148)
+  float s7[7];
+  if( EXACT )
+  {
+    ordered_sums<7, false>( c1n, [&]( int i, float* t ) {
+      uint2 m = cm[i];
+      if( m.x == 0xffffffffu ) { return; }
+      float4 q = cq[i];
+      float w = weight( q, m );
+      float4 p2 = __ldg( g.recs + m.x );
+      t[0] = w;
+      t[1] = __fmul_rn( q.x, w ); t[2] = __fmul_rn( q.y, w ); t[3] = __fmul_rn( q.z, w );
+      t[4] = __fmul_rn( p2.x, w ); t[5] = __fmul_rn( p2.y, w ); t[6] = __fmul_rn( p2.z, w );
+    }, tile, fout, dout );
+#pragma unroll
+    for( int j = 0; j < 7; ++j ) { s7[j] = fout[j]; }
+  }
+  else
+  {
+    double v[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    for( int i = tid; i < c1n; i += ICP_THREADS )
+    {
+      uint2 m = cm[i];
+      if( m.x == 0xffffffffu ) { continue; }
+      float4 q = cq[i];
+      float w = weight( q, m );
+      float4 p2 = __ldg( g.recs + m.x );
+      v[0] += (double)w;
+      v[1] += (double)__fmul_rn( q.x, w ); v[2] += (double)__fmul_rn( q.y, w ); v[3] += (double)__fmul_rn( q.z, w );
+      v[4] += (double)__fmul_rn( p2.x, w ); v[5] += (double)__fmul_rn( p2.y, w ); v[6] += (double)__fmul_rn( p2.z, w );
+    }
+    block_reduce<7>( v, sh );
+#pragma unroll
+    for( int j = 0; j < 7; ++j ) { s7[j] = (float)sh.out[j]; }
+  }
+  const float tw = s7[0];
+  if( (double)tw <= 1e-7 ) { return false; } // (icp.h:459-468)
+  const float itw = __fdiv_rn( 1.0f, tw ); // msh_vec3_scalar_div multiplies by the reciprocal (msh_vec_math.h:754-758)
+  const float c1x = __fmul_rn( s7[1], itw ), c1y = __fmul_rn( s7[2], itw ), c1z = __fmul_rn( s7[3], itw );
+  const float c2x = __fmul_rn( s7[4], itw ), c2y = __fmul_rn( s7[5], itw ), c2z = __fmul_rn( s7[6], itw );
+  __syncthreads();
+  // ---- (B3) normal equations (icp.h:226-252): TL = sum w c c^T, TR = sum w c n^T, BR = sum w n n^T, b = sum w [c;n] (d.n)
+  // 29 terms per correspondence: TL (6 unique), TR (9), BR (6 unique), b (6), w (d.n)^2, w
+  auto terms29 = [&]( int i, float* t ) -> bool {
+    uint2 m = cm[i];
+    if( m.x == 0xffffffffu ) { return false; }
+    float4 q4 = cq[i];
+    float w = weight( q4, m );
+    float4 p2 = __ldg( g.recs + m.x ), nn = __ldg( g.nrm + m.x );
+    float px = __fsub_rn( q4.x, c1x ), py = __fsub_rn( q4.y, c1y ), pz = __fsub_rn( q4.z, c1z );
+    float qx = __fsub_rn( p2.x, c2x ), qy = __fsub_rn( p2.y, c2y ), qz = __fsub_rn( p2.z, c2z );
+    float dx = __fsub_rn( px, qx ), dy = __fsub_rn( py, qy ), dz = __fsub_rn( pz, qz );
+    float c[3], n[3] = { nn.x, nn.y, nn.z };
+    c[0] = __fsub_rn( __fmul_rn( py, nn.z ), __fmul_rn( pz, nn.y ) );
+    c[1] = __fsub_rn( __fmul_rn( pz, nn.x ), __fmul_rn( px, nn.z ) );
+    c[2] = __fsub_rn( __fmul_rn( px, nn.y ), __fmul_rn( py, nn.x ) );
+    float dn = dot3_exact( dx, dy, dz, nn.x, nn.y, nn.z );
+    int o = 0;
+#pragma unroll
+    for( int col = 0; col < 3; ++col )
+#pragma unroll
+      for( int row = col; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( c[row], c[col] ), w ); }
+#pragma unroll
+    for( int col = 0; col < 3; ++col )
+#pragma unroll
+      for( int row = 0; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( c[row], n[col] ), w ); }
+#pragma unroll
+    for( int col = 0; col < 3; ++col )
+#pragma unroll
+      for( int row = col; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( n[row], n[col] ), w ); }
+#pragma unroll
+    for( int a = 0; a < 3; ++a ) { t[21 + a] = __fmul_rn( __fmul_rn( w, c[a] ), dn ); t[24 + a] = __fmul_rn( __fmul_rn( w, n[a] ), dn ); }
+    t[27] = __fmul_rn( __fmul_rn( w, dn ), dn );
+    t[28] = w;
+    return true;
+  };
+  if( EXACT )
+  {
+    ordered_sums<29, true>( c1n, [&]( int i, float* t ) { terms29( i, t ); }, tile, fout, dout );
+    if( tid < 27 ) { sh.out[tid] = (double)fout[tid]; }
+    if( tid == 27 || tid == 28 ) { sh.out[tid] = dout[tid]; }
+    __syncthreads();
+  }
+  else
+  {
+    double v[29];
+#pragma unroll
+    for( int j = 0; j < 29; ++j ) { v[j] = 0.0; }
+    for( int i = tid; i < c1n; i += ICP_THREADS )
+    {
+      float t[29];
+      if( terms29( i, t ) )
+      {
+#pragma unroll
+        for( int j = 0; j < 29; ++j ) { v[j] += (double)t[j]; }
+      }
+    }
+    block_reduce<29>( v, sh );
+  }
+  // ---- (C) solve + compose (icp.h:253-295), one thread
+  if( tid == 0 )
+  {
+    const double* s = sh.out;
+    float TL[3][3], TR[3][3], BR[3][3]; // [col][row]
+    int o = 0;
+    for( int col = 0; col < 3; ++col ) for( int row = col; row < 3; ++row ) { TL[col][row] = TL[row][col] = (float)s[o++]; }
+    for( int col = 0; col < 3; ++col ) for( int row = 0; row < 3; ++row ) { TR[col][row] = (float)s[o++]; }
+    for( int col = 0; col < 3; ++col ) for( int row = col; row < 3; ++row ) { BR[col][row] = BR[row][col] = (float)s[o++]; }
+    float err = (float)sqrt( __ddiv_rn( s[27], s[28] ) );
+    double A[6][6], rhs[6], x[6] = { 0, 0, 0, 0, 0, 0 };
+    for( int r = 0; r < 3; ++r )
+      for( int c = 0; c < 3; ++c )
+      {
+        A[r][c] = TL[c][r]; A[r][3 + c] = TR[c][r];
+        A[3 + r][c] = TR[r][c]; A[3 + r][3 + c] = BR[c][r];
+      }
+    for( int a = 0; a < 6; ++a ) { rhs[a] = -(double)(float)s[21 + a]; }
+    ldlt_solve6( A, rhs, x );
+    float T[16];
+    for( int i = 0; i < 16; ++i ) { T[i] = ( i % 5 == 0 ) ? 1.0f : 0.0f; }
+    xf_translate( T, c1x, c1y, c1z );
+    xf_translate( T, (float)x[3], (float)x[4], (float)x[5] );
+    xf_rotate( T, (float)x[0], 1.0f, 0.0f, 0.0f );
+    xf_rotate( T, (float)x[1], 0.0f, 1.0f, 0.0f );
+    xf_rotate( T, (float)x[2], 0.0f, 0.0f, 1.0f );
+    xf_translate( T, -c1x, -c1y, -c1z );
+    float Tn[16];
+    xf_mul( T, sh.T, Tn );
+    for( int i = 0; i < 16; ++i ) { sh.T[i] = Tn[i]; }
+    sh.err = err; sh.steps += 1;
+    float delta = fabsf( __fsub_rn( sh.prev_err, err ) );
+    if( it > 5 && (double)delta < 1e-5 ) { sh.stop = 1; }
+    double shrunk = __dmul_rn( (double)max_dist, 0.95 );
+    sh.max_dist = (float)( shrunk > 0.05 ? shrunk : 0.05 );
+  }
+  __syncthreads();
+  return true;
+}
+
+// ---- variant 1: one thread block per alignment, resident for all its iterations (RSGPU_ICP_IMPL=block)
 template <bool EXACT>
 __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const IcpBlock* __restrict__ blocks,
                                                              float* __restrict__ T1_io, const float* __restrict__ T2i, float max_dist0,
@@ -200,253 +440,102 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
                                                              int* __restrict__ iters )
 {
   const IcpBlock blk = blocks[blockIdx.x];
-  const float* __restrict__ p1 = blk.p1;
-  const float* __restrict__ n1 = blk.n1;
-  const int c1n = blk.n;
   __shared__ IcpShared sh;
   extern __shared__ float tile[]; // EXACT: ICP_THREADS * TILE_LD floats
   __shared__ float fout[32];
   __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
   __shared__ unsigned char s_slot[ICP_WARPS][32];
   __shared__ double dout[32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
   float4* cq = scratch_q + blk.scratch_off;  // {q, d2}
   uint2* cm = scratch_m + blk.scratch_off;   // {recs position or ~0, dot bits}
   if( tid < 16 ) { sh.T[tid] = T1_io[16 * (size_t)b + tid]; sh.M[tid] = T2i[tid]; }
   if( tid == 0 ) { sh.max_dist = max_dist0; sh.prev_err = 1e6f; sh.err = 1e6f; sh.stop = 0; sh.steps = 0; }
   __syncthreads();
-
   for( int it = 0; it < max_iter; ++it )
   {
     if( tid == 0 ) { sh.prev_err = sh.err; }
-    const float max_dist = sh.max_dist;
-    const double radius = (double)max_dist;
+    const double radius = (double)sh.max_dist;
     const float r2f = (float)__dmul_rn( radius, radius );
-    // ---- (A) correspondences (icp.h:339-391): 32 object points per warp batch, searched 8 at a time by 4-lane groups
-    for( int ib = warp * 32; ib < c1n; ib += ICP_WARPS * 32 )
+    for( int ib = warp * 32; ib < blk.n; ib += ICP_WARPS * 32 )
     {
-      const int i = ib + lane;
-      const bool valid = i < c1n;
-      LaneQuery q;
-      q.px = q.py = q.pz = q.nx = q.ny = q.nz = 0.f;
-      if( valid )
-      {
-        float ax, ay, az, bx, by, bz;
-        xf_apply( sh.T, __ldg( p1 + 3 * (size_t)i ), __ldg( p1 + 3 * (size_t)i + 1 ), __ldg( p1 + 3 * (size_t)i + 2 ), 1.0f, ax, ay, az );
-        xf_apply( sh.T, __ldg( n1 + 3 * (size_t)i ), __ldg( n1 + 3 * (size_t)i + 1 ), __ldg( n1 + 3 * (size_t)i + 2 ), 0.0f, bx, by, bz );
-        xf_apply( sh.M, ax, ay, az, 1.0f, q.px, q.py, q.pz );
-        xf_apply( sh.M, bx, by, bz, 0.0f, q.nx, q.ny, q.nz );
-      }
-      const rsg::Stage1 s1 = rsg::stage1_test( g, radius, dot_thr, true, q.px, q.py, q.pz, q.nx, q.ny, q.nz, valid );
-      const bool fastq = s1.active && s1.fast, slowq = s1.active && !s1.fast;
-      const unsigned fastm = __ballot_sync( RS_FULL, fastq );
-      const int rank = __popc( fastm & ( ( 1u << lane ) - 1u ) );
-      if( fastq ) { s_slot[warp][rank] = (unsigned char)lane; }
-      __syncwarp();
-      auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz ) -> bool {
-        const int src = s_slot[warp][r];
-        px = __shfl_sync( RS_FULL, q.px, src ); py = __shfl_sync( RS_FULL, q.py, src ); pz = __shfl_sync( RS_FULL, q.pz, src );
-        nx = __shfl_sync( RS_FULL, q.nx, src ); ny = __shfl_sync( RS_FULL, q.ny, src ); nz = __shfl_sync( RS_FULL, q.nz, src );
-        return true;
-      };
-      const NearestHit hr = rsg::group_round<ICP_G>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, s_cand[warp] );
-      // lane L of the round holds the result of the query with rank L
-      NearestHit h;
-      h.d2 = __shfl_sync( RS_FULL, hr.d2, rank ); h.dot = __shfl_sync( RS_FULL, hr.dot, rank );
-      h.pos = __shfl_sync( RS_FULL, hr.pos, rank ); h.found = __shfl_sync( RS_FULL, (int)hr.found, rank ) != 0 && fastq;
-      if( __any_sync( RS_FULL, slowq ) )
-      {
-        NearestHit hs = nearest_compatible_batch<false>( g, q, slowq, radius, r2f, dot_thr, 16, nullptr );
-        if( slowq ) { h = hs; }
-      }
-      if( valid )
-      {
-        cq[i] = make_float4( q.px, q.py, q.pz, h.d2 );
-        float dot = h.dot > 0.0f ? h.dot : 0.0f;
-        cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
-      }
-      __syncwarp();
+      icp_correspond_batch( g, sh.T, sh.M, blk.p1, blk.n1, blk.n, ib, radius, r2f, dot_thr, cq, cm, s_cand[warp], s_slot[warp] );
     }
     __syncthreads();
-    // ---- (B1) statistics of the squared distances (icp.h:394-396; msh_std.h:1778-1824)
-    int nc; float sum_d, sum_dd;
-    if( EXACT )
-    {
-      int mine = 0;
-      for( int i = tid; i < c1n; i += ICP_THREADS ) { mine += cm[i].x != 0xffffffffu; }
-      {
-        double v[1] = { (double)mine };
-        block_reduce<1>( v, sh );
-        nc = (int)sh.out[0];
-      }
-      ordered_sums<2>( c1n, [&]( int i, float* t ) {
-        if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; t[0] = d; t[1] = __fmul_rn( d, d ); }
-      }, tile, fout, dout );
-      sum_d = fout[0]; sum_dd = fout[1];
-    }
-    else
-    {
-      double v[3] = { 0, 0, 0 };
-      for( int i = tid; i < c1n; i += ICP_THREADS )
-      {
-        if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; v[0] += 1.0; v[1] += (double)d; v[2] += (double)__fmul_rn( d, d ); }
-      }
-      block_reduce<3>( v, sh );
-      nc = (int)sh.out[0]; sum_d = (float)sh.out[1]; sum_dd = (float)sh.out[2];
-    }
-    if( nc == 0 ) { break; } // (icp.h:453-457)
-    const float mean = __fdiv_rn( sum_d, (float)nc );
-    const float sd = (float)sqrt( (double)__fsub_rn( __fdiv_rn( sum_dd, (float)nc ), __fmul_rn( mean, mean ) ) );
-    const bool reject = (double)sd > 0.000001;
-    const float cut = __fmul_rn( 2.5f, sd );
-    __syncthreads();
-    // weight of correspondence i (icp.h:387, 397-402)
-    auto weight = [&]( const float4& q, const uint2& m ) {
-      float w = __fmul_rn( __fsub_rn( 1.0f, __fdiv_rn( q.w, max_dist ) ), __uint_as_float( m.y ) );
-      if( reject && q.w > cut ) { w = 0.0f; }
-      return w;
-    };
-    // ---- (B2) weighted centroids (icp.h:137-148)
-    float s7[7];
-    if( EXACT )
-    {
-      ordered_sums<7>( c1n, [&]( int i, float* t ) {
-        uint2 m = cm[i];
-        if( m.x == 0xffffffffu ) { return; }
-        float4 q = cq[i];
-        float w = weight( q, m );
-        float4 p2 = __ldg( g.recs + m.x );
-        t[0] = w;
-        t[1] = __fmul_rn( q.x, w ); t[2] = __fmul_rn( q.y, w ); t[3] = __fmul_rn( q.z, w );
-        t[4] = __fmul_rn( p2.x, w ); t[5] = __fmul_rn( p2.y, w ); t[6] = __fmul_rn( p2.z, w );
-      }, tile, fout, dout );
-#pragma unroll
-      for( int j = 0; j < 7; ++j ) { s7[j] = fout[j]; }
-    }
-    else
-    {
-      double v[7] = { 0, 0, 0, 0, 0, 0, 0 };
-      for( int i = tid; i < c1n; i += ICP_THREADS )
-      {
-        uint2 m = cm[i];
-        if( m.x == 0xffffffffu ) { continue; }
-        float4 q = cq[i];
-        float w = weight( q, m );
-        float4 p2 = __ldg( g.recs + m.x );
-        v[0] += (double)w;
-        v[1] += (double)__fmul_rn( q.x, w ); v[2] += (double)__fmul_rn( q.y, w ); v[3] += (double)__fmul_rn( q.z, w );
-        v[4] += (double)__fmul_rn( p2.x, w ); v[5] += (double)__fmul_rn( p2.y, w ); v[6] += (double)__fmul_rn( p2.z, w );
-      }
-      block_reduce<7>( v, sh );
-#pragma unroll
-      for( int j = 0; j < 7; ++j ) { s7[j] = (float)sh.out[j]; }
-    }
-    const float tw = s7[0];
-    if( (double)tw <= 1e-7 ) { break; } // (icp.h:459-468)
-    const float itw = __fdiv_rn( 1.0f, tw ); // msh_vec3_scalar_div multiplies by the reciprocal (msh_vec_math.h:754-758)
-    const float c1x = __fmul_rn( s7[1], itw ), c1y = __fmul_rn( s7[2], itw ), c1z = __fmul_rn( s7[3], itw );
-    const float c2x = __fmul_rn( s7[4], itw ), c2y = __fmul_rn( s7[5], itw ), c2z = __fmul_rn( s7[6], itw );
-    __syncthreads();
-    // ---- (B3) normal equations (icp.h:226-252): TL = sum w c c^T, TR = sum w c n^T, BR = sum w n n^T, b = sum w [c;n] (d.n)
-    // 29 terms per correspondence: TL (6 unique), TR (9), BR (6 unique), b (6), w (d.n)^2, w
-    auto terms29 = [&]( int i, float* t ) -> bool {
-      uint2 m = cm[i];
-      if( m.x == 0xffffffffu ) { return false; }
-      float4 q4 = cq[i];
-      float w = weight( q4, m );
-      float4 p2 = __ldg( g.recs + m.x ), nn = __ldg( g.nrm + m.x );
-      float px = __fsub_rn( q4.x, c1x ), py = __fsub_rn( q4.y, c1y ), pz = __fsub_rn( q4.z, c1z );
-      float qx = __fsub_rn( p2.x, c2x ), qy = __fsub_rn( p2.y, c2y ), qz = __fsub_rn( p2.z, c2z );
-      float dx = __fsub_rn( px, qx ), dy = __fsub_rn( py, qy ), dz = __fsub_rn( pz, qz );
-      float c[3], n[3] = { nn.x, nn.y, nn.z };
-      c[0] = __fsub_rn( __fmul_rn( py, nn.z ), __fmul_rn( pz, nn.y ) );
-      c[1] = __fsub_rn( __fmul_rn( pz, nn.x ), __fmul_rn( px, nn.z ) );
-      c[2] = __fsub_rn( __fmul_rn( px, nn.y ), __fmul_rn( py, nn.x ) );
-      float dn = dot3_exact( dx, dy, dz, nn.x, nn.y, nn.z );
-      int o = 0;
-#pragma unroll
-      for( int col = 0; col < 3; ++col )
-#pragma unroll
-        for( int row = col; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( c[row], c[col] ), w ); }
-#pragma unroll
-      for( int col = 0; col < 3; ++col )
-#pragma unroll
-        for( int row = 0; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( c[row], n[col] ), w ); }
-#pragma unroll
-      for( int col = 0; col < 3; ++col )
-#pragma unroll
-        for( int row = col; row < 3; ++row ) { t[o++] = __fmul_rn( __fmul_rn( n[row], n[col] ), w ); }
-#pragma unroll
-      for( int a = 0; a < 3; ++a ) { t[21 + a] = __fmul_rn( __fmul_rn( w, c[a] ), dn ); t[24 + a] = __fmul_rn( __fmul_rn( w, n[a] ), dn ); }
-      t[27] = __fmul_rn( __fmul_rn( w, dn ), dn );
-      t[28] = w;
-      return true;
-    };
-    if( EXACT )
-    {
-      ordered_sums<29>( c1n, [&]( int i, float* t ) { terms29( i, t ); }, tile, fout, dout );
-      if( tid < 27 ) { sh.out[tid] = (double)fout[tid]; }
-      if( tid == 27 || tid == 28 ) { sh.out[tid] = dout[tid]; }
-      __syncthreads();
-    }
-    else
-    {
-      double v[29];
-#pragma unroll
-      for( int j = 0; j < 29; ++j ) { v[j] = 0.0; }
-      for( int i = tid; i < c1n; i += ICP_THREADS )
-      {
-        float t[29];
-        if( terms29( i, t ) )
-        {
-#pragma unroll
-          for( int j = 0; j < 29; ++j ) { v[j] += (double)t[j]; }
-        }
-      }
-      block_reduce<29>( v, sh );
-    }
-    // ---- (C) solve + compose (icp.h:253-295), one thread
-    if( tid == 0 )
-    {
-      const double* s = sh.out;
-      float TL[3][3], TR[3][3], BR[3][3]; // [col][row]
-      int o = 0;
-      for( int col = 0; col < 3; ++col ) for( int row = col; row < 3; ++row ) { TL[col][row] = TL[row][col] = (float)s[o++]; }
-      for( int col = 0; col < 3; ++col ) for( int row = 0; row < 3; ++row ) { TR[col][row] = (float)s[o++]; }
-      for( int col = 0; col < 3; ++col ) for( int row = col; row < 3; ++row ) { BR[col][row] = BR[row][col] = (float)s[o++]; }
-      float err = (float)sqrt( __ddiv_rn( s[27], s[28] ) );
-      double A[6][6], rhs[6], x[6] = { 0, 0, 0, 0, 0, 0 };
-      for( int r = 0; r < 3; ++r )
-        for( int c = 0; c < 3; ++c )
-        {
-          A[r][c] = TL[c][r]; A[r][3 + c] = TR[c][r];
-          A[3 + r][c] = TR[r][c]; A[3 + r][3 + c] = BR[c][r];
-        }
-      for( int a = 0; a < 6; ++a ) { rhs[a] = -(double)(float)s[21 + a]; }
-      ldlt_solve6( A, rhs, x );
-      float T[16];
-      for( int i = 0; i < 16; ++i ) { T[i] = ( i % 5 == 0 ) ? 1.0f : 0.0f; }
-      xf_translate( T, c1x, c1y, c1z );
-      xf_translate( T, (float)x[3], (float)x[4], (float)x[5] );
-      xf_rotate( T, (float)x[0], 1.0f, 0.0f, 0.0f );
-      xf_rotate( T, (float)x[1], 0.0f, 1.0f, 0.0f );
-      xf_rotate( T, (float)x[2], 0.0f, 0.0f, 1.0f );
-      xf_translate( T, -c1x, -c1y, -c1z );
-      float Tn[16];
-      xf_mul( T, sh.T, Tn );
-      for( int i = 0; i < 16; ++i ) { sh.T[i] = Tn[i]; }
-      sh.err = err; sh.steps += 1;
-      float delta = fabsf( __fsub_rn( sh.prev_err, err ) );
-      if( it > 5 && (double)delta < 1e-5 ) { sh.stop = 1; }
-      double shrunk = __dmul_rn( (double)max_dist, 0.95 );
-      sh.max_dist = (float)( shrunk > 0.05 ? shrunk : 0.05 );
-    }
-    __syncthreads();
+    if( !icp_update<EXACT>( g, blk.n, cq, cm, it, sh, tile, fout, dout ) ) { break; }
     if( sh.stop ) { break; }
   }
   __syncthreads();
   if( tid < 16 ) { T1_io[16 * (size_t)b + tid] = sh.T[tid]; }
   if( tid == 0 ) { errs[b] = sh.err; if( iters ) { iters[b] = sh.steps; } }
+}
+
+// ---- variant 2 (default): iteration-synchronous over the whole batch.  Alignments differ 20x in work (points x
+// iterations), so resident blocks leave most of the GPU idle behind the slowest one.  Here every iteration is two
+// launches: icp_search_kernel spreads the correspondence searches of ALL still-running alignments over the whole
+// GPU (one warp task = 32 consecutive points of one alignment), icp_solve_kernel runs (B) + (C) with one block per
+// running alignment.  State lives in global memory between launches.
+struct IcpState
+{
+  float T[16];
+  float max_dist, prev_err, err;
+  int active, steps;
+};
+
+__global__ void __launch_bounds__( ICP_THREADS ) icp_search_kernel( GridView g, const IcpBlock* __restrict__ blocks, const IcpState* __restrict__ state,
+                                                                    const unsigned* __restrict__ task_start /* n_align + 1 */, int n_align,
+                                                                    const float* __restrict__ T2i, float dot_thr, float4* __restrict__ scratch_q,
+                                                                    uint2* __restrict__ scratch_m )
+{
+  __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
+  __shared__ unsigned char s_slot[ICP_WARPS][32];
+  __shared__ float s_T[ICP_WARPS][16], s_M[16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if( threadIdx.x < 16 ) { s_M[threadIdx.x] = T2i[threadIdx.x]; }
+  __syncthreads();
+  const unsigned n_tasks = task_start[n_align];
+  for( unsigned task = blockIdx.x * ICP_WARPS + warp; task < n_tasks; task += gridDim.x * ICP_WARPS )
+  {
+    // alignment of this task: last a with task_start[a] <= task
+    int lo = 0, hi = n_align;
+    while( hi - lo > 1 ) { int mid = ( lo + hi ) >> 1; if( __ldg( task_start + mid ) <= task ) { lo = mid; } else { hi = mid; } }
+    const int a = lo;
+    if( !state[a].active ) { continue; }
+    const IcpBlock blk = blocks[a];
+    if( lane < 16 ) { s_T[warp][lane] = state[a].T[lane]; }
+    __syncwarp();
+    const double radius = (double)state[a].max_dist;
+    const float r2f = (float)__dmul_rn( radius, radius );
+    icp_correspond_batch( g, s_T[warp], s_M, blk.p1, blk.n1, blk.n, (int)( task - __ldg( task_start + a ) ) * 32, radius, r2f, dot_thr,
+                          scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, s_cand[warp], s_slot[warp] );
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__( ICP_THREADS ) icp_solve_kernel( GridView g, const IcpBlock* __restrict__ blocks, IcpState* __restrict__ state, int it,
+                                                                   const float4* __restrict__ scratch_q, const uint2* __restrict__ scratch_m,
+                                                                   int* __restrict__ n_active )
+{
+  const int a = blockIdx.x, tid = threadIdx.x;
+  if( !state[a].active ) { return; }
+  const IcpBlock blk = blocks[a];
+  __shared__ IcpShared sh;
+  extern __shared__ float tile[];
+  __shared__ float fout[32];
+  __shared__ double dout[32];
+  if( tid < 16 ) { sh.T[tid] = state[a].T[tid]; }
+  if( tid == 0 ) { sh.max_dist = state[a].max_dist; sh.prev_err = state[a].err; sh.err = state[a].err; sh.stop = 0; sh.steps = state[a].steps; }
+  __syncthreads();
+  const bool updated = icp_update<EXACT>( g, blk.n, scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, it, sh, tile, fout, dout );
+  __syncthreads();
+  if( tid < 16 ) { state[a].T[tid] = sh.T[tid]; }
+  if( tid == 0 )
+  {
+    const int active = ( updated && !sh.stop ) ? 1 : 0;
+    state[a].max_dist = sh.max_dist; state[a].prev_err = sh.prev_err; state[a].err = sh.err; state[a].steps = sh.steps;
+    state[a].active = active;
+    if( active ) { atomicAdd( n_active, 1 ); }
+  }
 }
 
 // msh_mat4_inverse (msh_vec_math.h:1818-1917): cofactor expansion over 2x2 minors, all float, each cofactor
@@ -542,12 +631,17 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
   const char* mode = getenv( "RSGPU_ICP_SUMS" );
   const bool exact = !( mode && strcmp( mode, "fp64" ) == 0 );
+  // RSGPU_ICP_IMPL=block selects one resident block per alignment instead of the iteration-synchronous split
+  const char* imode = getenv( "RSGPU_ICP_IMPL" );
+  const bool split = !( imode && strcmp( imode, "block" ) == 0 );
   cudaStream_t st = rt().stream;
   float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
   mat4_inverse_ref( T2 ? T2 : ident, T2i );
   std::vector<IcpBlock> hb( total );
   std::vector<float> hT( total * 16 );
-  size_t bi = 0, off = 0;
+  std::vector<IcpState> hs( split ? total : 0 );
+  std::vector<unsigned> htask( split ? total + 1 : 0 );
+  size_t bi = 0, off = 0, n_tasks = 0;
   for( int j = 0; j < n_jobs; ++j )
   {
     const rsgpu_icp_job_t& J = jobs[j];
@@ -556,35 +650,78 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
       hb[bi].p1 = J.object->pos.p; hb[bi].n1 = J.object->nor.p; hb[bi].n = J.object->n; hb[bi].scratch_off = off;
       memcpy( &hT[bi * 16], J.T1 + 16 * (size_t)b, 64 );
       off += (size_t)( J.object->n > 0 ? J.object->n : 1 );
+      if( split )
+      {
+        memcpy( hs[bi].T, J.T1 + 16 * (size_t)b, 64 );
+        hs[bi].max_dist = max_dist; hs[bi].prev_err = 1e6f; hs[bi].err = 1e6f; hs[bi].active = 1; hs[bi].steps = 0;
+        htask[bi] = (unsigned)n_tasks;
+        n_tasks += (size_t)( ( J.object->n + 31 ) / 32 );
+      }
     }
   }
+  if( split ) { htask[total] = (unsigned)n_tasks; }
+  if( n_tasks > 0xffffffffull ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_icp_align: too many points" ); }
   DevBuf<IcpBlock> dB; DevBuf<float> dT, dT2i, derr; DevBuf<int> dit; DevBuf<float4> sq; DevBuf<uint2> sm;
   RS_CUDA( dB.alloc( total ) ); RS_CUDA( dT.alloc( total * 16 ) ); RS_CUDA( dT2i.alloc( 16 ) ); RS_CUDA( derr.alloc( total ) ); RS_CUDA( dit.alloc( total ) );
   RS_CUDA( sq.alloc( scratch ) ); RS_CUDA( sm.alloc( scratch ) );
   RS_CUDA( cudaMemcpyAsync( dB.p, hb.data(), sizeof( IcpBlock ) * total, cudaMemcpyHostToDevice, st ) );
-  RS_CUDA( cudaMemcpyAsync( dT.p, hT.data(), sizeof( float ) * 16 * total, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemcpyAsync( dT2i.p, T2i, 64, cudaMemcpyHostToDevice, st ) );
-  {
-    ProfScope prof( "icp" );
-    const size_t tile_bytes = sizeof( float ) * ICP_THREADS * TILE_LD;
-    if( exact )
-    {
-      RS_CUDA( cudaFuncSetAttribute( icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
-      icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist,
-                                                                          compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
-    }
-    else
-    {
-      icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist,
-                                                                  compat_threshold_acosf( max_angle ), max_iter, sq.p, sm.p, derr.p, dit.p );
-    }
-    RS_CHECK_LAUNCH();
-  }
+  const size_t tile_bytes = sizeof( float ) * ICP_THREADS * TILE_LD;
+  const float dot_thr = compat_threshold_acosf( max_angle );
   std::vector<float> herr( total ); std::vector<int> hit( total );
-  RS_CUDA( cudaMemcpyAsync( hT.data(), dT.p, sizeof( float ) * 16 * total, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaMemcpyAsync( herr.data(), derr.p, sizeof( float ) * total, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaMemcpyAsync( hit.data(), dit.p, sizeof( int ) * total, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  if( split )
+  {
+    DevBuf<IcpState> dS; DevBuf<unsigned> dtask; DevBuf<int> dact;
+    RS_CUDA( dS.alloc( total ) ); RS_CUDA( dtask.alloc( total + 1 ) ); RS_CUDA( dact.alloc( (size_t)max_iter ) );
+    RS_CUDA( cudaMemcpyAsync( dS.p, hs.data(), sizeof( IcpState ) * total, cudaMemcpyHostToDevice, st ) );
+    RS_CUDA( cudaMemcpyAsync( dtask.p, htask.data(), sizeof( unsigned ) * ( total + 1 ), cudaMemcpyHostToDevice, st ) );
+    RS_CUDA( cudaMemsetAsync( dact.p, 0, sizeof( int ) * (size_t)max_iter, st ) );
+    if( exact ) { RS_CUDA( cudaFuncSetAttribute( icp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) ); }
+    int n_sm = 148;
+    cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, rt().device );
+    const unsigned search_blocks = (unsigned)std::min<size_t>( ( n_tasks + ICP_WARPS - 1 ) / ICP_WARPS, (size_t)n_sm * 16 );
+    {
+      ProfScope prof( "icp" );
+      // the host looks at the number of still-running alignments every CHECK iterations (one 4-byte copy)
+      const int CHECK = 4;
+      for( int it = 0; it < max_iter; ++it )
+      {
+        icp_search_kernel<<<search_blocks, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dS.p, dtask.p, (int)total, dT2i.p, dot_thr, sq.p, sm.p );
+        RS_CHECK_LAUNCH();
+        if( exact ) { icp_solve_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dS.p, it, sq.p, sm.p, dact.p + it ); }
+        else { icp_solve_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dS.p, it, sq.p, sm.p, dact.p + it ); }
+        RS_CHECK_LAUNCH();
+        if( it % CHECK == CHECK - 1 || it == max_iter - 1 )
+        {
+          int running = 0;
+          RS_CUDA( cudaMemcpyAsync( &running, dact.p + it, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+          RS_CUDA( cudaStreamSynchronize( st ) );
+          if( running == 0 ) { break; }
+        }
+      }
+    }
+    RS_CUDA( cudaMemcpyAsync( hs.data(), dS.p, sizeof( IcpState ) * total, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( cudaStreamSynchronize( st ) );
+    for( size_t i = 0; i < total; ++i ) { memcpy( &hT[i * 16], hs[i].T, 64 ); herr[i] = hs[i].err; hit[i] = hs[i].steps; }
+  }
+  else
+  {
+    RS_CUDA( cudaMemcpyAsync( dT.p, hT.data(), sizeof( float ) * 16 * total, cudaMemcpyHostToDevice, st ) );
+    {
+      ProfScope prof( "icp" );
+      if( exact )
+      {
+        RS_CUDA( cudaFuncSetAttribute( icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
+        icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, derr.p, dit.p );
+      }
+      else { icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, derr.p, dit.p ); }
+      RS_CHECK_LAUNCH();
+    }
+    RS_CUDA( cudaMemcpyAsync( hT.data(), dT.p, sizeof( float ) * 16 * total, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( cudaMemcpyAsync( herr.data(), derr.p, sizeof( float ) * total, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( cudaMemcpyAsync( hit.data(), dit.p, sizeof( int ) * total, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( cudaStreamSynchronize( st ) );
+  }
   bi = 0;
   for( int j = 0; j < n_jobs; ++j )
   {

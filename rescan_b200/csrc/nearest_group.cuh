@@ -287,3 +287,101 @@ __device__ __forceinline__ NearestHit group_round( const GridView& g, int n_roun
 }
 } // namespace rsg
 #endif // __CUDACC__
+
+#ifdef __CUDACC__
+namespace rsg
+{
+static __constant__ unsigned char kCandCode[28] = {
+  (unsigned char)cand_code( 0 ),  (unsigned char)cand_code( 1 ),  (unsigned char)cand_code( 2 ),  (unsigned char)cand_code( 3 ),
+  (unsigned char)cand_code( 4 ),  (unsigned char)cand_code( 5 ),  (unsigned char)cand_code( 6 ),  (unsigned char)cand_code( 7 ),
+  (unsigned char)cand_code( 8 ),  (unsigned char)cand_code( 9 ),  (unsigned char)cand_code( 10 ), (unsigned char)cand_code( 11 ),
+  (unsigned char)cand_code( 12 ), (unsigned char)cand_code( 13 ), (unsigned char)cand_code( 14 ), (unsigned char)cand_code( 15 ),
+  (unsigned char)cand_code( 16 ), (unsigned char)cand_code( 17 ), (unsigned char)cand_code( 18 ), (unsigned char)cand_code( 19 ),
+  (unsigned char)cand_code( 20 ), (unsigned char)cand_code( 21 ), (unsigned char)cand_code( 22 ), (unsigned char)cand_code( 23 ),
+  (unsigned char)cand_code( 24 ), (unsigned char)cand_code( 25 ), (unsigned char)cand_code( 26 ), 0 };
+
+// One query per THREAD (same definition and arithmetic as group_search): the thread walks the <= 27 cells of its
+// window itself, own cell first.  Meant for warps whose 32 queries are spatial neighbours (object points in their
+// stored order at levels 1-3, queries sorted by cell): the lanes then read the same cache lines at the same time
+// and run similar trip counts, and nothing is shuffled or staged.  Same precondition as group_search.
+__device__ __forceinline__ NearestHit lane_search( const GridView& g, bool qv, float px, float py, float pz, float nx, float ny, float nz,
+                                                   double radius, float r2f, float dot_thr, int k )
+{
+  NearestHit hit; hit.found = false; hit.d2 = 0.f; hit.dot = 0.f; hit.pos = 0;
+  const uint32_t r2bits = __float_as_uint( r2f );
+  CellWindow w; w.n_cells = 0;
+  if( qv ) { w = make_window( g, px, py, pz, radius ); qv = w.n_cells != 0; }
+  if( !qv ) { return hit; }
+  float a;
+  a = (float)__dsub_rn( (double)w.qx, __dmul_rn( (double)w.c0x, g.cell ) ); const float glx2 = __fmul_rn( a, a );
+  a = (float)__dsub_rn( __dmul_rn( (double)( w.c0x + 1 ), g.cell ), (double)w.qx ); const float ghx2 = __fmul_rn( a, a );
+  a = (float)__dsub_rn( (double)w.qy, __dmul_rn( (double)w.c0y, g.cell ) ); const float gly2 = __fmul_rn( a, a );
+  a = (float)__dsub_rn( __dmul_rn( (double)( w.c0y + 1 ), g.cell ), (double)w.qy ); const float ghy2 = __fmul_rn( a, a );
+  a = (float)__dsub_rn( (double)w.qz, __dmul_rn( (double)w.c0z, g.cell ) ); const float glz2 = __fmul_rn( a, a );
+  a = (float)__dsub_rn( __dmul_rn( (double)( w.c0z + 1 ), g.cell ), (double)w.qz ); const float ghz2 = __fmul_rn( a, a );
+  const int oxc = min( max( w.c0x - w.lox, 0 ), 2 ), oyc = min( max( w.c0y - w.loy, 0 ), 2 ), ozc = min( max( w.c0z - w.loz, 0 ), 2 );
+  const bool inside = w.c0x >= 0 && w.c0x < g.W && w.c0y >= 0 && w.c0y < g.H && w.c0z >= 0 && w.c0z < g.D;
+  bool cap = true;
+  if( inside && g.occ27 ) { cap = __ldg( g.occ27 + ( ( (size_t)w.c0z * g.H + w.c0y ) * g.W + w.c0x ) ) >= (uint32_t)k; }
+  const ConeCull cull = make_cull( g, dot_thr, nx, ny, nz );
+
+  // cell e of the visiting order: point range and conservative gap bits (false: not in the window / out of range / empty)
+  auto cell_of = [&]( int e, uint32_t lim, uint32_t& s, uint32_t& t, uint32_t& id ) -> bool {
+    const unsigned code = kCandCode[e];
+    int ix = oxc + (int)( code & 3u ), iy = oyc + (int)( ( code >> 2 ) & 3u ), iz = ozc + (int)( code >> 4 );
+    ix -= ix >= 3 ? 3 : 0; iy -= iy >= 3 ? 3 : 0; iz -= iz >= 3 ? 3 : 0;
+    if( ix >= w.nx || iy >= w.ny || iz >= w.nz ) { return false; }
+    const int cx = w.lox + ix, cy = w.loy + iy, cz = w.loz + iz;
+    const float gx2 = cx < w.c0x ? glx2 : ( cx > w.c0x ? ghx2 : 0.0f );
+    const float gy2 = cy < w.c0y ? gly2 : ( cy > w.c0y ? ghy2 : 0.0f );
+    const float gz2 = cz < w.c0z ? glz2 : ( cz > w.c0z ? ghz2 : 0.0f );
+    const uint32_t gapc = __float_as_uint( __fadd_rn( __fadd_rn( gz2, gy2 ), gx2 ) ) & 0xffffffe0u;
+    if( gapc >= lim ) { return false; }
+    id = (uint32_t)( ( cz * g.H + cy ) * g.W + cx );
+    s = __ldg( g.cell_start + id ); t = __ldg( g.cell_start + id + 1 );
+    return s < t;
+  };
+
+  unsigned long long limkey = (unsigned long long)r2bits << 32;
+  float bestdot = 0.f;
+  for( int e = 0; e < 27; ++e )
+  {
+    uint32_t s, t, id;
+    if( !cell_of( e, (uint32_t)( limkey >> 32 ), s, t, id ) ) { continue; }
+    if( !cone_possible( g.cone, cull, (size_t)id, nx, ny, nz ) ) { continue; }
+    for( uint32_t p = s; p < t; ++p )
+    {
+      const float4 rec = __ldg( g.recs + p );
+      const unsigned long long key = ( (unsigned long long)__float_as_uint( dist2_exact( rec, px, py, pz ) ) << 32 ) | p;
+      if( key < limkey )
+      {
+        const float4 mm = __ldg( g.nrm + p );
+        const float dot = dot3_exact( mm.x, mm.y, mm.z, nx, ny, nz );
+        if( dot >= dot_thr && dot <= 1.0f ) { limkey = key; bestdot = dot; }
+      }
+    }
+  }
+  const uint32_t dcb = (uint32_t)( limkey >> 32 );
+  if( dcb >= r2bits ) { return hit; }
+  hit.d2 = __uint_as_float( dcb ); hit.pos = (uint32_t)limkey; hit.dot = bestdot; hit.found = true;
+  if( cap )
+  {
+    const float dcf = hit.d2;
+    const uint32_t uk = (uint32_t)k;
+    uint32_t cnt = 0;
+    for( int e = 0; e < 27 && cnt < uk; ++e )
+    {
+      uint32_t s, t, id;
+      if( !cell_of( e, dcb, s, t, id ) ) { continue; }
+      for( uint32_t p = s; p < t; ++p )
+      {
+        const float4 rec = __ldg( g.recs + p );
+        cnt += dist2_exact( rec, px, py, pz ) < dcf;
+      }
+    }
+    hit.found = cnt < uk;
+  }
+  return hit;
+}
+} // namespace rsg
+#endif // __CUDACC__

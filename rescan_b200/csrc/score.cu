@@ -115,7 +115,7 @@ __global__ void __launch_bounds__( 128 ) score_kernel( GridView g, const float* 
 constexpr int SC_WARPS = 4;
 constexpr int SC_LIST_CAP = 1024;
 
-template <bool GRID, int SC_G, int MINB>
+template <bool GRID, int SC_G, int MINB, bool LANE>
 __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridView g, const float* __restrict__ obj_pos, const float* __restrict__ obj_nor,
                                                                    int n_obj, PoseSource ps, long long n_poses, int n_split, int chunk,
                                                                    ScoreParams sp, double prune_cnt, double* __restrict__ partial )
@@ -181,7 +181,14 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
       xf_apply( m, __ldg( obj_nor + 3 * (size_t)i ), __ldg( obj_nor + 3 * (size_t)i + 1 ), __ldg( obj_nor + 3 * (size_t)i + 2 ), 0.0f, nx, ny, nz );
       return ( e & 0x8000 ) == 0;
     };
-    NearestHit h = rsg::group_round<SC_G>( g, n_round, query_of, sp.radius, sp.r2f, sp.dot_thr, sp.k, cand );
+    NearestHit h;
+    if( LANE )
+    {
+      float px = 0.f, py = 0.f, pz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+      const bool qv = lane < n_round && query_of( lane, px, py, pz, nx, ny, nz );
+      h = rsg::lane_search( g, qv, px, py, pz, nx, ny, nz, sp.radius, sp.r2f, sp.dot_thr, sp.k );
+    }
+    else { h = rsg::group_round<SC_G>( g, n_round, query_of, sp.radius, sp.r2f, sp.dot_thr, sp.k, cand ); }
     // windows the group path cannot take (last-bit cases, radius > cell size): generic warp-cooperative search
     const bool slow = lane < n_round && ( list[base + lane] & 0x8000 ) != 0;
     if( __any_sync( RS_FULL, slow ) )
@@ -296,13 +303,19 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
       static const int cfg_g = []() { const char* e = getenv( "RSGPU_SCORE_G" ); return e ? atoi( e ) : 4; }();
       static const int cfg_b = []() { const char* e = getenv( "RSGPU_SCORE_MINB" ); return e ? atoi( e ) : 6; }();
 #define RS_SCORE_G_LAUNCH( GRIDM, GG, MB ) \
-      score_kernel_g<GRIDM, GG, MB><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p )
+      score_kernel_g<GRIDM, GG, MB, false><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p )
 #define RS_SCORE_G_PICK( GRIDM ) \
       do { \
         if( cfg_g == 8 ) { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 8 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 6 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 8, 4 ); } } \
         else { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 8 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 4 ); } } \
       } while( 0 )
-      if( grid_mode ) { RS_SCORE_G_PICK( true ); } else { RS_SCORE_G_PICK( false ); }
+      static const bool lane_env = []() { const char* e = getenv( "RSGPU_SEARCH" ); return e && strcmp( e, "lane" ) == 0; }();
+      if( lane_env )
+      {
+        if( grid_mode ) { score_kernel_g<true, 4, 6, true><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p ); }
+        else { score_kernel_g<false, 4, 6, true><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p ); }
+      }
+      else if( grid_mode ) { RS_SCORE_G_PICK( true ); } else { RS_SCORE_G_PICK( false ); }
 #undef RS_SCORE_G_PICK
 #undef RS_SCORE_G_LAUNCH
     }

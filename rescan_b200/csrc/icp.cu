@@ -156,29 +156,49 @@ constexpr int TILE_LD = 33;
 template <int NV, bool WITH_F64, class TermFn>
 __device__ __forceinline__ void ordered_sums( int n, TermFn term_fn, float* tile, float* fout, double* dout )
 {
+  // Two tiles: while warp 0 (float sums) and warp 1 (the two fp64 sums of the error term, icp.h:250-253: columns NV-2,
+  // NV-1) walk down the rows of one tile, the remaining warps form the terms of the next one.
+  constexpr int FIRST_FILL = WITH_F64 ? 2 : 1;
+  constexpr int FILL_THREADS = ICP_THREADS - 32 * FIRST_FILL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float fa = 0.0f; double da = 0.0;
-  for( int base = 0; base < n; base += ICP_THREADS )
+  const int stages = ( n + ICP_THREADS - 1 ) / ICP_THREADS;
+  auto fill = [&]( int stage ) {
+    float* buf = tile + ( stage & 1 ) * ( ICP_THREADS * TILE_LD );
+    const int base = stage * ICP_THREADS, rows = min( ICP_THREADS, n - base );
+    for( int r = tid - 32 * FIRST_FILL; r < rows; r += FILL_THREADS )
+    {
+      float t[NV];
+#pragma unroll
+      for( int v = 0; v < NV; ++v ) { t[v] = 0.0f; }
+      term_fn( base + r, t );
+#pragma unroll
+      for( int v = 0; v < NV; ++v ) { buf[r * TILE_LD + v] = t[v]; }
+    }
+  };
+  if( warp >= FIRST_FILL ) { fill( 0 ); }
+  __syncthreads();
+  for( int stage = 0; stage < stages; ++stage )
   {
-    float t[NV];
-#pragma unroll
-    for( int v = 0; v < NV; ++v ) { t[v] = 0.0f; }
-    if( base + tid < n ) { term_fn( base + tid, t ); }
-#pragma unroll
-    for( int v = 0; v < NV; ++v ) { tile[tid * TILE_LD + v] = t[v]; }
-    __syncthreads();
-    const int rows = min( ICP_THREADS, n - base );
-    if( warp == 0 && lane < NV )
+    const float* buf = tile + ( stage & 1 ) * ( ICP_THREADS * TILE_LD );
+    const int rows = min( ICP_THREADS, n - stage * ICP_THREADS );
+    if( warp == 0 )
     {
+      if( lane < NV )
+      {
 #pragma unroll 8
-      for( int r = 0; r < rows; ++r ) { fa = __fadd_rn( fa, tile[r * TILE_LD + lane] ); }
+        for( int r = 0; r < rows; ++r ) { fa = __fadd_rn( fa, buf[r * TILE_LD + lane] ); }
+      }
     }
-    else if( WITH_F64 && warp == 1 && lane < 2 )
+    else if( WITH_F64 && warp == 1 )
     {
-      // the two fp64 sums of the error term (icp.h:250-253: columns NV-2, NV-1) run beside the float sums on another warp
+      if( lane < 2 )
+      {
 #pragma unroll 8
-      for( int r = 0; r < rows; ++r ) { da = __dadd_rn( da, (double)tile[r * TILE_LD + ( NV - 2 + lane )] ); }
+        for( int r = 0; r < rows; ++r ) { da = __dadd_rn( da, (double)buf[r * TILE_LD + ( NV - 2 + lane )] ); }
+      }
     }
+    else if( stage + 1 < stages ) { fill( stage + 1 ); }
     __syncthreads();
   }
   if( warp == 0 ) { fout[lane] = fa; }
@@ -441,7 +461,7 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
 {
   const IcpBlock blk = blocks[blockIdx.x];
   __shared__ IcpShared sh;
-  extern __shared__ float tile[]; // EXACT: ICP_THREADS * TILE_LD floats
+  extern __shared__ float tile[]; // EXACT: 2 * ICP_THREADS * TILE_LD floats
   __shared__ float fout[32];
   __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
   __shared__ unsigned char s_slot[ICP_WARPS][32];
@@ -666,7 +686,7 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   RS_CUDA( sq.alloc( scratch ) ); RS_CUDA( sm.alloc( scratch ) );
   RS_CUDA( cudaMemcpyAsync( dB.p, hb.data(), sizeof( IcpBlock ) * total, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemcpyAsync( dT2i.p, T2i, 64, cudaMemcpyHostToDevice, st ) );
-  const size_t tile_bytes = sizeof( float ) * ICP_THREADS * TILE_LD;
+  const size_t tile_bytes = 2 * sizeof( float ) * ICP_THREADS * TILE_LD; // two tiles (ordered_sums)
   const float dot_thr = compat_threshold_acosf( max_angle );
   std::vector<float> herr( total ); std::vector<int> hit( total );
   if( split )

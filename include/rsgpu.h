@@ -104,6 +104,10 @@ int rsgpu_grid_knn_search( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, 
 /* same with every buffer of `desc` in device memory (n_neighbors then is uint64 on the device) */
 int rsgpu_grid_radius_search_dev( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, size_t* total );
 int rsgpu_grid_knn_search_dev( const rsgpu_grid_t* grid, rsgpu_search_desc_t* desc, size_t* total );
+/* measurement aid: what msh_hash_grid_radius_search reads for these (device-resident) queries by the reference's
+   data layout — counts[0] = non-empty cells overlapping the query windows, counts[1] = points stored in them
+   (msh_hash_grid.h:1187-1225, :826-862); no early-out credit */
+int rsgpu_grid_search_census_dev( const rsgpu_grid_t* grid, const float* d_query_pts, size_t n_query_pts, float radius, int64_t counts[2] );
 
 /* ------------------------------------------------------------------------------------------------ clouds */
 /* positions + normals of one sampling level of an object model (rs_pointcloud_t::positions[lvl] / normals[lvl]) */

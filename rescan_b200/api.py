@@ -86,6 +86,7 @@ SIGNATURES = {
     "rsgpu_grid_knn_search": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
     "rsgpu_grid_radius_search_dev": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
     "rsgpu_grid_knn_search_dev": (_int, [_vp, C.POINTER(SearchDesc), C.POINTER(_sz)]),
+    "rsgpu_grid_search_census_dev": (_int, [_vp, _vp, _sz, _f32, C.POINTER(_i64)]),
     "rsgpu_cloud_create": (_int, [_vp, _vp, _i32, C.POINTER(_vp)]),
     "rsgpu_cloud_destroy": (None, [_vp]),
     "rsgpu_cloud_size": (_i32, [_vp]),
@@ -239,6 +240,19 @@ class HashGrid:
 
     def knn_search(self, q, k, sort=1):
         return self._search(lib().rsgpu_grid_knn_search, q, 0.0, k, sort)
+
+    def radius_search_dev(self, q_ptr, nq, radius, k, d2_ptr, idx_ptr, nn_ptr=None):
+        """same search with every buffer already in HBM (raw device pointers; n_neighbors is uint64) -> total"""
+        sd = SearchDesc(q_ptr, nq, d2_ptr, idx_ptr, nn_ptr, radius, k, 1)
+        tot = C.c_size_t(0)
+        _check(lib().rsgpu_grid_radius_search_dev(self.h, C.byref(sd), C.byref(tot)))
+        return int(tot.value)
+
+    def search_census_dev(self, q_ptr, nq, radius):
+        """(non-empty cells, points) the reference's radius search reads for these device-resident queries"""
+        c = (C.c_int64 * 2)()
+        _check(lib().rsgpu_grid_search_census_dev(self.h, C.c_void_p(q_ptr), nq, radius, c))
+        return int(c[0]), int(c[1])
 
     def close(self):
         if getattr(self, "h", None):

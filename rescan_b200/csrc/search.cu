@@ -257,6 +257,26 @@ __global__ void __launch_bounds__( 128 ) neighborhood_kernel( GridView g, const 
   }
 }
 
+// census of what a radius search reads by the reference's data layout: per query the non-empty cells
+// overlapping its window (B) and the points stored in them (C), no early-out credit
+__global__ void __launch_bounds__( 256 ) search_census_kernel( GridView g, const float* __restrict__ q, size_t nq, double radius,
+                                                               unsigned long long* __restrict__ counts )
+{
+  unsigned long long nB = 0, nC = 0;
+  for( size_t qi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; qi < nq; qi += gridDim.x * (size_t)blockDim.x )
+  {
+    CellWindow w = make_window( g, __ldg( q + 3 * qi ), __ldg( q + 3 * qi + 1 ), __ldg( q + 3 * qi + 2 ), radius );
+    for( int e = 0; e < w.n_cells; ++e )
+    {
+      uint32_t s, t; float gap2;
+      window_cell( g, w, e, s, t, gap2 );
+      if( s < t ) { nB += 1; nC += t - s; }
+    }
+  }
+  for( int o = 16; o > 0; o >>= 1 ) { nB += __shfl_down_sync( RS_FULL, nB, o ); nC += __shfl_down_sync( RS_FULL, nC, o ); }
+  if( ( threadIdx.x & 31 ) == 0 ) { atomicAdd( counts + 0, nB ); atomicAdd( counts + 1, nC ); }
+}
+
 template <int EPL>
 int launch_search( bool knn, const GridView& g, const float* d_q, size_t nq, double radius, float r2f, int k, float* d_d2,
                    int32_t* d_idx, unsigned long long* d_nn, unsigned long long* d_total )
@@ -352,6 +372,25 @@ int rsgpu_grid_knn_search_dev( const rsgpu_grid_t* g, rsgpu_search_desc_t* d, si
   RS_TRY( ensure_device() );
   return search_dev( true, g, d->query_pts, d->n_query_pts, d->radius, d->k, d->distances_sq, d->indices,
                      (unsigned long long*)d->n_neighbors, total );
+}
+
+int rsgpu_grid_search_census_dev( const rsgpu_grid_t* g, const float* d_query_pts, size_t n_query_pts, float radius, int64_t counts[2] )
+{
+  if( !g || !counts || ( n_query_pts > 0 && !d_query_pts ) || !( radius > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_grid_search_census: bad argument" ); }
+  RS_TRY( ensure_device() );
+  counts[0] = counts[1] = 0;
+  if( n_query_pts == 0 || g->info.n_pts == 0 ) { return RSGPU_OK; }
+  DevBuf<unsigned long long> dc;
+  RS_CUDA( dc.alloc( 2 ) );
+  RS_CUDA( cudaMemsetAsync( dc.p, 0, 16, rt().stream ) );
+  size_t blocks = ( n_query_pts + 255 ) / 256; if( blocks > 148 * 16 ) { blocks = 148 * 16; }
+  search_census_kernel<<<(unsigned)blocks, 256, 0, rt().stream>>>( g->view(), d_query_pts, n_query_pts, (double)radius, dc.p );
+  RS_CHECK_LAUNCH();
+  unsigned long long h[2];
+  RS_CUDA( cudaMemcpyAsync( h, dc.p, 16, cudaMemcpyDeviceToHost, rt().stream ) );
+  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  counts[0] = (int64_t)h[0]; counts[1] = (int64_t)h[1];
+  return RSGPU_OK;
 }
 
 int rsgpu_neighborhood( const rsgpu_grid_t* grid, const float* pos, const float* nor, int32_t n, int32_t max_nn, float radius_sq,

@@ -52,6 +52,9 @@ const char* rsgpu_version( void );
 /* Per-kernel device timing with CUDA events on the launch stream (used by bench.py for the roofline line).
    names: "grid_build", "search", "score_dense" (pose-grid launches), "score" (explicit pose lists), "icp",
    "labels", "unary", "edges".  ms = summed event time. */
+/* tuning / A-B knobs ("search_impl" = lane|warp, "score_impl" = coop, "prune" = 0, "icp_impl" = block, "icp_sums" = fp64,
+   ...); value NULL or "" restores the default.  The same knobs are read from the environment as RSGPU_<NAME>. */
+int rsgpu_set_option( const char* name, const char* value );
 int rsgpu_profile_enable( int on );
 int rsgpu_profile_reset( void );
 int rsgpu_profile_get( const char* name, double* ms, int64_t* launches );

@@ -71,6 +71,7 @@ SIGNATURES = {
     "rsgpu_synchronize": (_int, []),
     "rsgpu_last_error": (C.c_char_p, []),
     "rsgpu_version": (C.c_char_p, []),
+    "rsgpu_set_option": (_int, [C.c_char_p, C.c_char_p]),
     "rsgpu_profile_enable": (_int, [_int]),
     "rsgpu_profile_reset": (_int, []),
     "rsgpu_profile_get": (_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
@@ -151,6 +152,11 @@ def synchronize():
 
 def launch_count():
     return int(lib().rsgpu_launch_count())
+
+
+def set_option(name, value=None):
+    """tuning / A-B knob of the library (see include/rsgpu.h); value None restores the default"""
+    _check(lib().rsgpu_set_option(name.encode(), None if value is None else str(value).encode()))
 
 
 def profile_enable(on=True):

@@ -649,11 +649,9 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   if( !( max_dist > 0.f ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_icp_align: max_dist must be > 0" ); }
   if( max_iter <= 0 ) { max_iter = 100; }
   // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
-  const char* mode = getenv( "RSGPU_ICP_SUMS" );
-  const bool exact = !( mode && strcmp( mode, "fp64" ) == 0 );
+  const bool exact = option( "icp_sums" ) != "fp64";
   // RSGPU_ICP_IMPL=block selects one resident block per alignment instead of the iteration-synchronous split
-  const char* imode = getenv( "RSGPU_ICP_IMPL" );
-  const bool split = !( imode && strcmp( imode, "block" ) == 0 );
+  const bool split = option( "icp_impl" ) != "block";
   cudaStream_t st = rt().stream;
   float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
   mat4_inverse_ref( T2 ? T2 : ident, T2i );

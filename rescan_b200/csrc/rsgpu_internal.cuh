@@ -26,6 +26,8 @@ Runtime& rt();
 int fail( int code, const std::string& msg );
 int cuda_fail( cudaError_t e, const char* what, const char* file, int line );
 int ensure_device();
+std::string option( const char* key );   // value set by rsgpu_set_option, else environment RSGPU_<KEY>, else ""
+void set_option( const char* key, const char* value );
 void count_launch(); // one of OUR kernels was launched (library kernels such as CUB are not counted)
 
 // RAII device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are enqueued on the

@@ -6,6 +6,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <cctype>
 
 namespace rs
 {
@@ -19,6 +21,27 @@ static std::vector<Pending>* g_pending = nullptr;
 static std::atomic<long long> g_launches{ 0 };
 void count_launch() { g_launches.fetch_add( 1, std::memory_order_relaxed ); }
 long long launches() { return g_launches.load(); }
+
+// tuning / A-B knobs: rsgpu_set_option( "search_impl", "lane" ) or the environment variable RSGPU_SEARCH_IMPL
+static std::mutex g_opt_mu;
+static std::map<std::string, std::string> g_opts;
+std::string option( const char* key )
+{
+  {
+    std::lock_guard<std::mutex> lk( g_opt_mu );
+    auto it = g_opts.find( key );
+    if( it != g_opts.end() ) { return it->second; }
+  }
+  std::string env = "RSGPU_";
+  for( const char* c = key; *c; ++c ) { env += (char)toupper( (unsigned char)*c ); }
+  const char* e = getenv( env.c_str() );
+  return e ? std::string( e ) : std::string();
+}
+void set_option( const char* key, const char* value )
+{
+  std::lock_guard<std::mutex> lk( g_opt_mu );
+  if( value && *value ) { g_opts[key] = value; } else { g_opts.erase( key ); }
+}
 
 Runtime& rt()
 {
@@ -107,6 +130,13 @@ ProfScope::~ProfScope()
 using namespace rs;
 
 extern "C" {
+
+int rsgpu_set_option( const char* name, const char* value )
+{
+  if( !name || !*name ) { return fail( RSGPU_ERR_INVALID, "rsgpu_set_option: empty name" ); }
+  set_option( name, value );
+  return RSGPU_OK;
+}
 
 int rsgpu_device_count( void )
 {

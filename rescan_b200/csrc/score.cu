@@ -283,7 +283,7 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
     if( n_split < 1 ) { n_split = 1; }
   }
   // RSGPU_SCORE_IMPL=coop selects the warp-per-query kernel (the census pass always uses it)
-  static const bool coop_env = []() { const char* e = getenv( "RSGPU_SCORE_IMPL" ); return e && strcmp( e, "coop" ) == 0; }();
+  const bool coop_env = option( "score_impl" ) == "coop";
   const bool group_impl = !d_counts && !coop_env;
   if( group_impl && n_split < ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP ) { n_split = ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP; }
   int chunk = ( ( obj->n + n_split - 1 ) / n_split + 31 ) / 32 * 32;
@@ -300,8 +300,8 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
     if( group_impl )
     {
       // lanes per query and resident blocks per SM (register cap) of the group kernel; the defaults are the measured best
-      static const int cfg_g = []() { const char* e = getenv( "RSGPU_SCORE_G" ); return e ? atoi( e ) : 4; }();
-      static const int cfg_b = []() { const char* e = getenv( "RSGPU_SCORE_MINB" ); return e ? atoi( e ) : 6; }();
+      const std::string og = option( "score_g" ), ob = option( "score_minb" );
+      const int cfg_g = og.empty() ? 4 : atoi( og.c_str() ), cfg_b = ob.empty() ? 6 : atoi( ob.c_str() );
 #define RS_SCORE_G_LAUNCH( GRIDM, GG, MB ) \
       score_kernel_g<GRIDM, GG, MB, false><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p )
 #define RS_SCORE_G_PICK( GRIDM ) \
@@ -309,7 +309,7 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
         if( cfg_g == 8 ) { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 8 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 6 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 8, 4 ); } } \
         else { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 8 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 4 ); } } \
       } while( 0 )
-      static const bool lane_env = []() { const char* e = getenv( "RSGPU_SEARCH" ); return e && strcmp( e, "lane" ) == 0; }();
+      const bool lane_env = option( "search" ) == "lane";
       if( lane_env )
       {
         if( grid_mode ) { score_kernel_g<true, 4, 6, true><<<(unsigned)blocks, 32 * SC_WARPS, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p ); }
@@ -495,7 +495,7 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   // level 4: dense search.  Scores that provably cannot exceed the level's threshold are not resolved (reported as
   // 0): they can neither be emitted nor change which rotation is emitted (RSGPU_PRUNE=0 resolves every score).
   {
-    static const bool no_prune = []() { const char* e = getenv( "RSGPU_PRUNE" ); return e && strcmp( e, "0" ) == 0; }();
+    const bool no_prune = option( "prune" ) == "0";
     PoseSource ps; memset( &ps, 0, sizeof( ps ) ); ps.rots = dr.p; ps.trans = dt.p; ps.n_rot = n_rot;
     RS_TRY( score_launch( o4, scene, ps, true, n, opts.max_n_neigh, opts.radius, ds.p, nullptr, no_prune ? 0.0f : opts.thresholds[0] ) );
   }

@@ -9,6 +9,8 @@
 // rows come out ascending and ties are broken by the lower original index, deterministically.
 #include "rsgpu_internal.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 using namespace rs;
 
@@ -136,6 +138,84 @@ __global__ void __launch_bounds__( 128 ) radius_search_kernel( GridView g, const
     local_total += count;
   }
   if( lane == 0 && local_total ) { atomicAdd( total, local_total ); }
+}
+
+// One query per THREAD, for small k on sparse windows (a few dozen candidate points per query): the warp-per-query
+// kernel above spends ~300 instructions of election / reduction / shuffle per query there, while the whole job is a
+// handful of distance tests.  Same result definition: the k nearest points with dist^2 < r^2, ascending by
+// (dist^2, original index); the sorted list lives in K registers of the thread (insertion = K compare-selects).
+template <int K>
+__global__ void __launch_bounds__( 128 ) radius_search_lane_kernel( GridView g, const float* __restrict__ q, size_t nq, double radius,
+                                                                    float r2f, int k, float* __restrict__ out_d2,
+                                                                    int32_t* __restrict__ out_idx, unsigned long long* __restrict__ out_nn,
+                                                                    unsigned long long* __restrict__ total )
+{
+  unsigned long long local_total = 0;
+  const uint32_t r2bits = __float_as_uint( r2f );
+  for( size_t qi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; qi < nq; qi += gridDim.x * (size_t)blockDim.x )
+  {
+    const float px = __ldg( q + 3 * qi ), py = __ldg( q + 3 * qi + 1 ), pz = __ldg( q + 3 * qi + 2 );
+    const CellWindow w = make_window( g, px, py, pz, radius );
+    unsigned long long keys[K];
+#pragma unroll
+    for( int s = 0; s < K; ++s ) { keys[s] = KEY_INF; }
+    unsigned long long thr = KEY_INF; // keys[K - 1]
+    uint32_t seen = 0;
+    for( int e = 0; e < w.n_cells; ++e )
+    {
+      uint32_t cs, ce; float gap2;
+      window_cell( g, w, e, cs, ce, gap2 );
+      const uint32_t gbits = __float_as_uint( gap2 );
+      // empty / out of range, or the list is full and the cell cannot beat its last entry (:1232-1236)
+      if( cs >= ce || !( gbits < r2bits ) || ( thr != KEY_INF && gbits >= (uint32_t)( thr >> 32 ) ) ) { continue; }
+      for( uint32_t p = cs; p < ce; ++p )
+      {
+        const float4 rec = __ldg( g.recs + p );
+        const uint32_t db = __float_as_uint( dist2_exact( rec, px, py, pz ) );
+        if( db < r2bits )
+        {
+          ++seen;
+          const unsigned long long x = ( (unsigned long long)db << 32 ) | __float_as_uint( rec.w );
+          if( x < thr )
+          {
+#pragma unroll
+            for( int s = K - 1; s >= 0; --s )
+            {
+              const unsigned long long prev = s > 0 ? keys[s - 1] : 0ull;
+              keys[s] = ( keys[s] <= x ) ? keys[s] : ( prev <= x ? x : prev );
+            }
+            thr = keys[K - 1]; // K >= k: pruning by the K-th best is merely a little weaker than by the k-th
+          }
+        }
+      }
+    }
+    const uint32_t count = seen < (uint32_t)k ? seen : (uint32_t)k;
+#pragma unroll
+    for( int s = 0; s < K; ++s )
+    {
+      if( (uint32_t)s < count )
+      {
+        out_d2[qi * k + s] = __uint_as_float( (uint32_t)( keys[s] >> 32 ) );
+        out_idx[qi * k + s] = (int32_t)(uint32_t)( keys[s] & 0xffffffffull );
+      }
+    }
+    if( out_nn ) { out_nn[qi] = count; }
+    local_total += count;
+  }
+  for( int o = 16; o > 0; o >>= 1 ) { local_total += __shfl_down_sync( RS_FULL, local_total, o ); }
+  if( ( threadIdx.x & 31 ) == 0 && local_total ) { atomicAdd( total, local_total ); }
+}
+
+template <int K>
+int launch_search_lane( const GridView& g, const float* d_q, size_t nq, double radius, float r2f, int k, float* d_d2, int32_t* d_idx,
+                        unsigned long long* d_nn, unsigned long long* d_total )
+{
+  size_t blocks = ( nq + 127 ) / 128;
+  const size_t max_blocks = 148 * 32;
+  if( blocks > max_blocks ) { blocks = max_blocks; }
+  radius_search_lane_kernel<K><<<(unsigned)blocks, 128, 0, rt().stream>>>( g, d_q, nq, radius, r2f, k, d_d2, d_idx, d_nn, d_total );
+  RS_CHECK_LAUNCH();
+  return RSGPU_OK;
 }
 
 // msh_hash_grid_knn_search: shells of cells around the query's cell are opened layer by layer and the search
@@ -309,7 +389,23 @@ int search_dev( bool knn, const rsgpu_grid_t* grid, const float* d_q, size_t nq,
     double r = radius;
     float r2f = (float)( r * r ); // double product narrowed when handed down (:1111, 828)
     int kk = (int)k, s;
-    if( kk <= 32 ) { s = launch_search<1>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    // thread-per-query kernel for small k when a window holds few candidate points (sparse cells); the warp-per-query
+    // kernel otherwise.  RSGPU_SEARCH_IMPL=lane|warp forces one of them.
+    const std::string oimpl = option( "search_impl" );
+    const int impl_env = oimpl == "lane" ? 1 : ( oimpl == "warp" ? 2 : 0 );
+    const double pts_per_bin = grid->info.n_bins > 0 ? (double)grid->info.n_pts / (double)grid->info.n_bins : 0.0;
+    const double cells_axis = 2.0 * r / grid->info.cell_size + 1.0; // expected cells per axis under the window
+    const double est_candidates = pts_per_bin * cells_axis * cells_axis; // surfaces: ~2-D occupancy
+    // measured crossovers on B200 (profiles/nn_sweep_r01.md): ~300 candidate points per query for k <= 4, ~60 for k <= 16
+    const bool lane = !knn && kk <= 16 && ( impl_env == 1 || ( impl_env == 0 && est_candidates <= ( kk <= 4 ? 320.0 : 64.0 ) ) );
+    if( lane )
+    {
+      if( kk <= 1 ) { s = launch_search_lane<1>( g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else if( kk <= 4 ) { s = launch_search_lane<4>( g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else if( kk <= 8 ) { s = launch_search_lane<8>( g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else { s = launch_search_lane<16>( g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    }
+    else if( kk <= 32 ) { s = launch_search<1>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
     else if( kk <= 64 ) { s = launch_search<2>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
     else if( kk <= 128 ) { s = launch_search<4>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
     else if( kk <= 256 ) { s = launch_search<8>( knn, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }

@@ -46,11 +46,14 @@ def main():
     ap.add_argument("--queries", type=int, default=4_000_000)
     ap.add_argument("--cpu-queries", type=int, default=20_000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--impl", default="", help="force the search kernel: lane | warp (default: the library's own choice)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "nn_sweep.json"))
     args = ap.parse_args()
     import torch
     from rescan_b200 import api
     api.set_device(0)
+    if args.impl:
+        api.set_option("search_impl", args.impl)
     dev = torch.device("cuda", 0)
     peak = 6650.0
     try:

@@ -1,0 +1,105 @@
+"""Every kernel variant behind rsgpu_set_option must give the same answers: the production defaults are tested against
+the oracle in test_gpu_parity.py; here the alternatives (thread- vs warp-per-query search, warp-per-query vs 4-lane
+group scoring, bound pruning on/off, resident-block vs iteration-synchronous ICP) are held to the defaults bit for bit,
+and the thread-per-query search to the oracle directly."""
+import numpy as np
+import pytest
+
+from oracle import orcbind as O
+from rescan_b200 import api, synth
+from tests import common
+from tests.test_gpu_parity import _compare_rows, _queries
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return common.small_scene()
+
+
+@pytest.fixture(autouse=True)
+def _restore_options():
+    yield
+    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb"):
+        api.set_option(name, None)
+
+
+@pytest.mark.parametrize("impl", ["lane", "warp"])
+@pytest.mark.parametrize("radius,k", [(0.05, 1), (0.05, 16), (0.075, 8), (0.10, 3), (0.02, 5)])
+def test_radius_search_variants_match_oracle(scene, impl, radius, k):
+    p = scene.scan.pos(1)
+    og, gg = O.OrcGrid(p, 0.05), api.HashGrid(p, 0.05)
+    rng = np.random.default_rng(17)
+    q = _queries(rng, p, 4000, 0.03)
+    q[:40] += 7.0           # outside the grid
+    q[40:80] = p[:40]       # exact hits
+    api.set_option("search_impl", impl)
+    gi, gd, gn, gt = gg.radius_search(q, radius, k)
+    oi, od, on, ot = og.radius_search(q, radius, k)
+    assert gt == ot
+    _compare_rows(gi, gd, gn, oi, od, on, k)
+
+
+def test_radius_search_lane_many_cells(scene):
+    """thread-per-query kernel on windows far larger than 27 cells (capped at 512 like the reference)"""
+    p = scene.scan.pos(3)
+    og, gg = O.OrcGrid(p, 0.02), api.HashGrid(p, 0.02)
+    q = _queries(np.random.default_rng(5), p, 400, 0.02)
+    api.set_option("search_impl", "lane")
+    for radius, k in [(0.15, 16), (0.25, 8)]:
+        gi, gd, gn, gt = gg.radius_search(q, radius, k)
+        oi, od, on, ot = og.radius_search(q, radius, k)
+        assert gt == ot
+        _compare_rows(gi, gd, gn, oi, od, on, k)
+
+
+def _propose_all(scene, grid, rots, trans, top_k=0):
+    out = []
+    for o in scene.objects:
+        if o.is_static:
+            continue
+        c4, c3, c2 = (api.PointCloud(o.cloud.pos(l), o.cloud.nor(l)) for l in (4, 3, 2))
+        props, ids = api.propose_poses(c4, c3, c2, grid, rots, trans, top_k=top_k)
+        out.append((props.copy(), ids.copy()))
+    return out
+
+
+def test_scoring_variants_bit_identical(scene):
+    p, n = scene.scan.pos(1), scene.scan.nor(1)
+    grid = api.HashGrid(p, 0.05, normals=n)
+    rots, _ = common.rotation_xforms(12)
+    trans = synth.translation_seeds(scene.scan, 160, seed=9)
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    o = [x for x in scene.objects if not x.is_static][0]
+    c4 = api.PointCloud(o.cloud.pos(4), o.cloud.nor(4))
+    base_scores = api.score_pose_grid(c4, grid, rots, trans)
+    base_props = _propose_all(scene, grid, rots, trans)
+    assert sum(len(pr) for pr, _ in base_props) > 0
+    for opts in ({"score_impl": "coop"}, {"prune": "0"}, {"score_g": "8"}, {"score_minb": "4"}, {"search": "lane"}):
+        for k, v in opts.items():
+            api.set_option(k, v)
+        s = api.score_pose_grid(c4, grid, rots, trans)
+        assert (s == base_scores).all(), f"dense scores differ under {opts}"
+        for (pa, ia), (pb, ib) in zip(base_props, _propose_all(scene, grid, rots, trans)):
+            assert (ia == ib).all() and (pa == pb).all(), f"proposals differ under {opts}"
+        for k in opts:
+            api.set_option(k, None)
+
+
+def test_icp_variants_bit_identical(scene):
+    p2, n2 = scene.scan.pos(2), scene.scan.nor(2)
+    grid = api.HashGrid(p2, 0.05, normals=n2)
+    rng = np.random.default_rng(33)
+    objs, starts = [], []
+    for o in scene.objects:
+        objs.append(api.PointCloud(o.cloud.pos(2), o.cloud.nor(2)))
+        starts.append(np.stack([common.colmajor(m) for _, m in common.perturbed_poses(rng, type("S", (), {"objects": [o]})(), 5, 0.03, 0.08)]))
+    ang = np.float32(np.deg2rad(60.0))
+    base = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
+    api.set_option("icp_impl", "block")
+    alt = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
+    for (Ta, ea, ia), (Tb, eb, ib) in zip(base, alt):
+        assert (ia == ib).all() and (ea == eb).all() and (Ta == Tb).all()
+    assert max(int(i.max()) for _, _, i in base) > 6

@@ -162,3 +162,50 @@ def make_workload(name):
     rotations = posegrid.rotation_xforms(cfg["n_rot"])
     translations = synth.translation_seeds(scene.scan, cfg["n_seeds"])
     return scene, rotations, translations
+
+
+# ------------------------------------------------------------------------------------------------ label transfer / unary terms
+@dataclasses.dataclass
+class UnaryResult:
+    labels: np.ndarray      # int8 [V]: 1 + index into the sorted placement list, 0 = unlabelled (rs_pointcloud_filters.cpp:738-778)
+    placement_order: list   # indices into the caller's placement list, dynamic first / static last (:823-835)
+    data_cost: np.ndarray   # int32 [V, L] (:926-939)
+    neighbors: np.ndarray   # int32 [V, 8] candidate edges (-1 = none) and their weights (:674-722)
+    weights: np.ndarray
+
+
+def upload_object_grids(objects):
+    """level-1 hash grids of the object models (what rspf__assign_temporary_labels searches), built once per database"""
+    return [api.HashGrid(o.cloud.pos(1), 0.05, normals=o.cloud.nor(1)) for o in objects]
+
+
+def run_unary(scan_lvl1, scan_grid, placements, object_grids, is_static, with_edges=True):
+    """segment_transfer's unary path on the GPU for one scan: rspf_arrangement_to_labels (dynamic placements with
+    r = 0.05, then static ones with r = 0.075, reference rs_pointcloud_filters.cpp:823-848), the data_cost block of
+    rspf_smooth_labels (:926-939) and the 8-NN edge weights of rspf_compute_neighborhood (:674-722).
+    placements: list of (object index, 4x4 column-major float32[16]); is_static: per object."""
+    p1, n1 = scan_lvl1
+    V = len(p1)
+    order = sorted(range(len(placements)), key=lambda i: bool(is_static[placements[i][0]]))  # stable: dynamic first
+    poses = np.stack([np.asarray(placements[i][1], np.float32).reshape(16) for i in order]) if order else np.zeros((0, 16), np.float32)
+    grids = [object_grids[placements[i][0]] for i in order]
+    n_dyn = sum(not is_static[placements[i][0]] for i in order)
+    labels, min_d = np.zeros(V, np.int8), np.full(V, 1e9, np.float32)
+    if n_dyn == len(order):
+        # no static placement: first_static_obj_idx stays 0, pass 1 is empty and everything is matched with r = 0.075 (:830-835)
+        passes = ((0, len(order), 0.075),)
+    else:
+        passes = ((0, n_dyn, 0.05), (n_dyn, len(order), 0.075))
+    for first, last, r in passes:
+        if last > first:
+            api.assign_labels(p1, n1, poses, grids, first, last, r, labels, min_d)
+    lab32 = labels.astype(np.int32)
+    L = len(order) + 5
+    static_flag = np.zeros(L, np.uint8)
+    for j, i in enumerate(order):
+        static_flag[j + 1] = 1 if is_static[placements[i][0]] else 0
+    cost = api.unary_costs(lab32, static_flag, L)
+    nbr = wgt = None
+    if with_edges:
+        nbr, wgt = api.neighborhood(scan_grid, p1, n1)
+    return UnaryResult(labels, order, cost, nbr, wgt)

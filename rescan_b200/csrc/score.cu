@@ -12,6 +12,7 @@
 #include "rsgpu_internal.cuh"
 #include "nearest.cuh"
 #include "nearest_group.cuh"
+#include "warplist.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -378,6 +379,77 @@ __global__ void verify_kernel( float* __restrict__ scores, const float* __restri
   if( !( scores[i] > 0.0f ) ) { return; }
   scores[i] = fresh[i] > thr ? fresh[i] : -1.0f;
 }
+// Warp-cooperative top-k of one object's verified proposals: descending score, ties by ascending pose id (= emission
+// order).  One warp streams the scores through a sorted list of k keys held in its registers (warplist.cuh); only
+// survivors of the reference's final copy, |score| > 1e-6 (:352), enter.  sel[j] = index of the j-th best.
+template <int EPL>
+__global__ void __launch_bounds__( 32 ) topk_kernel( const float* __restrict__ scores, int n, int k, int* __restrict__ sel, int* __restrict__ n_sel )
+{
+  const int lane = threadIdx.x;
+  WarpList<EPL> list; list.init();
+  unsigned long long thr = KEY_INF;
+  int seen = 0;
+  for( int base = 0; base < n; base += 32 )
+  {
+    const int i = base + lane;
+    unsigned long long key = KEY_INF;
+    bool ok = false;
+    if( i < n )
+    {
+      const float sc = scores[i];
+      ok = fabsf( sc ) > 0.000001f;
+      uint32_t u = __float_as_uint( sc );
+      u = ( u & 0x80000000u ) ? ~u : ( u | 0x80000000u ); // ascending order of floats as unsigned
+      key = ( (unsigned long long)( ~u ) << 32 ) | (uint32_t)i; // descending score, then ascending index
+    }
+    seen += __popc( __ballot_sync( RS_FULL, ok ) );
+    unsigned m = __ballot_sync( RS_FULL, ok && key < thr );
+    while( m )
+    {
+      const int src = __ffs( m ) - 1; m &= m - 1;
+      const unsigned long long x = __shfl_sync( RS_FULL, key, src );
+      if( x < thr ) { list.insert( x, lane ); thr = list.get( k - 1 ); }
+    }
+  }
+  const int count = seen < k ? seen : k;
+#pragma unroll
+  for( int s = 0; s < EPL; ++s )
+  {
+    const int j = lane * EPL + s;
+    if( j < count ) { sel[j] = (int)(uint32_t)( list.v[s] & 0xffffffffull ); }
+  }
+  if( lane == 0 ) { *n_sel = count; }
+}
+
+// all survivors in emission order (top_k = 0): sel = indices with |score| > 1e-6, ascending
+__global__ void survivors_kernel( const float* __restrict__ scores, int n, int* __restrict__ sel, int* __restrict__ n_sel )
+{
+  // one warp, ordered compaction by ballot
+  const int lane = threadIdx.x;
+  int w = 0;
+  for( int base = 0; base < n; base += 32 )
+  {
+    const int i = base + lane;
+    const bool ok = i < n && fabsf( scores[i] ) > 0.000001f;
+    const unsigned b = __ballot_sync( RS_FULL, ok );
+    if( ok ) { sel[w + __popc( b & ( ( 1u << lane ) - 1u ) )] = i; }
+    w += __popc( b );
+  }
+  if( lane == 0 ) { *n_sel = w; }
+}
+
+// out[j] = {xform, score} of proposal sel[j], ids[j] = its dense pose id
+__global__ void gather_kernel( const int* __restrict__ sel, const int* __restrict__ n_sel, const float* __restrict__ xforms,
+                               const float* __restrict__ scores, const long long* __restrict__ pose_id, float* __restrict__ out,
+                               long long* __restrict__ ids )
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if( j >= *n_sel ) { return; }
+  const int i = sel[j];
+  for( int c = 0; c < 16; ++c ) { out[RSGPU_POSE_FLOATS * (size_t)j + c] = xforms[16 * (size_t)i + c]; }
+  out[RSGPU_POSE_FLOATS * (size_t)j + 16] = scores[i];
+  ids[j] = pose_id[i];
+}
 } // namespace
 
 extern "C" {
@@ -528,29 +600,40 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
     verify_kernel<<<( n_prop + 255 ) / 256, 256, 0, st>>>( psc.p, fresh.p, n_prop, opts.thresholds[1 + l] );
     RS_CHECK_LAUNCH();
   }
-  // survivor copy: |score| > 1e-6 (:352) — every entry here is either > threshold or -1, so all survive
-  std::vector<float> hx( (size_t)n_prop * 16 ), hs( n_prop ); std::vector<long long> hid( n_prop );
-  RS_CUDA( cudaMemcpyAsync( hx.data(), px.p, sizeof( float ) * 16 * (size_t)n_prop, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaMemcpyAsync( hs.data(), psc.p, sizeof( float ) * (size_t)n_prop, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaMemcpyAsync( hid.data(), pid.p, sizeof( long long ) * (size_t)n_prop, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
-  std::vector<int> order;
-  for( int i = 0; i < n_prop; ++i ) { if( fabsf( hs[i] ) > 0.000001f ) { order.push_back( i ); } }
+  // survivor copy: |score| > 1e-6 (:352) — every entry is either > threshold or -1, so all survive — and the
+  // per-object top-k (descending score, ties by pose id), selected on the device; only the selected rows travel
+  DevBuf<int> sel, nsel; DevBuf<float> dout; DevBuf<long long> dids;
+  const int cap_sel = opts.top_k > 0 ? std::min( opts.top_k, n_prop ) : n_prop;
+  RS_CUDA( sel.alloc( n_prop ) ); RS_CUDA( nsel.alloc( 1 ) ); RS_CUDA( dout.alloc( (size_t)cap_sel * RSGPU_POSE_FLOATS ) ); RS_CUDA( dids.alloc( cap_sel ) );
   if( opts.top_k > 0 )
   {
-    std::stable_sort( order.begin(), order.end(), [&]( int a, int b ) { return hs[a] != hs[b] ? hs[a] > hs[b] : hid[a] < hid[b]; } );
-    if( (int)order.size() > opts.top_k ) { order.resize( opts.top_k ); }
+    if( opts.top_k > 512 ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_propose_poses: top_k > 512" ); }
+    const int k = opts.top_k;
+    if( k <= 32 ) { topk_kernel<1><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }
+    else if( k <= 64 ) { topk_kernel<2><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }
+    else if( k <= 128 ) { topk_kernel<4><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }
+    else if( k <= 256 ) { topk_kernel<8><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }
+    else { topk_kernel<16><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }
   }
-  int64_t w = 0;
-  for( int i : order )
+  else { survivors_kernel<<<1, 32, 0, st>>>( psc.p, n_prop, sel.p, nsel.p ); }
+  RS_CHECK_LAUNCH();
+  gather_kernel<<<( cap_sel + 127 ) / 128, 128, 0, st>>>( sel.p, nsel.p, px.p, psc.p, pid.p, dout.p, dids.p );
+  RS_CHECK_LAUNCH();
+  int n_sel = 0;
+  RS_CUDA( cudaMemcpyAsync( &n_sel, nsel.p, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( cudaStreamSynchronize( st ) );
+  const int64_t n_copy = std::min<int64_t>( n_sel, out_cap );
+  if( n_copy > 0 )
   {
-    if( w >= out_cap ) { break; }
-    memcpy( out + RSGPU_POSE_FLOATS * w, hx.data() + 16 * (size_t)i, 64 );
-    out[RSGPU_POSE_FLOATS * w + 16] = hs[i];
-    if( out_pose_id ) { out_pose_id[w] = hid[i]; }
-    ++w;
+    RS_CUDA( cudaMemcpyAsync( out, dout.p, sizeof( float ) * RSGPU_POSE_FLOATS * (size_t)n_copy, cudaMemcpyDeviceToHost, st ) );
+    if( out_pose_id )
+    {
+      static_assert( sizeof( long long ) == sizeof( int64_t ), "pose ids are 64-bit" );
+      RS_CUDA( cudaMemcpyAsync( out_pose_id, dids.p, sizeof( int64_t ) * (size_t)n_copy, cudaMemcpyDeviceToHost, st ) );
+    }
+    RS_CUDA( cudaStreamSynchronize( st ) );
   }
-  *n_out = (int64_t)order.size(); // may exceed out_cap: the caller then knows how much room a retry needs
+  *n_out = (int64_t)n_sel; // may exceed out_cap: the caller then knows how much room a retry needs
   return RSGPU_OK;
 }
 

@@ -153,58 +153,106 @@ __device__ void ldlt_solve6( double A[6][6], const double* b, double* x )
 // correspondence hold zeros, which leave a float sum unchanged.
 constexpr int TILE_LD = 33;
 
-template <int NV, bool WITH_F64, class TermFn>
-__device__ __forceinline__ void ordered_sums( int n, TermFn term_fn, float* tile, float* fout, double* dout )
+// acc + col[0] + col[TILE_LD] + ... in row order, one dependent add per row; the loads of the next eight rows are
+// issued before the eight adds of the current ones, so the chain never waits on shared memory
+template <typename A>
+__device__ __forceinline__ A chain_add( A acc, float x );
+template <> __device__ __forceinline__ float chain_add<float>( float acc, float x ) { return __fadd_rn( acc, x ); }
+template <> __device__ __forceinline__ double chain_add<double>( double acc, float x ) { return __dadd_rn( acc, (double)x ); }
+template <typename A>
+__device__ __forceinline__ A chain_sum( A acc, const float* __restrict__ col, int rows )
 {
-  // Two tiles: while warp 0 (float sums) and warp 1 (the two fp64 sums of the error term, icp.h:250-253: columns NV-2,
-  // NV-1) walk down the rows of one tile, the remaining warps form the terms of the next one.
-  constexpr int FIRST_FILL = WITH_F64 ? 2 : 1;
-  constexpr int FILL_THREADS = ICP_THREADS - 32 * FIRST_FILL;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float fa = 0.0f; double da = 0.0;
-  const int stages = ( n + ICP_THREADS - 1 ) / ICP_THREADS;
-  auto fill = [&]( int stage ) {
-    float* buf = tile + ( stage & 1 ) * ( ICP_THREADS * TILE_LD );
-    const int base = stage * ICP_THREADS, rows = min( ICP_THREADS, n - base );
-    for( int r = tid - 32 * FIRST_FILL; r < rows; r += FILL_THREADS )
-    {
-      float t[NV];
-#pragma unroll
-      for( int v = 0; v < NV; ++v ) { t[v] = 0.0f; }
-      term_fn( base + r, t );
-#pragma unroll
-      for( int v = 0; v < NV; ++v ) { buf[r * TILE_LD + v] = t[v]; }
-    }
-  };
-  if( warp >= FIRST_FILL ) { fill( 0 ); }
-  __syncthreads();
-  for( int stage = 0; stage < stages; ++stage )
+  float x[8], y[8];
+  const int nchunk = rows >> 3;
+  int c = 0;
+  if( nchunk > 0 )
   {
-    const float* buf = tile + ( stage & 1 ) * ( ICP_THREADS * TILE_LD );
-    const int rows = min( ICP_THREADS, n - stage * ICP_THREADS );
-    if( warp == 0 )
+#pragma unroll
+    for( int j = 0; j < 8; ++j ) { x[j] = col[j * TILE_LD]; }
+  }
+  for( ; c + 2 <= nchunk; c += 2 )
+  {
+#pragma unroll
+    for( int j = 0; j < 8; ++j ) { y[j] = col[( 8 * ( c + 1 ) + j ) * TILE_LD]; }
+#pragma unroll
+    for( int j = 0; j < 8; ++j ) { acc = chain_add<A>( acc, x[j] ); }
+    if( c + 2 < nchunk )
     {
-      if( lane < NV )
+#pragma unroll
+      for( int j = 0; j < 8; ++j ) { x[j] = col[( 8 * ( c + 2 ) + j ) * TILE_LD]; }
+    }
+#pragma unroll
+    for( int j = 0; j < 8; ++j ) { acc = chain_add<A>( acc, y[j] ); }
+  }
+  if( c < nchunk ) // one chunk left, already in x
+  {
+#pragma unroll
+    for( int j = 0; j < 8; ++j ) { acc = chain_add<A>( acc, x[j] ); }
+    ++c;
+  }
+  for( int r = 8 * c; r < rows; ++r ) { acc = chain_add<A>( acc, col[r * TILE_LD] ); }
+  return acc;
+}
+
+template <int NV, bool WITH_F64, class LoadFn, class TermFn>
+__device__ __forceinline__ void ordered_sums( int n, LoadFn load_fn, TermFn term_fn, float* tile, float* fout, double* dout )
+{
+  // Three roles, pipelined over tiles of TR rows: warp 0 runs the float sums down the rows of tile s - 1, warp 1 (when
+  // asked) the two fp64 sums of the error term (icp.h:250-253: columns NV-2, NV-1), and every other thread owns one
+  // row per tile: it turns the inputs it loaded during the previous tile into the terms of tile s and issues the loads
+  // of tile s + 1, so a whole tile time hides the memory latency.
+  constexpr int FIRST_FILL = WITH_F64 ? 2 : 1;
+  constexpr int TR = ICP_THREADS - 32 * FIRST_FILL; // rows per tile = fill threads
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ft = tid - 32 * FIRST_FILL;
+  float fa = 0.0f; double da = 0.0;
+  const int stages = ( n + TR - 1 ) / TR;
+  // one pipeline step: stage s of the fill (terms from `mine`, loads of stage s + 1 into `other`) beside the sums of stage s - 1.
+  // Two input registers sets are used alternately (no copy between them: a copy would wait for the loads just issued).
+  decltype( load_fn( 0 ) ) in_a = {}, in_b = {};
+  auto step = [&]( int s, decltype( load_fn( 0 ) )& mine, decltype( load_fn( 0 ) )& other ) {
+    if( ft >= 0 )
+    {
+      if( s < stages )
       {
-#pragma unroll 8
-        for( int r = 0; r < rows; ++r ) { fa = __fadd_rn( fa, buf[r * TILE_LD + lane] ); }
+        const int inext = ( s + 1 ) * TR + ft;
+        if( inext < n ) { other = load_fn( inext ); }
+        float* buf = tile + ( s & 1 ) * ( ICP_THREADS * TILE_LD );
+        float t[NV];
+#pragma unroll
+        for( int v = 0; v < NV; ++v ) { t[v] = 0.0f; }
+        if( s * TR + ft < n ) { term_fn( mine, t ); }
+#pragma unroll
+        for( int v = 0; v < NV; ++v ) { buf[ft * TILE_LD + v] = t[v]; }
       }
     }
-    else if( WITH_F64 && warp == 1 )
+    else if( s >= 1 )
     {
-      if( lane < 2 )
+      const float* buf = tile + ( ( s - 1 ) & 1 ) * ( ICP_THREADS * TILE_LD );
+      const int rows = min( TR, n - ( s - 1 ) * TR );
+      if( warp == 0 )
       {
-#pragma unroll 8
-        for( int r = 0; r < rows; ++r ) { da = __dadd_rn( da, (double)buf[r * TILE_LD + ( NV - 2 + lane )] ); }
+        if( lane < NV ) { fa = chain_sum<float>( fa, buf + lane, rows ); }
       }
+      else if( lane < 2 ) { da = chain_sum<double>( da, buf + ( NV - 2 + lane ), rows ); } // WITH_F64, warp 1
     }
-    else if( stage + 1 < stages ) { fill( stage + 1 ); }
     __syncthreads();
+  };
+  if( ft >= 0 && ft < n ) { in_a = load_fn( ft ); }
+  for( int s = 0; s <= stages; s += 2 )
+  {
+    step( s, in_a, in_b );
+    if( s + 1 <= stages ) { step( s + 1, in_b, in_a ); }
   }
   if( warp == 0 ) { fout[lane] = fa; }
   if( WITH_F64 && warp == 1 && lane < 2 ) { dout[NV - 2 + lane] = da; }
   __syncthreads();
 }
+
+// inputs of one correspondence as the sums need them (all direct loads from the per-alignment scratch)
+struct CorrIn1 { uint32_t pos; float d; };
+struct CorrIn2 { uint2 m; float4 q, p2; };
+struct CorrIn3 { uint2 m; float4 q, p2, nn; };
 
 // what one alignment needs: which object it aligns and where its scratch lives
 struct IcpBlock
@@ -217,13 +265,14 @@ struct IcpBlock
 
 // (A) correspondences of one batch of 32 object points (icp.h:339-391), searched 8 at a time by 4-lane groups
 __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const float* __restrict__ T, const float* __restrict__ M,
-                                                      const float* __restrict__ p1, const float* __restrict__ n1, int c1n, int ib,
+                                                      const float* __restrict__ p1, const float* __restrict__ n1, int c1n, int ib, int n_batch,
                                                       double radius, float r2f, float dot_thr, float4* __restrict__ cq, uint2* __restrict__ cm,
+                                                      float4* __restrict__ cp, float4* __restrict__ cn,
                                                       uint4* __restrict__ cand, unsigned char* __restrict__ slot )
 {
   const int lane = threadIdx.x & 31;
   const int i = ib + lane;
-  const bool valid = i < c1n;
+  const bool valid = i < c1n && lane < n_batch;
   LaneQuery q;
   q.px = q.py = q.pz = q.nx = q.ny = q.nz = 0.f;
   if( valid )
@@ -261,6 +310,8 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
     cq[i] = make_float4( q.px, q.py, q.pz, h.d2 );
     float dot = h.dot > 0.0f ? h.dot : 0.0f;
     cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
+    // the correspondent's point and normal travel with the correspondence: the sums then read four plain streams
+    if( h.found ) { cp[i] = __ldg( g.recs + h.pos ); cn[i] = __ldg( g.nrm + h.pos ); }
   }
   __syncwarp();
 }
@@ -269,7 +320,8 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
 // Returns false when the reference leaves its loop before the update (no correspondences / no weight, icp.h:453-468);
 // otherwise sh.T, sh.err, sh.steps, sh.max_dist are updated and sh.stop is set when the stopping rule fires.
 template <bool EXACT>
-__device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const float4* __restrict__ cq, const uint2* __restrict__ cm, int it,
+__device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const float4* __restrict__ cq, const uint2* __restrict__ cm,
+                                            const float4* __restrict__ cp, const float4* __restrict__ cn, int it,
                                             IcpShared& sh, float* tile, float* fout, double* dout )
 {
   const int tid = threadIdx.x;
@@ -285,9 +337,10 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
       block_reduce<1>( v, sh );
       nc = (int)sh.out[0];
     }
-    ordered_sums<2, false>( c1n, [&]( int i, float* t ) {
-      if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; t[0] = d; t[1] = __fmul_rn( d, d ); }
-    }, tile, fout, dout );
+    ordered_sums<2, false>( c1n,
+      [&]( int i ) { CorrIn1 in; in.pos = cm[i].x; in.d = cq[i].w; return in; },
+      [&]( const CorrIn1& in, float* t ) { if( in.pos != 0xffffffffu ) { t[0] = in.d; t[1] = __fmul_rn( in.d, in.d ); } },
+      tile, fout, dout );
     sum_d = fout[0]; sum_dd = fout[1];
   }
   else
@@ -316,16 +369,15 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   float s7[7];
   if( EXACT )
   {
-    ordered_sums<7, false>( c1n, [&]( int i, float* t ) {
-      uint2 m = cm[i];
-      if( m.x == 0xffffffffu ) { return; }
-      float4 q = cq[i];
-      float w = weight( q, m );
-      float4 p2 = __ldg( g.recs + m.x );
-      t[0] = w;
-      t[1] = __fmul_rn( q.x, w ); t[2] = __fmul_rn( q.y, w ); t[3] = __fmul_rn( q.z, w );
-      t[4] = __fmul_rn( p2.x, w ); t[5] = __fmul_rn( p2.y, w ); t[6] = __fmul_rn( p2.z, w );
-    }, tile, fout, dout );
+    ordered_sums<7, false>( c1n,
+      [&]( int i ) { CorrIn2 in; in.m = cm[i]; in.q = cq[i]; in.p2 = cp[i]; return in; },
+      [&]( const CorrIn2& in, float* t ) {
+        if( in.m.x == 0xffffffffu ) { return; }
+        const float w = weight( in.q, in.m );
+        t[0] = w;
+        t[1] = __fmul_rn( in.q.x, w ); t[2] = __fmul_rn( in.q.y, w ); t[3] = __fmul_rn( in.q.z, w );
+        t[4] = __fmul_rn( in.p2.x, w ); t[5] = __fmul_rn( in.p2.y, w ); t[6] = __fmul_rn( in.p2.z, w );
+      }, tile, fout, dout );
 #pragma unroll
     for( int j = 0; j < 7; ++j ) { s7[j] = fout[j]; }
   }
@@ -338,7 +390,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
       if( m.x == 0xffffffffu ) { continue; }
       float4 q = cq[i];
       float w = weight( q, m );
-      float4 p2 = __ldg( g.recs + m.x );
+      float4 p2 = cp[i];
       v[0] += (double)w;
       v[1] += (double)__fmul_rn( q.x, w ); v[2] += (double)__fmul_rn( q.y, w ); v[3] += (double)__fmul_rn( q.z, w );
       v[4] += (double)__fmul_rn( p2.x, w ); v[5] += (double)__fmul_rn( p2.y, w ); v[6] += (double)__fmul_rn( p2.z, w );
@@ -355,12 +407,13 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   __syncthreads();
   // ---- (B3) normal equations (icp.h:226-252): TL = sum w c c^T, TR = sum w c n^T, BR = sum w n n^T, b = sum w [c;n] (d.n)
   // 29 terms per correspondence: TL (6 unique), TR (9), BR (6 unique), b (6), w (d.n)^2, w
-  auto terms29 = [&]( int i, float* t ) -> bool {
-    uint2 m = cm[i];
+  auto load29 = [&]( int i ) { CorrIn3 in; in.m = cm[i]; in.q = cq[i]; in.p2 = cp[i]; in.nn = cn[i]; return in; };
+  auto terms29 = [&]( const CorrIn3& in, float* t ) -> bool {
+    const uint2 m = in.m;
     if( m.x == 0xffffffffu ) { return false; }
-    float4 q4 = cq[i];
+    const float4 q4 = in.q;
     float w = weight( q4, m );
-    float4 p2 = __ldg( g.recs + m.x ), nn = __ldg( g.nrm + m.x );
+    const float4 p2 = in.p2, nn = in.nn;
     float px = __fsub_rn( q4.x, c1x ), py = __fsub_rn( q4.y, c1y ), pz = __fsub_rn( q4.z, c1z );
     float qx = __fsub_rn( p2.x, c2x ), qy = __fsub_rn( p2.y, c2y ), qz = __fsub_rn( p2.z, c2z );
     float dx = __fsub_rn( px, qx ), dy = __fsub_rn( py, qy ), dz = __fsub_rn( pz, qz );
@@ -390,7 +443,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   };
   if( EXACT )
   {
-    ordered_sums<29, true>( c1n, [&]( int i, float* t ) { terms29( i, t ); }, tile, fout, dout );
+    ordered_sums<29, true>( c1n, load29, [&]( const CorrIn3& in, float* t ) { terms29( in, t ); }, tile, fout, dout );
     if( tid < 27 ) { sh.out[tid] = (double)fout[tid]; }
     if( tid == 27 || tid == 28 ) { sh.out[tid] = dout[tid]; }
     __syncthreads();
@@ -403,7 +456,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
     for( int i = tid; i < c1n; i += ICP_THREADS )
     {
       float t[29];
-      if( terms29( i, t ) )
+      if( terms29( load29( i ), t ) )
       {
 #pragma unroll
         for( int j = 0; j < 29; ++j ) { v[j] += (double)t[j]; }
@@ -456,8 +509,8 @@ template <bool EXACT>
 __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const IcpBlock* __restrict__ blocks,
                                                              float* __restrict__ T1_io, const float* __restrict__ T2i, float max_dist0,
                                                              float dot_thr, int max_iter, float4* __restrict__ scratch_q,
-                                                             uint2* __restrict__ scratch_m, float* __restrict__ errs,
-                                                             int* __restrict__ iters )
+                                                             uint2* __restrict__ scratch_m, float4* __restrict__ scratch_p,
+                                                             float4* __restrict__ scratch_n, float* __restrict__ errs, int* __restrict__ iters )
 {
   const IcpBlock blk = blocks[blockIdx.x];
   __shared__ IcpShared sh;
@@ -469,6 +522,8 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
   float4* cq = scratch_q + blk.scratch_off;  // {q, d2}
   uint2* cm = scratch_m + blk.scratch_off;   // {recs position or ~0, dot bits}
+  float4* cp = scratch_p + blk.scratch_off;  // the correspondent's point ...
+  float4* cn = scratch_n + blk.scratch_off;  // ... and normal
   if( tid < 16 ) { sh.T[tid] = T1_io[16 * (size_t)b + tid]; sh.M[tid] = T2i[tid]; }
   if( tid == 0 ) { sh.max_dist = max_dist0; sh.prev_err = 1e6f; sh.err = 1e6f; sh.stop = 0; sh.steps = 0; }
   __syncthreads();
@@ -479,10 +534,10 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
     const float r2f = (float)__dmul_rn( radius, radius );
     for( int ib = warp * 32; ib < blk.n; ib += ICP_WARPS * 32 )
     {
-      icp_correspond_batch( g, sh.T, sh.M, blk.p1, blk.n1, blk.n, ib, radius, r2f, dot_thr, cq, cm, s_cand[warp], s_slot[warp] );
+      icp_correspond_batch( g, sh.T, sh.M, blk.p1, blk.n1, blk.n, ib, 32, radius, r2f, dot_thr, cq, cm, cp, cn, s_cand[warp], s_slot[warp] );
     }
     __syncthreads();
-    if( !icp_update<EXACT>( g, blk.n, cq, cm, it, sh, tile, fout, dout ) ) { break; }
+    if( !icp_update<EXACT>( g, blk.n, cq, cm, cp, cn, it, sh, tile, fout, dout ) ) { break; }
     if( sh.stop ) { break; }
   }
   __syncthreads();
@@ -503,9 +558,11 @@ struct IcpState
 };
 
 __global__ void __launch_bounds__( ICP_THREADS ) icp_search_kernel( GridView g, const IcpBlock* __restrict__ blocks, const IcpState* __restrict__ state,
-                                                                    const unsigned* __restrict__ task_start /* n_align + 1 */, int n_align,
+                                                                    const int* __restrict__ ids /* alignments of this partition */,
+                                                                    const unsigned* __restrict__ task_start /* n_align + 1 */, int n_align, int pts_per_task,
                                                                     const float* __restrict__ T2i, float dot_thr, float4* __restrict__ scratch_q,
-                                                                    uint2* __restrict__ scratch_m )
+                                                                    uint2* __restrict__ scratch_m, float4* __restrict__ scratch_p,
+                                                                    float4* __restrict__ scratch_n )
 {
   __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
   __shared__ unsigned char s_slot[ICP_WARPS][32];
@@ -519,24 +576,26 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_search_kernel( GridView g, 
     // alignment of this task: last a with task_start[a] <= task
     int lo = 0, hi = n_align;
     while( hi - lo > 1 ) { int mid = ( lo + hi ) >> 1; if( __ldg( task_start + mid ) <= task ) { lo = mid; } else { hi = mid; } }
-    const int a = lo;
+    const int a = ids[lo];
     if( !state[a].active ) { continue; }
     const IcpBlock blk = blocks[a];
     if( lane < 16 ) { s_T[warp][lane] = state[a].T[lane]; }
     __syncwarp();
     const double radius = (double)state[a].max_dist;
     const float r2f = (float)__dmul_rn( radius, radius );
-    icp_correspond_batch( g, s_T[warp], s_M, blk.p1, blk.n1, blk.n, (int)( task - __ldg( task_start + a ) ) * 32, radius, r2f, dot_thr,
-                          scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, s_cand[warp], s_slot[warp] );
+    icp_correspond_batch( g, s_T[warp], s_M, blk.p1, blk.n1, blk.n, (int)( task - __ldg( task_start + lo ) ) * pts_per_task, pts_per_task, radius, r2f, dot_thr,
+                          scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, scratch_p + blk.scratch_off, scratch_n + blk.scratch_off,
+                          s_cand[warp], s_slot[warp] );
   }
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__( ICP_THREADS ) icp_solve_kernel( GridView g, const IcpBlock* __restrict__ blocks, IcpState* __restrict__ state, int it,
-                                                                   const float4* __restrict__ scratch_q, const uint2* __restrict__ scratch_m,
-                                                                   int* __restrict__ n_active )
+__global__ void __launch_bounds__( ICP_THREADS ) icp_solve_kernel( GridView g, const IcpBlock* __restrict__ blocks, IcpState* __restrict__ state,
+                                                                   const int* __restrict__ ids, int it, const float4* __restrict__ scratch_q,
+                                                                   const uint2* __restrict__ scratch_m, const float4* __restrict__ scratch_p,
+                                                                   const float4* __restrict__ scratch_n, int* __restrict__ n_active )
 {
-  const int a = blockIdx.x, tid = threadIdx.x;
+  const int a = ids[blockIdx.x], tid = threadIdx.x;
   if( !state[a].active ) { return; }
   const IcpBlock blk = blocks[a];
   __shared__ IcpShared sh;
@@ -546,7 +605,8 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_solve_kernel( GridView g, c
   if( tid < 16 ) { sh.T[tid] = state[a].T[tid]; }
   if( tid == 0 ) { sh.max_dist = state[a].max_dist; sh.prev_err = state[a].err; sh.err = state[a].err; sh.stop = 0; sh.steps = state[a].steps; }
   __syncthreads();
-  const bool updated = icp_update<EXACT>( g, blk.n, scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, it, sh, tile, fout, dout );
+  const bool updated = icp_update<EXACT>( g, blk.n, scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, scratch_p + blk.scratch_off,
+                                              scratch_n + blk.scratch_off, it, sh, tile, fout, dout );
   __syncthreads();
   if( tid < 16 ) { state[a].T[tid] = sh.T[tid]; }
   if( tid == 0 )
@@ -658,8 +718,18 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   std::vector<IcpBlock> hb( total );
   std::vector<float> hT( total * 16 );
   std::vector<IcpState> hs( split ? total : 0 );
-  std::vector<unsigned> htask( split ? total + 1 : 0 );
-  size_t bi = 0, off = 0, n_tasks = 0;
+  // the split variant runs the alignments as NPART interleaved partitions on separate streams, so that the solve
+  // launches of one partition (a few busy warps per alignment) overlap the search launches of the others
+  int NPART = 2;
+  { const std::string o = option( "icp_parts" ); if( !o.empty() ) { NPART = std::min( 4, std::max( 1, atoi( o.c_str() ) ) ); } }
+  if( (size_t)NPART > total ) { NPART = (int)total; }
+  // object points per warp task of the search launches: small tasks shorten the late iterations (few alignments left,
+  // the launch is then pure latency), at the price of idle lanes in the cell-window pass
+  int TPT = 16;
+  { const std::string o = option( "icp_tpt" ); if( !o.empty() ) { const int v = atoi( o.c_str() ); if( v == 8 || v == 16 || v == 32 ) { TPT = v; } } }
+  std::vector<std::vector<int>> part_ids( NPART );
+  std::vector<std::vector<unsigned>> part_task( NPART );
+  size_t bi = 0, off = 0;
   for( int j = 0; j < n_jobs; ++j )
   {
     const rsgpu_icp_job_t& J = jobs[j];
@@ -672,16 +742,18 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
       {
         memcpy( hs[bi].T, J.T1 + 16 * (size_t)b, 64 );
         hs[bi].max_dist = max_dist; hs[bi].prev_err = 1e6f; hs[bi].err = 1e6f; hs[bi].active = 1; hs[bi].steps = 0;
-        htask[bi] = (unsigned)n_tasks;
-        n_tasks += (size_t)( ( J.object->n + 31 ) / 32 );
+        const int part = (int)( bi % (size_t)NPART );
+        if( part_task[part].empty() ) { part_task[part].push_back( 0u ); }
+        const unsigned long long next = (unsigned long long)part_task[part].back() + (unsigned long long)( ( J.object->n + TPT - 1 ) / TPT );
+        if( next > 0xffffffffull ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_icp_align: too many points" ); }
+        part_ids[part].push_back( (int)bi );
+        part_task[part].push_back( (unsigned)next );
       }
     }
   }
-  if( split ) { htask[total] = (unsigned)n_tasks; }
-  if( n_tasks > 0xffffffffull ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_icp_align: too many points" ); }
-  DevBuf<IcpBlock> dB; DevBuf<float> dT, dT2i, derr; DevBuf<int> dit; DevBuf<float4> sq; DevBuf<uint2> sm;
+  DevBuf<IcpBlock> dB; DevBuf<float> dT, dT2i, derr; DevBuf<int> dit; DevBuf<float4> sq, sp, sn; DevBuf<uint2> sm;
   RS_CUDA( dB.alloc( total ) ); RS_CUDA( dT.alloc( total * 16 ) ); RS_CUDA( dT2i.alloc( 16 ) ); RS_CUDA( derr.alloc( total ) ); RS_CUDA( dit.alloc( total ) );
-  RS_CUDA( sq.alloc( scratch ) ); RS_CUDA( sm.alloc( scratch ) );
+  RS_CUDA( sq.alloc( scratch ) ); RS_CUDA( sm.alloc( scratch ) ); RS_CUDA( sp.alloc( scratch ) ); RS_CUDA( sn.alloc( scratch ) );
   RS_CUDA( cudaMemcpyAsync( dB.p, hb.data(), sizeof( IcpBlock ) * total, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemcpyAsync( dT2i.p, T2i, 64, cudaMemcpyHostToDevice, st ) );
   const size_t tile_bytes = 2 * sizeof( float ) * ICP_THREADS * TILE_LD; // two tiles (ordered_sums)
@@ -689,35 +761,74 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   std::vector<float> herr( total ); std::vector<int> hit( total );
   if( split )
   {
-    DevBuf<IcpState> dS; DevBuf<unsigned> dtask; DevBuf<int> dact;
-    RS_CUDA( dS.alloc( total ) ); RS_CUDA( dtask.alloc( total + 1 ) ); RS_CUDA( dact.alloc( (size_t)max_iter ) );
+    DevBuf<IcpState> dS;
+    RS_CUDA( dS.alloc( total ) );
     RS_CUDA( cudaMemcpyAsync( dS.p, hs.data(), sizeof( IcpState ) * total, cudaMemcpyHostToDevice, st ) );
-    RS_CUDA( cudaMemcpyAsync( dtask.p, htask.data(), sizeof( unsigned ) * ( total + 1 ), cudaMemcpyHostToDevice, st ) );
-    RS_CUDA( cudaMemsetAsync( dact.p, 0, sizeof( int ) * (size_t)max_iter, st ) );
+    std::vector<DevBuf<int>> dids( NPART ), dact( NPART ); std::vector<DevBuf<unsigned>> dtask( NPART );
+    for( int p = 0; p < NPART; ++p )
+    {
+      const size_t np = part_ids[p].size();
+      RS_CUDA( dids[p].alloc( np ) ); RS_CUDA( dtask[p].alloc( np + 1 ) ); RS_CUDA( dact[p].alloc( (size_t)max_iter ) );
+      RS_CUDA( cudaMemcpyAsync( dids[p].p, part_ids[p].data(), sizeof( int ) * np, cudaMemcpyHostToDevice, st ) );
+      RS_CUDA( cudaMemcpyAsync( dtask[p].p, part_task[p].data(), sizeof( unsigned ) * ( np + 1 ), cudaMemcpyHostToDevice, st ) );
+      RS_CUDA( cudaMemsetAsync( dact[p].p, 0, sizeof( int ) * (size_t)max_iter, st ) );
+    }
     if( exact ) { RS_CUDA( cudaFuncSetAttribute( icp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) ); }
     int n_sm = 148;
     cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, rt().device );
-    const unsigned search_blocks = (unsigned)std::min<size_t>( ( n_tasks + ICP_WARPS - 1 ) / ICP_WARPS, (size_t)n_sm * 16 );
+    cudaStream_t* aux = nullptr;
+    RS_TRY( aux_streams( NPART, &aux ) );
+    cudaEvent_t fork = nullptr, join[4] = { nullptr, nullptr, nullptr, nullptr };
+    RS_CUDA( cudaEventCreateWithFlags( &fork, cudaEventDisableTiming ) );
+    for( int p = 0; p < NPART; ++p ) { RS_CUDA( cudaEventCreateWithFlags( &join[p], cudaEventDisableTiming ) ); }
+    int status = RSGPU_OK;
     {
       ProfScope prof( "icp" );
-      // the host looks at the number of still-running alignments every CHECK iterations (one 4-byte copy)
+      cudaEventRecord( fork, st );
+      for( int p = 0; p < NPART; ++p ) { cudaStreamWaitEvent( aux[p], fork, 0 ); }
+      // the host looks at the number of still-running alignments every CHECK iterations (one 4-byte copy per partition)
       const int CHECK = 4;
-      for( int it = 0; it < max_iter; ++it )
+      std::vector<char> done( NPART, 0 );
+      const bool phase_prof = rt().profile && option( "icp_phases" ) == "1";
+      for( int it = 0; it < max_iter && status == RSGPU_OK; ++it )
       {
-        icp_search_kernel<<<search_blocks, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dS.p, dtask.p, (int)total, dT2i.p, dot_thr, sq.p, sm.p );
-        RS_CHECK_LAUNCH();
-        if( exact ) { icp_solve_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dS.p, it, sq.p, sm.p, dact.p + it ); }
-        else { icp_solve_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dS.p, it, sq.p, sm.p, dact.p + it ); }
-        RS_CHECK_LAUNCH();
+        for( int p = 0; p < NPART; ++p )
+        {
+          if( done[p] ) { continue; }
+          const int np = (int)part_ids[p].size();
+          const unsigned n_tasks = part_task[p].back();
+          const unsigned search_blocks = (unsigned)std::min<size_t>( ( (size_t)n_tasks + ICP_WARPS - 1 ) / ICP_WARPS, (size_t)n_sm * 16 );
+          // "icp_phases" = 1: time the two kinds of launches separately (rsgpu_profile_get "icp_search" / "icp_solve")
+          cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+          if( phase_prof ) { cudaEventCreate( &e0 ); cudaEventCreate( &e1 ); cudaEventCreate( &e2 ); cudaEventRecord( e0, aux[p] ); }
+          icp_search_kernel<<<search_blocks, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, dtask[p].p, np, TPT, dT2i.p, dot_thr, sq.p, sm.p, sp.p, sn.p );
+          count_launch();
+          if( phase_prof ) { cudaEventRecord( e1, aux[p] ); }
+          if( exact ) { icp_solve_kernel<true><<<(unsigned)np, ICP_THREADS, tile_bytes, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
+          else { icp_solve_kernel<false><<<(unsigned)np, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
+          count_launch();
+          if( phase_prof ) { cudaEventRecord( e2, aux[p] ); prof_add_pending( "icp_search", e0, e1, true, false ); prof_add_pending( "icp_solve", e1, e2, true, true ); }
+        }
+        if( cudaGetLastError() != cudaSuccess ) { status = fail( RSGPU_ERR_CUDA, "rsgpu_icp_align: kernel launch failed" ); break; }
         if( it % CHECK == CHECK - 1 || it == max_iter - 1 )
         {
-          int running = 0;
-          RS_CUDA( cudaMemcpyAsync( &running, dact.p + it, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
-          RS_CUDA( cudaStreamSynchronize( st ) );
-          if( running == 0 ) { break; }
+          int running[4] = { 0, 0, 0, 0 };
+          for( int p = 0; p < NPART; ++p ) { if( !done[p] ) { cudaMemcpyAsync( &running[p], dact[p].p + it, sizeof( int ), cudaMemcpyDeviceToHost, aux[p] ); } }
+          bool all_done = true;
+          for( int p = 0; p < NPART; ++p )
+          {
+            if( done[p] ) { continue; }
+            if( cudaStreamSynchronize( aux[p] ) != cudaSuccess ) { status = cuda_fail( cudaGetLastError(), "icp partition", __FILE__, __LINE__ ); }
+            if( running[p] == 0 ) { done[p] = 1; } else { all_done = false; }
+          }
+          if( all_done ) { break; }
         }
       }
+      for( int p = 0; p < NPART; ++p ) { cudaEventRecord( join[p], aux[p] ); cudaStreamWaitEvent( st, join[p], 0 ); }
     }
+    cudaEventDestroy( fork );
+    for( int p = 0; p < NPART; ++p ) { cudaEventDestroy( join[p] ); }
+    RS_TRY( status );
     RS_CUDA( cudaMemcpyAsync( hs.data(), dS.p, sizeof( IcpState ) * total, cudaMemcpyDeviceToHost, st ) );
     RS_CUDA( cudaStreamSynchronize( st ) );
     for( size_t i = 0; i < total; ++i ) { memcpy( &hT[i * 16], hs[i].T, 64 ); herr[i] = hs[i].err; hit[i] = hs[i].steps; }
@@ -730,9 +841,9 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
       if( exact )
       {
         RS_CUDA( cudaFuncSetAttribute( icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
-        icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, derr.p, dit.p );
+        icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, sp.p, sn.p, derr.p, dit.p );
       }
-      else { icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, derr.p, dit.p ); }
+      else { icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, sp.p, sn.p, derr.p, dit.p ); }
       RS_CHECK_LAUNCH();
     }
     RS_CUDA( cudaMemcpyAsync( hT.data(), dT.p, sizeof( float ) * 16 * total, cudaMemcpyDeviceToHost, st ) );

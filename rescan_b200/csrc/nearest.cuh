@@ -66,7 +66,8 @@ __device__ __forceinline__ bool cone_possible( const float4* __restrict__ cones,
   if( !c.on ) { return true; }
   float4 u = __ldg( cones + cell_id ); // {ux, uy, uz, cos(alpha)} (cos(alpha) <= 0: no usable cone)
   if( !( u.w > 0.0f ) ) { return true; }
-  float sa = sqrtf( fmaxf( 0.0f, 1.0f - u.w * u.w ) ) + 1e-5f;
+  const float s2 = fmaxf( 1e-12f, 1.0f - u.w * u.w );
+  float sa = s2 * rsqrtf( s2 ) + 2e-5f; // sin(alpha) from the hardware reciprocal square root, rounded up by the margin
   float ct = u.x * nx + u.y * ny + u.z * nz;
   return !( ct < u.w * c.cb - sa * c.sb );
 }

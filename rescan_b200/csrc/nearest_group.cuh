@@ -99,6 +99,12 @@ __device__ __forceinline__ Stage1 stage1_test( const GridView& g, double radius,
   return r;
 }
 
+static __device__ __noinline__ float normal_dot_call( const float4* __restrict__ nrm, uint32_t p, float nx, float ny, float nz )
+{
+  const float4 mm = __ldg( nrm + p );
+  return dot3_exact( mm.x, mm.y, mm.z, nx, ny, nz );
+}
+
 template <int G>
 __device__ __forceinline__ unsigned long long group_min64( unsigned long long v, unsigned gmask )
 {
@@ -210,16 +216,16 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
       const float4 rec1 = __ldg( g.recs + ( two ? p + G : p ) );
       const unsigned long long key0 = ( (unsigned long long)__float_as_uint( dist2_exact( rec0, px, py, pz ) ) << 32 ) | p;
       const unsigned long long key1 = ( (unsigned long long)__float_as_uint( dist2_exact( rec1, px, py, pz ) ) << 32 ) | ( p + G );
+      // the normal test is rare once a near point is known: keep it a real branch (an out-of-line call stops the
+      // compiler from predicating its ~15 instructions into every step)
       if( key0 < lk )
       {
-        const float4 mm = __ldg( g.nrm + p );
-        const float dot = dot3_exact( mm.x, mm.y, mm.z, nx, ny, nz );
+        const float dot = normal_dot_call( g.nrm, p, nx, ny, nz );
         if( dot >= dot_thr && dot <= 1.0f ) { lk = key0; mykey = key0; mydot = dot; }
       }
       if( two && key1 < lk )
       {
-        const float4 mm = __ldg( g.nrm + p + G );
-        const float dot = dot3_exact( mm.x, mm.y, mm.z, nx, ny, nz );
+        const float dot = normal_dot_call( g.nrm, p + G, nx, ny, nz );
         if( dot >= dot_thr && dot <= 1.0f ) { lk = key1; mykey = key1; mydot = dot; }
       }
     }

@@ -28,6 +28,8 @@ int cuda_fail( cudaError_t e, const char* what, const char* file, int line );
 int ensure_device();
 std::string option( const char* key );   // value set by rsgpu_set_option, else environment RSGPU_<KEY>, else ""
 void set_option( const char* key, const char* value );
+int aux_streams( int n, cudaStream_t** out ); // helper streams (non-blocking) for internally overlapped work
+void prof_add_pending( const char* name, cudaEvent_t a, cudaEvent_t b, bool own_a, bool own_b );
 void count_launch(); // one of OUR kernels was launched (library kernels such as CUB are not counted)
 
 // RAII device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are enqueued on the
@@ -164,21 +166,23 @@ __device__ __forceinline__ CellWindow make_window( const GridView& g, float px, 
 {
   CellWindow w;
   w.qx = __fsub_rn( px, g.mnx ); w.qy = __fsub_rn( py, g.mny ); w.qz = __fsub_rn( pz, g.mnz );
-  double dq[3] = { (double)w.qx, (double)w.qy, (double)w.qz };
-  long long c0[3], lo[3], hi[3];
+  const double dq[3] = { (double)w.qx, (double)w.qy, (double)w.qz };
+  int c0[3], lo[3], hi[3];
 #pragma unroll
   for( int a = 0; a < 3; ++a )
   {
-    c0[a] = __double2ll_rz( __dmul_rn( dq[a], g.inv_cell ) );
-    hi[a] = __double2ll_rz( __dmul_rn( __dadd_rn( dq[a], radius ), g.inv_cell ) );
-    lo[a] = __double2ll_rz( __dmul_rn( __dsub_rn( dq[a], radius ), g.inv_cell ) );
+    // (int64)( q * inv_cell ) of the reference (:1165-1183); the saturating 32-bit conversion followed by the clamps
+    // below gives the same cell numbers as the 64-bit one for every finite input
+    c0[a] = __double2int_rz( __dmul_rn( dq[a], g.inv_cell ) );
+    hi[a] = __double2int_rz( __dmul_rn( __dadd_rn( dq[a], radius ), g.inv_cell ) );
+    lo[a] = __double2int_rz( __dmul_rn( __dsub_rn( dq[a], radius ), g.inv_cell ) );
   }
-  const long long big = 1 << 28;
-  w.c0x = clamp_ll( c0[0], -big, big ); w.c0y = clamp_ll( c0[1], -big, big ); w.c0z = clamp_ll( c0[2], -big, big );
+  const int big = 1 << 28;
+  w.c0x = min( max( c0[0], -big ), big ); w.c0y = min( max( c0[1], -big ), big ); w.c0z = min( max( c0[2], -big ), big );
   int hx, hy, hz;
-  w.lox = clamp_ll( lo[0], 0, g.W ); hx = clamp_ll( hi[0], -1, g.W - 1 );
-  w.loy = clamp_ll( lo[1], 0, g.H ); hy = clamp_ll( hi[1], -1, g.H - 1 );
-  w.loz = clamp_ll( lo[2], 0, g.D ); hz = clamp_ll( hi[2], -1, g.D - 1 );
+  w.lox = min( max( lo[0], 0 ), g.W ); hx = min( max( hi[0], -1 ), g.W - 1 );
+  w.loy = min( max( lo[1], 0 ), g.H ); hy = min( max( hi[1], -1 ), g.H - 1 );
+  w.loz = min( max( lo[2], 0 ), g.D ); hz = min( max( hi[2], -1 ), g.D - 1 );
   w.nx = hx - w.lox + 1; w.ny = hy - w.loy + 1; w.nz = hz - w.loz + 1;
   if( w.nx <= 0 || w.ny <= 0 || w.nz <= 0 ) { w.nx = w.ny = w.nz = 0; }
   long long n = (long long)w.nx * w.ny * w.nz;

@@ -15,7 +15,7 @@ static thread_local std::string g_err;
 static std::mutex g_prof_mu;
 struct ProfEntry { double ms = 0; int64_t launches = 0; };
 static std::map<std::string, ProfEntry> g_prof;
-struct Pending { std::string name; cudaEvent_t a, b; };
+struct Pending { std::string name; cudaEvent_t a, b; bool own_a = true, own_b = true; };
 static std::vector<Pending>* g_pending = nullptr;
 
 static std::atomic<long long> g_launches{ 0 };
@@ -47,6 +47,19 @@ Runtime& rt()
 {
   static Runtime r;
   return r;
+}
+
+// helper streams for work the library overlaps internally (ICP partitions); created once per process
+int aux_streams( int n, cudaStream_t** out )
+{
+  static cudaStream_t streams[4] = { nullptr, nullptr, nullptr, nullptr };
+  if( n > 4 ) { return fail( RSGPU_ERR_INVALID, "rsgpu: at most 4 helper streams" ); }
+  for( int i = 0; i < n; ++i )
+  {
+    if( !streams[i] ) { RS_CUDA( cudaStreamCreateWithFlags( &streams[i], cudaStreamNonBlocking ) ); }
+  }
+  *out = streams;
+  return RSGPU_OK;
 }
 
 int fail( int code, const std::string& msg )
@@ -106,9 +119,19 @@ static void drain_pending()
       g_prof[p.name].ms += ms;
       g_prof[p.name].launches += 1;
     }
-    cudaEventDestroy( p.a ); cudaEventDestroy( p.b );
+    if( p.own_a ) { cudaEventDestroy( p.a ); }
+    if( p.own_b ) { cudaEventDestroy( p.b ); }
   }
   g_pending->clear();
+}
+
+// a - b interval measured by the caller's own events; the events are destroyed when the interval is read
+// (own_x false: that event also bounds a LATER pending interval, which destroys it)
+void prof_add_pending( const char* name, cudaEvent_t a, cudaEvent_t b, bool own_a, bool own_b )
+{
+  std::lock_guard<std::mutex> lk( g_prof_mu );
+  if( !g_pending ) { g_pending = new std::vector<Pending>(); }
+  g_pending->push_back( Pending{ name, a, b, own_a, own_b } );
 }
 
 ProfScope::ProfScope( const char* n ) : name( n )
@@ -123,7 +146,7 @@ ProfScope::~ProfScope()
   cudaEventRecord( b, rt().stream );
   std::lock_guard<std::mutex> lk( g_prof_mu );
   if( !g_pending ) { g_pending = new std::vector<Pending>(); }
-  g_pending->push_back( Pending{ name, a, b } );
+  g_pending->push_back( Pending{ name, a, b, true, true } );
 }
 } // namespace rs
 

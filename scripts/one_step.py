@@ -29,6 +29,6 @@ h = hashlib.sha1()
 for p, i in zip(res.proposals, res.pose_ids):
     h.update(np.ascontiguousarray(p).tobytes())
     h.update(np.ascontiguousarray(i).tobytes())
-prof = {n: round(api.profile_get(n)[0] / n_steps, 3) for n in ("grid_build", "score_dense", "score", "icp")}
+prof = {n: round(api.profile_get(n)[0] / n_steps, 3) for n in ("grid_build", "score_dense", "score", "icp", "icp_search", "icp_solve")}
 env = {k: v for k, v in os.environ.items() if k.startswith("RSGPU_")}
 print(f"env {env} wall {dt * 1e3:.2f} ms/step kernels {prof} evaluations {res.n_evaluations} launches {api.launch_count()} digest {h.hexdigest()[:12]}")

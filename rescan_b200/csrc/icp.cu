@@ -265,7 +265,7 @@ struct IcpBlock
 
 // (A) correspondences of one batch of 32 object points (icp.h:339-391), searched 8 at a time by 4-lane groups
 __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const float* __restrict__ T, const float* __restrict__ M,
-                                                      const float* __restrict__ p1, const float* __restrict__ n1, int c1n, int ib, int n_batch,
+                                                      const float* __restrict__ p1, const float* __restrict__ n1, int c1n, int ib, int n_batch, bool warm,
                                                       double radius, float r2f, float dot_thr, float4* __restrict__ cq, uint2* __restrict__ cm,
                                                       float4* __restrict__ cp, float4* __restrict__ cn,
                                                       uint4* __restrict__ cand, unsigned char* __restrict__ slot )
@@ -285,14 +285,29 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
   }
   const rsg::Stage1 s1 = rsg::stage1_test( g, radius, dot_thr, true, q.px, q.py, q.pz, q.nx, q.ny, q.nz, valid );
   const bool fastq = s1.active && s1.fast, slowq = s1.active && !s1.fast;
+  // warm start: the previous iteration's correspondent, if it is still compatible and inside the (shrunken) radius,
+  // bounds the search from its first cell on (the scratch starts out as "no correspondence")
+  unsigned long long seedkey = ~0ull; float seeddot = 0.f;
+  if( fastq && warm )
+  {
+    const uint32_t prev = cm[i].x;
+    if( prev != 0xffffffffu )
+    {
+      const float4 rec = __ldg( g.recs + prev ), mm = __ldg( g.nrm + prev );
+      const float d2 = dist2_exact( rec, q.px, q.py, q.pz );
+      const float dot = dot3_exact( mm.x, mm.y, mm.z, q.nx, q.ny, q.nz );
+      if( d2 < r2f && dot >= dot_thr && dot <= 1.0f ) { seedkey = ( (unsigned long long)__float_as_uint( d2 ) << 32 ) | prev; seeddot = dot; }
+    }
+  }
   const unsigned fastm = __ballot_sync( RS_FULL, fastq );
   const int rank = __popc( fastm & ( ( 1u << lane ) - 1u ) );
   if( fastq ) { slot[rank] = (unsigned char)lane; }
   __syncwarp();
-  auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz ) -> bool {
+  auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz, unsigned long long& sk, float& sd ) -> bool {
     const int src = slot[r];
     px = __shfl_sync( RS_FULL, q.px, src ); py = __shfl_sync( RS_FULL, q.py, src ); pz = __shfl_sync( RS_FULL, q.pz, src );
     nx = __shfl_sync( RS_FULL, q.nx, src ); ny = __shfl_sync( RS_FULL, q.ny, src ); nz = __shfl_sync( RS_FULL, q.nz, src );
+    sk = __shfl_sync( RS_FULL, seedkey, src ); sd = __shfl_sync( RS_FULL, seeddot, src );
     return true;
   };
   const NearestHit hr = rsg::group_round<ICP_G>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, cand );
@@ -534,7 +549,7 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
     const float r2f = (float)__dmul_rn( radius, radius );
     for( int ib = warp * 32; ib < blk.n; ib += ICP_WARPS * 32 )
     {
-      icp_correspond_batch( g, sh.T, sh.M, blk.p1, blk.n1, blk.n, ib, 32, radius, r2f, dot_thr, cq, cm, cp, cn, s_cand[warp], s_slot[warp] );
+      icp_correspond_batch( g, sh.T, sh.M, blk.p1, blk.n1, blk.n, ib, 32, it > 0, radius, r2f, dot_thr, cq, cm, cp, cn, s_cand[warp], s_slot[warp] );
     }
     __syncthreads();
     if( !icp_update<EXACT>( g, blk.n, cq, cm, cp, cn, it, sh, tile, fout, dout ) ) { break; }
@@ -583,7 +598,7 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_search_kernel( GridView g, 
     __syncwarp();
     const double radius = (double)state[a].max_dist;
     const float r2f = (float)__dmul_rn( radius, radius );
-    icp_correspond_batch( g, s_T[warp], s_M, blk.p1, blk.n1, blk.n, (int)( task - __ldg( task_start + lo ) ) * pts_per_task, pts_per_task, radius, r2f, dot_thr,
+    icp_correspond_batch( g, s_T[warp], s_M, blk.p1, blk.n1, blk.n, (int)( task - __ldg( task_start + lo ) ) * pts_per_task, pts_per_task, state[a].steps > 0, radius, r2f, dot_thr,
                           scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, scratch_p + blk.scratch_off, scratch_n + blk.scratch_off,
                           s_cand[warp], s_slot[warp] );
   }

@@ -128,8 +128,11 @@ __device__ __forceinline__ unsigned group_sum32( unsigned v, unsigned gmask )
 // this warp's table of GroupCfg<G>::CAND_WORDS uint4 in shared memory.  The result is replicated in the group.
 template <int G>
 __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, float px, float py, float pz, float nx, float ny, float nz,
-                                                    double radius, float r2f, float dot_thr, int k, uint4* __restrict__ cand )
+                                                    double radius, float r2f, float dot_thr, int k, uint4* __restrict__ cand,
+                                                    unsigned long long seedkey = ~0ull, float seeddot = 0.f )
 {
+  // seedkey (optional): key (d2 bits << 32 | recs position) of a point already known to be compatible and inside the
+  // radius — e.g. the previous ICP iteration's correspondent; it only tightens the pruning bound from the start
   constexpr int NC = GroupCfg<G>::NC;
   const int lane = threadIdx.x & 31, sub = lane & ( G - 1 ), gbase = lane & ~( G - 1 );
   const unsigned gmask = ( ( G == 32 ) ? 0xffffffffu : ( ( 1u << G ) - 1u ) ) << gbase;
@@ -160,6 +163,8 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
     }
   }
 
+  // a seed bounds everything: no cell at or beyond its distance can hold a closer compatible point or a point of its rank
+  const uint32_t lim1 = ( qv && (uint32_t)( seedkey >> 32 ) < r2bits ) ? (uint32_t)( seedkey >> 32 ) : r2bits;
   // ---- phase 1: evaluate the candidate cells, G at a time (loads of all candidates are in flight together)
   const ConeCull cull = make_cull( g, dot_thr, nx, ny, nz );
   unsigned cmask = 0, smask = 0; // bit e: cell e is in range and non-empty / ... and its normal cone admits a compatible point
@@ -178,7 +183,7 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
       const float gz2 = cz < w.c0z ? glz2 : ( cz > w.c0z ? ghz2 : 0.0f );
       // (gz*gz + gy*gy) + gx*gx (:1221); dropping 5 mantissa bits only makes every pruning test more conservative
       const uint32_t gapc = __float_as_uint( __fadd_rn( __fadd_rn( gz2, gy2 ), gx2 ) ) & 0xffffffe0u;
-      if( gapc < r2bits )
+      if( gapc < lim1 )
       {
         const uint32_t id = (uint32_t)( ( cz * g.H + cy ) * g.W + cx ); // n_cells <= 2^30 (grid.cu)
         const uint32_t s = __ldg( g.cell_start + id ), t = __ldg( g.cell_start + id + 1 );
@@ -202,6 +207,11 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
   // ---- phase 2: nearest compatible point; key = (d2 bits, recs position), smaller wins
   unsigned long long limkey = (unsigned long long)r2bits << 32, mykey = ~0ull;
   float mydot = 0.f;
+  if( qv && seedkey < limkey )
+  {
+    limkey = seedkey;
+    if( sub == 0 ) { mykey = seedkey; mydot = seeddot; }
+  }
   for( unsigned m = smask; m; )
   {
     const int e = __ffs( m ) - 1; m &= m - 1;
@@ -265,7 +275,7 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
   return hit;
 }
 
-// One round = up to 32 queries, G warp steps of 32 / G queries each.  query_of(r, px, py, pz, nx, ny, nz) must be
+// One round = up to 32 queries, G warp steps of 32 / G queries each.  query_of(r, px, py, pz, nx, ny, nz, seedkey, seeddot) must be
 // callable by all lanes with any r in [0, n_round) and give the r-th query of the round (the lanes of one group
 // ask for the same r); it returns false for a query the group path must not take (left unfound here).  On return
 // lane L holds the result of query L of the round.
@@ -279,9 +289,10 @@ __device__ __forceinline__ NearestHit group_round( const GridView& g, int n_roun
   for( int step = 0; step * NG < n_round; ++step )
   {
     const int r = step * NG + lane / G;
-    float px, py, pz, nx, ny, nz;
-    const bool ok = query_of( r < n_round ? r : n_round - 1, px, py, pz, nx, ny, nz );
-    const NearestHit h = group_search<G>( g, ok && r < n_round, px, py, pz, nx, ny, nz, radius, r2f, dot_thr, k, cand );
+    float px, py, pz, nx, ny, nz, seeddot = 0.f;
+    unsigned long long seedkey = ~0ull;
+    const bool ok = query_of( r < n_round ? r : n_round - 1, px, py, pz, nx, ny, nz, seedkey, seeddot );
+    const NearestHit h = group_search<G>( g, ok && r < n_round, px, py, pz, nx, ny, nz, radius, r2f, dot_thr, k, cand, seedkey, seeddot );
     // query L of the round was served in step L / NG by group L % NG
     const int src = ( lane % NG ) * G;
     const float d2 = __shfl_sync( RS_FULL, h.d2, src ), dot = __shfl_sync( RS_FULL, h.dot, src );

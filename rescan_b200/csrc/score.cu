@@ -175,7 +175,7 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
     if( prune_cnt >= 0.0 && (double)( n_found + ( n_list - base ) ) < prune_cnt ) { pruned = true; break; }
     const int n_round = min( 32, n_list - base );
     // ---- pass B: the searches of this round (:115-148)
-    auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz ) -> bool {
+    auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz, unsigned long long& seedkey, float& seeddot ) -> bool {
       const int e = list[base + r];
       const int i = i0 + ( e & 0x7fff );
       xf_apply( m, __ldg( obj_pos + 3 * (size_t)i ), __ldg( obj_pos + 3 * (size_t)i + 1 ), __ldg( obj_pos + 3 * (size_t)i + 2 ), 1.0f, px, py, pz );
@@ -186,7 +186,8 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
     if( LANE )
     {
       float px = 0.f, py = 0.f, pz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-      const bool qv = lane < n_round && query_of( lane, px, py, pz, nx, ny, nz );
+      unsigned long long sk = ~0ull; float sd = 0.f;
+      const bool qv = lane < n_round && query_of( lane, px, py, pz, nx, ny, nz, sk, sd );
       h = rsg::lane_search( g, qv, px, py, pz, nx, ny, nz, sp.radius, sp.r2f, sp.dot_thr, sp.k );
     }
     else { h = rsg::group_round<SC_G>( g, n_round, query_of, sp.radius, sp.r2f, sp.dot_thr, sp.k, cand ); }
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
     if( __any_sync( RS_FULL, slow ) )
     {
       LaneQuery q;
-      if( slow ) { query_of( lane, q.px, q.py, q.pz, q.nx, q.ny, q.nz ); }
+      unsigned long long sk2 = ~0ull; float sd2 = 0.f;
+      if( slow ) { query_of( lane, q.px, q.py, q.pz, q.nx, q.ny, q.nz, sk2, sd2 ); }
       NearestHit hs = nearest_compatible_batch<false>( g, q, slow, sp.radius, sp.r2f, sp.dot_thr, sp.k, nullptr );
       if( slow ) { h = hs; }
     }

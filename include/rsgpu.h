@@ -216,6 +216,18 @@ int rsgpu_neighborhood( const rsgpu_grid_t* grid, const float* pos, const float*
                         int32_t max_nn, float radius_sq, float dist_exp, float angle_exp, int32_t* neighbors,
                         float* weights );
 
+/* ---- non-maxima suppression of one object's proposals ------------------------------------------
+   rsgpu_overlap_factors replaces isect_get_overlap_factor (lib/rs/intersect.h:309-368) for ONE cloud under a reference
+   pose against n other poses (column-major 4x4 each): lvl3 = the object's level-3 cloud (posed bounding boxes,
+   :119-130), lvl1 = its level-1 cloud (occupancy, :177-306).  out[i] is bit-identical to the reference's float.
+   rsgpu_nms replaces mgs_non_maxima_suppresion for one object (apps/pose_proposal/pose_proposal.cpp:371-452):
+   proposals = n x RSGPU_POSE_FLOATS, centroid = rs_pointcloud_centroid( shape, 0 ) (computed by the caller),
+   keep[i] = 1 for the survivors (the caller copies them in their original order, :440-447). */
+int rsgpu_overlap_factors( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1, const float* pose_ref, const float* poses, int32_t n,
+                           float voxel_size, int32_t voxelize_inside, int32_t normalize_by_smaller, float* out );
+int rsgpu_nms( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1, const float centroid[3], const float* proposals, int32_t n,
+               float dist_threshold, uint8_t* keep );
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,9 @@ def load():
         "orc_icp_align": (f32, [_f32p, _f32p, i32, _f32p, _f32p, i32, _f32p, _f32p, f32, f32, C.POINTER(i32)]),
         "orc_assign_labels": (None, [_f32p, _f32p, i32, _f32p, C.POINTER(vp), C.POINTER(vp), i32, i32, f32, _i8p, _f32p]),
         "orc_unary_costs": (None, [_i32p, _u8p, i32, i32, _i32p]),
+        "orc_posed_bbox": (None, [_f32p, i32, _f32p, _f32p]),
+        "orc_overlap_factor": (f32, [_f32p, i32, _f32p, i32, _f32p, _f32p, f32, C.c_int, C.c_int]),
+        "orc_nms": (None, [_f32p, i32, _f32p, i32, _f32p, _f32p, i32, f32, _u8p]),
         "orc_neighborhood": (None, [vp, _f32p, _f32p, i32, i32, f32, f32, f32, _i32p, _f32p]),
     }
     for name, (res, args) in sig.items():
@@ -208,3 +211,29 @@ def neighborhood(grid: OrcGrid, pos, nor, max_nn=8, radius_sq=np.float32(0.05) *
     load().orc_neighborhood(grid.h, p.reshape(-1), n.reshape(-1), len(p), max_nn, radius_sq, dist_exp, angle_exp,
                             nbr.reshape(-1), w.reshape(-1))
     return nbr, w
+
+
+def overlap_factor(pos3, pos1, pose_a, pose_b, voxel=0.1, inside=1, normalize_by_smaller=0):
+    """isect_get_overlap_factor restated: level-3 points give the boxes, level-1 points the occupancy"""
+    p3, p1 = _f32(pos3).reshape(-1, 3), _f32(pos1).reshape(-1, 3)
+    return float(load().orc_overlap_factor(p3.reshape(-1), len(p3), p1.reshape(-1), len(p1), _f32(pose_a).reshape(16),
+                                           _f32(pose_b).reshape(16), voxel, inside, normalize_by_smaller))
+
+
+def centroid(pos0):
+    """rs_pointcloud_centroid: double accumulation in point order, narrowed to float (rs_pointcloud.h:1319-1339)"""
+    p = _f32(pos0).reshape(-1, 3)
+    c = np.zeros(3, np.float64)
+    for a in range(3):
+        c[a] = np.cumsum(p[:, a].astype(np.float64))[-1] if len(p) else 0.0
+    return (c / float(len(p))).astype(np.float32)
+
+
+def nms(pos3, pos1, centroid_xyz, proposals, dist_threshold=0.2):
+    """mgs_non_maxima_suppresion for one object -> keep flags [n]"""
+    p3, p1 = _f32(pos3).reshape(-1, 3), _f32(pos1).reshape(-1, 3)
+    pr = _f32(proposals).reshape(-1, 17)
+    keep = np.zeros(len(pr), np.uint8)
+    load().orc_nms(p3.reshape(-1), len(p3), p1.reshape(-1), len(p1), _f32(centroid_xyz).reshape(3), pr.reshape(-1), len(pr),
+                   dist_threshold, keep)
+    return keep.astype(bool)

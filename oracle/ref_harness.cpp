@@ -413,4 +413,45 @@ int64_t ref_compute_neighborhood( void* cloud, int lvl, int max_nn, float radius
   return n;
 }
 
+/* ---------------------------------------------------------------- NMS (pose_proposal.cpp:371-452, intersect.h:309-368) */
+} /* extern "C" */
+float isect_get_overlap_factor( const rs_pointcloud_t* pc_a, const msh_mat4_t pose_a, const rs_pointcloud_t* pc_b, const msh_mat4_t pose_b,
+                                const float voxel_size, const int voxelize_inside, const int normalize_by_smaller ); /* defined in pose_proposal.cpp's TU */
+extern "C" {
+float ref_overlap_factor( void* cloud, const float* pose_a, const float* pose_b, float voxel, int inside, int norm_smaller )
+{
+  return isect_get_overlap_factor( (rs_pointcloud_t*)cloud, mat_from( pose_a ), (rs_pointcloud_t*)cloud, mat_from( pose_b ), voxel, inside, norm_smaller );
+}
+void ref_cloud_centroid( void* cloud, float* c )
+{
+  msh_vec3_t v = rs_pointcloud_centroid( (rs_pointcloud_t*)cloud, 0 );
+  c[0] = v.x; c[1] = v.y; c[2] = v.z;
+}
+/* mgs_non_maxima_suppresion restricted to one object of the database: proposals in (n x 17 floats), survivors out
+   (same layout, reference order); returns their number */
+int32_t ref_nms( void* db, int object_idx, const float* proposals, int32_t n, float dist_threshold, float* kept )
+{
+  rsdb_t* rsdb = (rsdb_t*)db;
+  msh_array( msh_array( pose_proposal_t ) ) pp = NULL;
+  for( size_t i = 0; i < msh_array_len( rsdb->objects ); ++i )
+  {
+    msh_array( pose_proposal_t ) cur = NULL;
+    if( (int)i == object_idx )
+    {
+      for( int32_t j = 0; j < n; ++j )
+      {
+        pose_proposal_t p; memcpy( p.xform.data, proposals + 17 * (size_t)j, 64 ); p.score = proposals[17 * (size_t)j + 16];
+        msh_array_push( cur, p );
+      }
+    }
+    msh_array_push( pp, cur );
+  }
+  mgs_non_maxima_suppresion( rsdb, &pp, 0, dist_threshold );
+  int32_t m = (int32_t)msh_array_len( pp[object_idx] );
+  for( int32_t j = 0; j < m; ++j ) { memcpy( kept + 17 * (size_t)j, pp[object_idx][j].xform.data, 64 ); kept[17 * (size_t)j + 16] = pp[object_idx][j].score; }
+  for( size_t i = 0; i < msh_array_len( pp ); ++i ) { if( pp[i] ) { msh_array_free( pp[i] ); } }
+  msh_array_free( pp );
+  return m;
+}
+
 } /* extern "C" */

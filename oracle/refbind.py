@@ -71,6 +71,9 @@ def load(openmp=False):
         "ref_smooth_labels_capture": (C.c_int, [vp, vp]),
         "ref_capture_n_edges": (i64, []),
         "ref_capture_get": (None, [vp, vp, vp, vp, vp, vp]),
+        "ref_overlap_factor": (f32, [vp, _f32p, _f32p, f32, C.c_int, C.c_int]),
+        "ref_cloud_centroid": (None, [vp, _f32p]),
+        "ref_nms": (i32, [vp, C.c_int, _f32p, i32, f32, _f32p]),
         "ref_compute_neighborhood": (i64, [vp, C.c_int, C.c_int, f32, f32, f32, C.POINTER(C.POINTER(C.c_int32)),
                                           C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_float))]),
     }
@@ -253,6 +256,13 @@ class RefDB:
             o += c
         return out
 
+    def nms(self, object_idx, proposals, dist_threshold=0.2):
+        """mgs_non_maxima_suppresion for one object -> surviving proposals [m, 17] in the reference's order"""
+        pr = _f32(proposals).reshape(-1, 17)
+        kept = np.zeros_like(pr)
+        m = self.L.ref_nms(self.h, int(object_idx), pr.reshape(-1), len(pr), dist_threshold, kept.reshape(-1))
+        return kept[:m].copy()
+
     def arrangement_to_labels(self, scan: RefCloud, object_idx, uidx, poses_colmajor, radius, prioritize_static=False):
         oi = np.ascontiguousarray(object_idx, np.int32)
         ui = np.ascontiguousarray(uidx, np.int32)
@@ -312,3 +322,14 @@ def icp_pt2pl(cp1, cp2, cn2, w, T1_colmajor):
     T1 = _f32(T1_colmajor).copy()
     err = L.ref_icp_pt2pl(_f32(cp1).reshape(-1), _f32(cp2).reshape(-1), _f32(cn2).reshape(-1), _f32(w), len(w), T1)
     return T1, float(err)
+
+
+def overlap_factor(cloud: RefCloud, pose_a, pose_b, voxel=0.1, inside=1, normalize_by_smaller=0):
+    """isect_get_overlap_factor of one cloud under two poses (column-major float32[16])"""
+    return float(cloud.L.ref_overlap_factor(cloud.h, _f32(pose_a).reshape(16), _f32(pose_b).reshape(16), voxel, inside, normalize_by_smaller))
+
+
+def cloud_centroid(cloud: RefCloud):
+    c = np.zeros(3, np.float32)
+    cloud.L.ref_cloud_centroid(cloud.h, c)
+    return c

@@ -724,3 +724,154 @@ void orc_neighborhood( const orc_grid_t* grid, const float* pos, const float* no
   }
   free( d2 ); free( id );
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxel-occupancy overlap of one object under two poses, and the greedy non-maxima suppression built on
+ * it (reference lib/rs/intersect.h:309-368, apps/pose_proposal/pose_proposal.cpp:371-452).  Restated as
+ * three flat passes over one byte grid per pose (mark, fill, count) instead of the reference's slice
+ * copies and scan-line scratch arrays; the grid geometry, the per-row "odd number of boundary exits seen
+ * from both ends" fill rule and every float expression are the reference's.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { float mn[3], mx[3]; } orc_bbox_t;
+
+/* bounding box of the level-3 points under a pose (intersect.h:119-130, msh_geometry.h:945-969) */
+void orc_posed_bbox( const float* pos3, int32_t n3, const float* pose, float* mn_mx )
+{
+  float mn[3] = { 1e9f, 1e9f, 1e9f }, mx[3] = { -1e9f, -1e9f, -1e9f };
+  for( int32_t i = 0; i < n3; ++i )
+  {
+    float p[3];
+    xf_apply( pose, pos3 + 3 * (size_t)i, 1, p );
+    for( int a = 0; a < 3; ++a ) { if( p[a] < mn[a] ) { mn[a] = p[a]; } if( p[a] > mx[a] ) { mx[a] = p[a]; } }
+  }
+  memcpy( mn_mx, mn, 12 ); memcpy( mn_mx + 3, mx, 12 );
+}
+
+/* occupancy of the level-1 points under `pose` on the pair grid: 1 = boundary, 2 = inside (voxelize_inside);
+   returns the number of non-free cells (intersect.h:177-306).  Cell (x,y,z) lives at (y*zr + z)*xr + x (:108). */
+static int32_t orc_occupancy( const float* pos1, int32_t n1, const float* pose, const float* origin, float voxel,
+                              int xr, int yr, int zr, int inside, uint8_t* grid )
+{
+  const size_t n_cells = (size_t)xr * yr * zr;
+  memset( grid, 0, n_cells );
+  for( int32_t i = 0; i < n1; ++i )
+  {
+    float p[3];
+    xf_apply( pose, pos1 + 3 * (size_t)i, 1, p );
+    const int x = (int)floorf( ( p[0] - origin[0] ) / voxel ), y = (int)floorf( ( p[1] - origin[1] ) / voxel ),
+              z = (int)floorf( ( p[2] - origin[2] ) / voxel ); /* (:226-230); in range by construction of the grid */
+    if( x < 0 || x >= xr || y < 0 || y >= yr || z < 0 || z >= zr ) { continue; }
+    grid[( (size_t)y * zr + z ) * xr + x] = 1;
+  }
+  int32_t count = 0;
+  if( !inside )
+  {
+    for( size_t c = 0; c < n_cells; ++c ) { count += grid[c] == 1; }
+    return count;
+  }
+  /* per y layer, a free cell becomes "inside" iff along its x-row AND along its z-row the number of boundary->free
+     transitions passed is odd when walking from the row's start and odd when walking from its end (:129-175, 253-284) */
+  uint8_t* in_x = (uint8_t*)malloc( (size_t)xr * zr );
+  uint8_t* in_z = (uint8_t*)malloc( (size_t)xr * zr );
+  for( int y = 0; y < yr; ++y )
+  {
+    uint8_t* layer = grid + (size_t)y * zr * xr;
+    memset( in_x, 0, (size_t)xr * zr ); memset( in_z, 0, (size_t)xr * zr );
+    for( int dir = 0; dir < 2; ++dir )
+    {
+      /* dir 0: rows of constant z, walking x (the reference's dir = 0: r1 = z, r2 = x); dir 1: constant x, walking z */
+      const int n_rows = dir == 0 ? zr : xr, len = dir == 0 ? xr : zr;
+      uint8_t* out = dir == 0 ? in_x : in_z;
+      for( int r = 0; r < n_rows; ++r )
+      {
+        #define ORC_CELL( t ) ( dir == 0 ? (size_t)r * xr + ( t ) : (size_t)( t ) * xr + r )
+        int fill = 0, prev = 0;
+        for( int t = 0; t < len; ++t )
+        {
+          const int v = layer[ORC_CELL( t )];
+          if( v == 0 && prev == 1 ) { fill += 1; }
+          if( fill % 2 == 1 ) { out[ORC_CELL( t )] = 1; } /* forward mark */
+          prev = v;
+        }
+        fill = 0; prev = 0;
+        for( int t = len - 1; t >= 0; --t )
+        {
+          const int v = layer[ORC_CELL( t )];
+          if( v == 0 && prev == 1 ) { fill += 1; }
+          /* inside along this direction = forward AND backward odd AND not a boundary cell */
+          out[ORC_CELL( t )] = (uint8_t)( out[ORC_CELL( t )] && ( fill % 2 == 1 ) && v != 1 );
+          prev = v;
+        }
+        #undef ORC_CELL
+      }
+    }
+    for( size_t c = 0; c < (size_t)xr * zr; ++c )
+    {
+      if( layer[c] != 1 && in_x[c] && in_z[c] ) { layer[c] = 2; }
+    }
+  }
+  free( in_x ); free( in_z );
+  for( size_t c = 0; c < n_cells; ++c ) { count += grid[c] > 0; }
+  return count;
+}
+
+float orc_overlap_factor( const float* pos3, int32_t n3, const float* pos1, int32_t n1, const float* pose_a, const float* pose_b,
+                          float voxel, int inside, int normalize_by_smaller )
+{
+  float ba[6], bb[6];
+  orc_posed_bbox( pos3, n3, pose_a, ba );
+  orc_posed_bbox( pos3, n3, pose_b, bb );
+  /* mshgeo_bbox_intersect (msh_geometry.h:1010-1015) */
+  for( int a = 0; a < 3; ++a ) { if( !( ba[3 + a] >= bb[a] && bb[3 + a] >= ba[a] ) ) { return 0.0f; } }
+  float mn[3], mx[3];
+  for( int a = 0; a < 3; ++a )
+  {
+    mn[a] = ba[a] < bb[a] ? ba[a] : bb[a];
+    mx[a] = ba[3 + a] > bb[3 + a] ? ba[3 + a] : bb[3 + a];
+    mn[a] = mn[a] - 0.3f; mx[a] = mx[a] + 0.3f; /* fat_factor (intersect.h:61-65) */
+  }
+  const int xr = (int)ceilf( ( mx[0] - mn[0] ) / voxel ) + 1, yr = (int)ceilf( ( mx[1] - mn[1] ) / voxel ) + 1,
+            zr = (int)ceilf( ( mx[2] - mn[2] ) / voxel ) + 1; /* (:67-69) */
+  const size_t n_cells = (size_t)xr * yr * zr;
+  uint8_t* ga = (uint8_t*)malloc( n_cells ), *gb = (uint8_t*)malloc( n_cells );
+  const int32_t ca = orc_occupancy( pos1, n1, pose_a, mn, voxel, xr, yr, zr, inside, ga );
+  const int32_t cb = orc_occupancy( pos1, n1, pose_b, mn, voxel, xr, yr, zr, inside, gb );
+  int32_t both = 0;
+  for( size_t c = 0; c < n_cells; ++c ) { both += ( ga[c] == 1 || ga[c] == 2 ) && ( gb[c] == 1 || gb[c] == 2 ); }
+  free( ga ); free( gb );
+  const int32_t denom = normalize_by_smaller ? ( ca < cb ? ca : cb ) : ( ca > cb ? ca : cb );
+  return denom > 0 ? (float)both / (float)denom : 1.0f; /* (:350-357) */
+}
+
+/* mgs_non_maxima_suppresion for one object (pose_proposal.cpp:371-452): keep[i] = 1 for the survivors.
+   proposals: n x 17 floats (xform column-major + score); centroid = rs_pointcloud_centroid( shape, 0 ). */
+void orc_nms( const float* pos3, int32_t n3, const float* pos1, int32_t n1, const float* centroid, const float* proposals, int32_t n,
+              float dist_threshold, uint8_t* keep )
+{
+  uint8_t* mark = (uint8_t*)calloc( n > 0 ? n : 1, 1 ); /* 0 unmarked, 1 keep, 2 discard */
+  int32_t marked = 0;
+  while( marked != n )
+  {
+    int32_t best = -1; float best_score = -1e9f;
+    for( int32_t i = 0; i < n; ++i )
+    {
+      if( mark[i] == 0 && proposals[17 * (size_t)i + 16] > best_score ) { best_score = proposals[17 * (size_t)i + 16]; best = i; }
+    }
+    if( best < 0 ) { break; } /* only NaN scores left: the reference would index [-1]; nothing sensible to keep */
+    mark[best] = 1; marked++;
+    float p1[3];
+    xf_apply( proposals + 17 * (size_t)best, centroid, 1, p1 );
+    for( int32_t i = 0; i < n; ++i )
+    {
+      if( mark[i] != 0 ) { continue; }
+      float p2[3];
+      xf_apply( proposals + 17 * (size_t)i, centroid, 1, p2 );
+      const float dx = p1[0] - p2[0], dy = p1[1] - p2[1], dz = p1[2] - p2[2];
+      const float dist = (float)sqrt( (double)( dx * dx + dy * dy + dz * dz ) ); /* msh_vec3_norm (msh_vec_math.h:988-991) */
+      const float overlap = orc_overlap_factor( pos3, n3, pos1, n1, proposals + 17 * (size_t)best, proposals + 17 * (size_t)i, 0.1f, 1, 0 );
+      if( overlap > 0.5f || dist < dist_threshold || proposals[17 * (size_t)i + 16] < 0.01f ) { mark[i] = 2; marked++; }
+    }
+  }
+  for( int32_t i = 0; i < n; ++i ) { keep[i] = mark[i] == 1; }
+  free( mark );
+}

@@ -104,6 +104,8 @@ SIGNATURES = {
     "rsgpu_icp_align_batch_ex": (_int, [_vp, _vp, _vp, _i32, _vp, _f32, _f32, _i32, _vp, _vp]),
     "rsgpu_assign_labels": (_int, [_vp, _vp, _i32, _vp, C.POINTER(_vp), _i32, _i32, _f32, _vp, _vp]),
     "rsgpu_unary_costs": (_int, [_vp, _vp, _i32, _i32, _vp]),
+    "rsgpu_overlap_factors": (_int, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp]),
+    "rsgpu_nms": (_int, [_vp, _vp, _vp, _vp, _i32, _f32, _vp]),
     "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
 }
 
@@ -363,3 +365,21 @@ def neighborhood(grid: HashGrid, pos, nor, max_nn=8, radius_sq=np.float32(0.05) 
     _check(lib().rsgpu_neighborhood(grid.h, _ptr(p), _ptr(n), len(p), max_nn, radius_sq, dist_exp, angle_exp, _ptr(nbr),
                                     _ptr(w)))
     return nbr, w
+
+
+def overlap_factors(obj_lvl3: PointCloud, obj_lvl1: PointCloud, pose_ref, poses, voxel=0.1, inside=1, normalize_by_smaller=0):
+    """isect_get_overlap_factor (lib/rs/intersect.h:309) of one object under ``pose_ref`` against every pose of ``poses``"""
+    pr = _f32(pose_ref).reshape(16)
+    ps = _f32(poses).reshape(-1, 16)
+    out = np.zeros(len(ps), np.float32)
+    _check(lib().rsgpu_overlap_factors(obj_lvl3.h, obj_lvl1.h, _ptr(pr), _ptr(ps), len(ps), voxel, inside, normalize_by_smaller, _ptr(out)))
+    return out
+
+
+def non_maxima_suppression(obj_lvl3: PointCloud, obj_lvl1: PointCloud, centroid, proposals, dist_threshold=0.2):
+    """mgs_non_maxima_suppresion (apps/pose_proposal/pose_proposal.h:56) for one object -> keep flags [n]"""
+    pr = _f32(proposals).reshape(-1, POSE_FLOATS)
+    c = _f32(centroid).reshape(3)
+    keep = np.zeros(len(pr), np.uint8)
+    _check(lib().rsgpu_nms(obj_lvl3.h, obj_lvl1.h, _ptr(c), _ptr(pr), len(pr), dist_threshold, _ptr(keep)))
+    return keep.astype(bool)

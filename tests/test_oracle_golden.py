@@ -135,3 +135,20 @@ def test_neighborhood_edges(G):
             assert abs(cand[(int(a), int(b))] - ww) <= 2e-6 * max(abs(ww), 1e-3)
             hits += 1
     assert hits > 3000
+
+
+def test_overlap_and_nms_match_golden():
+    """tests/golden/nms_golden.npz (written from the compiled reference by make_golden_nms.py)"""
+    import os
+    z, scan, objs = common.golden()
+    g = dict(np.load(os.path.join(os.path.dirname(common.GOLDEN), "nms_golden.npz")))
+    for i, o in enumerate(objs):
+        props = g[f"nms{i}_props"]
+        c = O.centroid(o.pos(0))
+        assert (c == g[f"nms{i}_centroid"]).all()
+        got = np.array([O.overlap_factor(o.pos(3), o.pos(1), props[0, :16], props[j, :16], 0.1, 1, 0) for j in range(len(props))], np.float32)
+        assert (got == g[f"nms{i}_overlap"]).all()
+        gotb = np.array([O.overlap_factor(o.pos(3), o.pos(1), props[0, :16], props[j, :16], 0.1, 0, 1) for j in range(16)], np.float32)
+        assert (gotb == g[f"nms{i}_overlap_boundary"]).all()
+        keep = O.nms(o.pos(3), o.pos(1), c, props, 0.2)
+        assert (props[keep] == g[f"nms{i}_kept"]).all() and len(g[f"nms{i}_kept"]) == keep.sum()

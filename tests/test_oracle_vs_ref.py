@@ -77,3 +77,45 @@ def test_icp_align(S):
     To, eo, _ = O.icp_align(o.cloud.pos(2), o.cloud.nor(2), scene.scan.pos(2), scene.scan.nor(2), s, 0.10, ang)
     Tr, er = R.icp_align(o.cloud.pos(2), o.cloud.nor(2), scene.scan.pos(2), scene.scan.nor(2), s, 0.10, ang)
     assert (To == Tr).all() and np.float32(eo) == np.float32(er)
+
+
+def _nms_case(scene, oi, rng, n=40):
+    """proposals of one object: jittered copies of its true pose, far-away poses and a few with failed scores"""
+    o = scene.objects[oi]
+    props = np.zeros((n, 17), np.float32)
+    for j in range(n):
+        if j % 5 == 4:
+            m = synth.yaw_pose(rng.uniform(0, 6.28), rng.uniform(0.5, 2.5), rng.uniform(0.5, 2.0))
+        else:
+            d = synth.yaw_pose(rng.uniform(-0.6, 0.6), rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.02, 0.02))
+            m = (d.astype(np.float64) @ o.pose.astype(np.float64)).astype(np.float32)
+        props[j, :16] = common.colmajor(m)
+        props[j, 16] = np.float32(rng.uniform(0.3, 0.99)) if j % 7 else np.float32(-1.0)
+    props[3, 16] = props[2, 16]  # a score tie: the first maximum wins
+    return props
+
+
+def test_overlap_factor_and_nms(S):
+    """intersect.h:309-368 and pose_proposal.cpp:371-452: bit-identical overlap factors, identical survivor lists"""
+    scene, _, objs = S
+    rng = np.random.default_rng(77)
+    db = R.RefDB()
+    for o, rc in zip(scene.objects, objs):
+        db.add_object(rc, o.uidx, o.class_idx)
+    n_pairs = n_pos = 0
+    for oi, (o, rc) in enumerate(zip(scene.objects, objs)):
+        props = _nms_case(scene, oi, rng)
+        for j in range(1, 12):
+            for inside, smaller in ((1, 0), (0, 0), (1, 1)):
+                want = R.overlap_factor(rc, props[0, :16], props[j, :16], 0.1, inside, smaller)
+                got = O.overlap_factor(o.cloud.pos(3), o.cloud.pos(1), props[0, :16], props[j, :16], 0.1, inside, smaller)
+                assert got == want, (oi, j, inside, smaller, got, want)
+                n_pairs += 1
+                n_pos += want > 0
+        c_ref, c_orc = R.cloud_centroid(rc), O.centroid(o.cloud.pos(0))
+        assert (c_ref == c_orc).all()
+        kept_ref = db.nms(oi, props, 0.2)
+        keep = O.nms(o.cloud.pos(3), o.cloud.pos(1), c_orc, props, 0.2)
+        assert len(kept_ref) == keep.sum() and (kept_ref == props[keep]).all()
+        assert 0 < keep.sum() < len(props)
+    assert n_pos > n_pairs // 3

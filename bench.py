@@ -31,7 +31,7 @@ UNIT = "pose evaluations/s"
 L2_FLUSH_BYTES = 256 << 20
 
 
-def workload_config(name, world):
+def workload_config(name, world, nms=True):
     from rescan_b200 import synth
     cfg = synth.CONFIGS[name]
     sc = cfg["scene"]
@@ -39,6 +39,8 @@ def workload_config(name, world):
             "objects": sc["n_objects"], "static_objects": sc["n_static"], "rotations": cfg["n_rot"],
             "translation_seeds_per_gpu": cfg["n_seeds"], "translation_seeds_total": cfg["n_seeds"] * world,
             "top_k": 64, "parallelism": f"pose-sharded x{world}",
+            "stages": "grid build, dense search lvl 4, verification lvl 3/2, top-k" + (", NMS" if nms else "") + ", ICP, rescoring lvl 1"
+                      + (", NMS" if nms else "") + ", sort",
             "l2": "flushed between steps (256 MiB write inside the timed region); working set is L2-resident within a step"}
 
 
@@ -181,6 +183,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nms", type=int, default=1, help="1: the two NMS passes of main.cpp:161/205 run on the GPU inside the step; 0: top-k only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -217,7 +220,8 @@ def main():
     def step(resident):
         flush.zero_()
         return pipeline.run_step((hp["p1"], hp["n1"]), (hp["p2"], hp["n2"]), models, rotations, translations, top_k=64, rank=rank,
-                                 world=world, dist=dist if world > 1 else None, device=device, scan_dev=scan_dev if resident else None)
+                                 world=world, dist=dist if world > 1 else None, device=device, scan_dev=scan_dev if resident else None,
+                                 nms_dist=0.2 if args.nms else None)
 
     def barrier():
         if world > 1:
@@ -255,7 +259,7 @@ def main():
     launches = api.launch_count() - l0
     api.profile_enable(False)
     dense_ms, dense_launches = api.profile_get("score_dense")
-    prof = {n: api.profile_get(n) for n in ("grid_build", "score_dense", "score", "icp")}  # ms over the timed steps, launches
+    prof = {n: api.profile_get(n) for n in ("grid_build", "score_dense", "score", "icp", "overlap")}  # ms over the timed steps, launches
     for _ in range(1):
         step(False)
     ms_e2e, res_e2e = timed(False, args.steps)
@@ -281,7 +285,7 @@ def main():
         achieved = steps_dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
         line = {"metric": METRIC, "value": evals / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world, bool(args.nms)),
                 "nn_queries_per_sec": queries / (ms_value * 1e-3),
                 "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

@@ -6,8 +6,11 @@ stages that stay reference code (NMS, sorting, .rsdb / .bin I/O):
 
   1. build the scan's level-1 grid (scoring) and level-2 grid (ICP)           rs_pointcloud.h:849-863
   2. per dynamic object: dense pose search at level 4 + verification at 3, 2   pose_proposal.cpp:325-369
+  2b. non-maxima suppression of every object's proposals (``nms_dist``)        main.cpp:161, pose_proposal.cpp:371-452
+  2c. the placements of previous arrangements join the list with score 10.0   main.cpp:163-173
   3. ICP refinement of the per-object survivors at level 2                    main.cpp:175-197
   4. rescoring of the refined poses at object level 1 with k = 32             main.cpp:199-201
+  5. non-maxima suppression again, then descending-score order                main.cpp:205-206
 
 Multi-GPU: translations are sharded over ranks in contiguous blocks (the per-translation arg-max over rotations
 stays rank-local); the only exchange is one all-gather of the per-object top-k proposals, after which every
@@ -18,7 +21,7 @@ from __future__ import annotations
 import dataclasses
 import numpy as np
 
-from . import api, synth
+from . import api, posegrid, synth
 
 
 @dataclasses.dataclass
@@ -27,6 +30,7 @@ class ObjectModel:
     class_idx: int
     is_static: bool
     levels: dict  # lvl -> api.PointCloud
+    centroid: np.ndarray = None  # rs_pointcloud_centroid( shape, 0 ) (rs_pointcloud.h:1319-1339), what NMS measures distances between
 
 
 @dataclasses.dataclass
@@ -43,7 +47,8 @@ def upload_objects(objects, levels=(4, 3, 2, 1)):
     out = []
     for o in objects:
         out.append(ObjectModel(o.uidx, o.class_idx, o.is_static,
-                               {l: api.PointCloud(o.cloud.pos(l), o.cloud.nor(l)) for l in levels}))
+                               {l: api.PointCloud(o.cloud.pos(l), o.cloud.nor(l)) for l in levels},
+                               posegrid.cloud_centroid(o.cloud.pos(0))))
     return out
 
 
@@ -64,29 +69,75 @@ def merge_topk(per_rank_props, per_rank_ids, top_k):
     return props[order], ids[order]
 
 
-def _allgather_var(arr, dist, device):
-    """all-gather of variable-length float32/int64 rows via torch.distributed (NCCL on GPU, gloo on CPU)"""
+def _allgather_bytes(buf, dist, device):
+    """ONE all-gather of equally sized byte buffers (NCCL over NVLink on GPU, gloo on CPU) -> uint8 [world, nbytes]"""
     import torch
     world = dist.get_world_size()
-    n = torch.tensor([arr.shape[0]], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-    width = int(np.prod(arr.shape[1:])) if arr.ndim > 1 else 1
-    buf = torch.zeros((cap, width), dtype=torch.from_numpy(arr[:0]).dtype, device=device)
-    if arr.shape[0]:
-        buf[: arr.shape[0]] = torch.from_numpy(np.ascontiguousarray(arr).reshape(arr.shape[0], width)).to(device)
-    outs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf)
-    return [o[:c].cpu().numpy().reshape((c,) + arr.shape[1:]) for o, c in zip(outs, counts)]
+    send = torch.from_numpy(np.ascontiguousarray(buf).view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+    recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(recv.view(-1), send)
+    return recv.cpu().numpy()
+
+
+def exchange_topk(props_list, ids_list, top_k, dist, device):
+    """The per-object top-k exchange of the pose-sharded search as ONE collective for all objects: every rank packs
+    its lists into {counts int64 [O], ids int64 [O, cap], rows float32 [O, cap, 17]}, one all-gather moves them, and the
+    same deterministic merge (descending score, ties by pose id) runs on every rank.  cap = top_k, or the largest list
+    on any rank when top_k == 0 (one extra 8-byte all-gather)."""
+    n_obj = len(props_list)
+    cap = int(top_k)
+    if cap <= 0:
+        mine = np.array([max([len(p) for p in props_list], default=0)], np.int64)
+        cap = max(int(_allgather_bytes(mine, dist, device).view(np.int64).max()), 1)
+    counts = np.array([len(p) for p in props_list], np.int64)
+    ids = np.zeros((n_obj, cap), np.int64)
+    rows = np.zeros((n_obj, cap, api.POSE_FLOATS), np.float32)
+    for k, (p, i) in enumerate(zip(props_list, ids_list)):
+        ids[k, : len(i)] = i
+        rows[k, : len(p)] = p
+    buf = np.concatenate([counts.view(np.uint8), ids.reshape(-1).view(np.uint8), rows.reshape(-1).view(np.uint8)])
+    got = _allgather_bytes(buf, dist, device)
+    o1, o2 = 8 * n_obj, 8 * n_obj + 8 * n_obj * cap
+    out_p, out_i = [], []
+    for k in range(n_obj):
+        gp, gi = [], []
+        for r in range(got.shape[0]):
+            c = int(got[r, :o1].view(np.int64)[k])
+            gi.append(got[r, o1:o2].view(np.int64).reshape(n_obj, cap)[k, :c])
+            gp.append(got[r, o2:].view(np.float32).reshape(n_obj, cap, api.POSE_FLOATS)[k, :c])
+        mp_, mi = merge_topk(gp, gi, top_k)
+        out_p.append(mp_.copy())
+        out_i.append(mi.copy())
+    return out_p, out_i
+
+
+def exchange_rows(upd_list, n_list, world, dist, device):
+    """Second exchange: object k's list has n_list[k] entries on every rank and rank r refined entries r, r + world, ...;
+    ONE all-gather of the padded [sum_k ceil(n_k / world), 17] rows returns, per object, the rows in list order."""
+    caps = [-(-n // world) for n in n_list]
+    off = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+    rows = np.zeros((max(int(off[-1]), 1), api.POSE_FLOATS), np.float32)
+    for k, u in enumerate(upd_list):
+        rows[off[k]: off[k] + len(u)] = u
+    got = _allgather_bytes(rows, dist, device).view(np.float32).reshape(world, -1, api.POSE_FLOATS)
+    out = []
+    for k, n in enumerate(n_list):
+        full = np.zeros((n, api.POSE_FLOATS), np.float32)
+        for r in range(world):
+            c = len(range(r, n, world))
+            full[r::world] = got[r, off[k]: off[k] + c]
+        out.append(full)
+    return out
 
 
 def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, icp_max_dist=0.10,
              icp_max_angle=np.float32(np.deg2rad(60.0)), rank=0, world=1, dist=None, device=None,
-             scan_dev=None, do_icp=True):
+             scan_dev=None, do_icp=True, nms_dist=None, previous=None):
     """scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
-    {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead."""
+    {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead.
+    nms_dist: centroid-distance threshold of the two NMS passes (the reference passes 0.2, main.cpp:161/205); None
+    skips both.  previous: per dynamic object, float32 [n,16] placements of earlier arrangements, appended with
+    score 10.0 and pose id -1 before the ICP (main.cpp:163-173)."""
     h2d = d2h = 0
     p1, n1 = scan_lvl1
     p2, n2 = scan_lvl2
@@ -108,26 +159,43 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     n_eval = n_query = 0
     dyn = [m for m in models if not m.is_static]  # pose_proposal.cpp:198
     out_props, out_ids = [], []
-    # ---- dense search + verification per object (+ all-gather of the per-object top-k)
+    # ---- dense search + verification per object on this rank's block of translations
     for m in dyn:
         props, ids = api.propose_poses(m.levels[4], m.levels[3], m.levels[2], g1, rotations, my_trans, top_k=top_k)
-        ids = ids + lo * n_rot
         d2h += props.nbytes + ids.nbytes
         n_eval += n_rot * len(my_trans)
         n_query += n_rot * len(my_trans) * len(m.levels[4])
-        if world > 1:
-            gp = _allgather_var(props, dist, device)
-            gi = _allgather_var(ids, dist, device)
-            props, ids = merge_topk(gp, gi, top_k)
         out_props.append(props)
-        out_ids.append(ids)
+        out_ids.append(ids + lo * n_rot)
+    # ---- the only exchange of the search: one all-gather of every object's top-k, identical merge on every rank
+    if world > 1:
+        out_props, out_ids = exchange_topk(out_props, out_ids, top_k, dist, device)
+    # ---- NMS (every rank suppresses the same merged lists: no exchange), then the previous placements join
+    if nms_dist is not None:
+        for k, m in enumerate(dyn):
+            if len(out_props[k]):
+                keep = api.non_maxima_suppression(m.levels[3], m.levels[1], m.centroid, out_props[k], nms_dist)
+                h2d += out_props[k].nbytes
+                d2h += keep.nbytes
+                out_props[k], out_ids[k] = out_props[k][keep], out_ids[k][keep]
+    if previous is not None:
+        for k, prev in enumerate(previous):
+            prev = np.asarray(prev, np.float32).reshape(-1, 16)
+            if len(prev):
+                add = np.concatenate([prev, np.full((len(prev), 1), 10.0, np.float32)], axis=1)
+                out_props[k] = np.concatenate([out_props[k], add])
+                out_ids[k] = np.concatenate([out_ids[k], np.full(len(prev), -1, np.int64)])
     # ---- ICP refinement of every surviving proposal of every object in ONE launch, then rescoring
     if do_icp:
-        shares = [np.nonzero(p[:, 16] > 0)[0][rank::world] if len(p) else np.zeros(0, np.int64) for p in out_props]
+        # without NMS the -1 verification failures (pose_proposal.cpp:292) are not worth refining; with it the list is
+        # what the reference's main refines: every survivor (main.cpp:175-204)
+        cands = [np.arange(len(p)) if nms_dist is not None else np.nonzero(p[:, 16] > 0)[0] for p in out_props]
+        shares = [c[rank::world] for c in cands]
         jobs = [(m, p[s, :16]) for m, p, s in zip(dyn, out_props, shares) if len(s)]
         refined = api.icp_align_multi([m.levels[2] for m, _ in jobs], g2, [t for _, t in jobs], icp_max_dist, icp_max_angle) if jobs else []
         ri = 0
-        for k, (m, props, ids, mine) in enumerate(zip(dyn, out_props, out_ids, shares)):
+        updates = []
+        for m, mine in zip(dyn, shares):
             if len(mine):
                 T, err, it = refined[ri]
                 ri += 1
@@ -136,16 +204,18 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
                 d2h += T.nbytes + err.nbytes + it.nbytes + sc.nbytes
                 n_eval += len(mine)
                 n_query += len(mine) * len(m.levels[1])
-                upd = np.concatenate([T, sc[:, None]], axis=1).astype(np.float32)
+                updates.append(np.concatenate([T, sc[:, None]], axis=1).astype(np.float32))
             else:
-                upd = np.zeros((0, api.POSE_FLOATS), np.float32)
-            if world > 1:
-                gu = _allgather_var(upd, dist, device)
-                gm = _allgather_var(mine.astype(np.int64), dist, device)
-                for u, mi in zip(gu, gm):
-                    props[mi] = u
-            elif len(mine):
-                props[mine] = upd
+                updates.append(np.zeros((0, api.POSE_FLOATS), np.float32))
+        if world > 1:  # second (and last) exchange: the refined rows of every object in one all-gather
+            updates = exchange_rows(updates, [len(c) for c in cands], world, dist, device)
+        for k, (m, c, upd) in enumerate(zip(dyn, cands, updates)):
+            props, ids = out_props[k], out_ids[k]
+            if len(c):
+                props[c] = upd
+            if nms_dist is not None and len(props):
+                keep = api.non_maxima_suppression(m.levels[3], m.levels[1], m.centroid, props, nms_dist)
+                props, ids = props[keep], ids[keep]
             order = np.lexsort((ids, -props[:, 16].astype(np.float64)))  # mgs_sort_poses: descending score
             out_props[k], out_ids[k] = props[order], ids[order]
     g1.close()

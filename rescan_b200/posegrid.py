@@ -115,3 +115,13 @@ def pose_grid(rotations, translations):
     out[:, :, 12:15] = t[:, None, :]
     out[:, :, 15] = 1.0
     return out
+
+
+def cloud_centroid(pos0):
+    """rs_pointcloud_centroid( pc, 0 ): fp64 accumulation in point order, divided, narrowed to float
+    (reference lib/rs/rs_pointcloud.h:1319-1339).  np.cumsum accumulates sequentially, np.sum would not."""
+    p = np.ascontiguousarray(pos0, np.float32).reshape(-1, 3)
+    if len(p) == 0:
+        return np.zeros(3, np.float32)
+    c = np.array([np.cumsum(p[:, a].astype(np.float64))[-1] for a in range(3)])
+    return (c / float(len(p))).astype(np.float32)

@@ -1,0 +1,94 @@
+"""The whole pose_proposal step of reference apps/pose_proposal/main.cpp:159-206 on the GPU (propose -> NMS -> previous
+placements appended with score 10 -> ICP -> rescore at level 1 with k = 32 -> NMS -> descending score) against the same
+sequence composed from the CPU oracle's routines."""
+import numpy as np
+import pytest
+
+from oracle import orcbind as O
+from rescan_b200 import api, pipeline, posegrid, synth
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_step(scene, rots_ang, trans, previous):
+    ang = rots_ang
+    og1 = O.OrcGrid(scene.scan.pos(1), 0.05)
+    n1 = scene.scan.nor(1)
+    xf = O.make_pose_grid(ang, trans)
+    out = []
+    dyn = [o for o in scene.objects if not o.is_static]
+    for k, o in enumerate(dyn):
+        ref, _ = O.score_poses(o.cloud.pos(4), o.cloud.nor(4), og1, n1, xf, 64, 0.10, n_threads=8)
+        ot, orr, osc = O.select_proposals(ref.reshape(len(trans), len(ang)), 0.25)
+        props = []
+        for t, r, s in zip(ot, orr, osc):
+            x = xf[t, r]
+            for lvl, thr in ((3, 0.35), (2, 0.40)):
+                if s > 0:
+                    v, _ = O.score_poses(o.cloud.pos(lvl), o.cloud.nor(lvl), og1, n1, x[None], 64, 0.10)
+                    s = v[0] if v[0] > thr else -1.0
+            props.append(np.concatenate([x.reshape(16), [s]]))
+        props = np.asarray(props, np.float32).reshape(-1, 17)
+        cen = O.centroid(o.cloud.pos(0))
+        if len(props):
+            props = props[O.nms(o.cloud.pos(3), o.cloud.pos(1), cen, props, 0.2)]
+        prev = np.asarray(previous[k], np.float32).reshape(-1, 16)
+        props = np.concatenate([props, np.concatenate([prev, np.full((len(prev), 1), 10.0, np.float32)], axis=1)])
+        for p in props:
+            T, err, it = O.icp_align(o.cloud.pos(2), o.cloud.nor(2), scene.scan.pos(2), scene.scan.nor(2), p[:16], 0.10,
+                                     np.float32(np.deg2rad(60.0)))
+            v, _ = O.score_poses(o.cloud.pos(1), o.cloud.nor(1), og1, n1, np.asarray(T, np.float32).reshape(1, 16), 32, 0.10)
+            p[:16] = np.asarray(T, np.float32).reshape(16)
+            p[16] = v[0]
+        if len(props):
+            props = props[O.nms(o.cloud.pos(3), o.cloud.pos(1), cen, props, 0.2)]
+        out.append(props[np.argsort(-props[:, 16].astype(np.float64), kind="stable")])
+    return out
+
+
+def test_full_step_with_nms_matches_oracle_sequence():
+    scene = common.tiny_scene()
+    rots, ang = common.rotation_xforms(8)
+    trans = synth.translation_seeds(scene.scan, 64, seed=9)
+    dyn = [o for o in scene.objects if not o.is_static]
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    rng = np.random.default_rng(4)
+    # one "previous arrangement" placement per dynamic object: the true pose, slightly off
+    previous = []
+    for o in dyn:
+        d = synth.yaw_pose(rng.uniform(-0.05, 0.05), rng.uniform(-0.03, 0.03), rng.uniform(-0.03, 0.03), 0.0)
+        previous.append(common.colmajor((d.astype(np.float64) @ o.pose.astype(np.float64)).astype(np.float32))[None])
+    models = pipeline.upload_objects(scene.objects)
+    for m, o in zip(models, scene.objects):
+        assert (m.centroid == O.centroid(o.cloud.pos(0))).all()
+    res = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans,
+                            top_k=0, nms_dist=0.2, previous=previous)
+    want = _oracle_step(scene, ang, trans, previous)
+    assert len(res.proposals) == len(want)
+    n_checked = 0
+    for got, w in zip(res.proposals, want):
+        assert len(got) == len(w)
+        # scores within the stated tolerance (1e-4 relative), poses within 1e-5 m / 1e-5 rad
+        assert np.allclose(got[:, 16], w[:, 16], rtol=1e-4, atol=1e-7)
+        for a, b in zip(got, w):
+            A, B = a[:16].reshape(4, 4).T.astype(np.float64), b[:16].reshape(4, 4).T.astype(np.float64)
+            assert np.linalg.norm(A[:3, 3] - B[:3, 3]) < 1e-5
+            R = A[:3, :3] @ B[:3, :3].T
+            assert np.linalg.norm(R - R.T) / (2 * np.sqrt(2)) < 1e-5
+            n_checked += 1
+    assert n_checked >= len(dyn)  # at least the previous placements came through
+
+
+def test_step_without_nms_is_a_superset():
+    """NMS only removes proposals: every pose id that survives the NMS step is in the plain top-k step"""
+    scene = common.tiny_scene()
+    rots, _ = common.rotation_xforms(8)
+    trans = synth.translation_seeds(scene.scan, 64, seed=9)
+    models = pipeline.upload_objects(scene.objects)
+    scan1, scan2 = (scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2))
+    a = pipeline.run_step(scan1, scan2, models, rots, trans, top_k=16)
+    b = pipeline.run_step(scan1, scan2, models, rots, trans, top_k=16, nms_dist=0.2)
+    for ia, ib in zip(a.pose_ids, b.pose_ids):
+        assert set(ib.tolist()) <= set(ia.tolist())

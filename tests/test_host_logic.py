@@ -75,3 +75,14 @@ def test_merge_topk_is_deterministic_and_order_independent():
     assert (np.diff(a[0][:, 16]) <= 0).all()
     full = pipeline.merge_topk([props], [ids], 0)
     assert len(full[0]) == 40
+
+
+def test_cloud_centroid_matches_oracle():
+    """rs_pointcloud_centroid (rs_pointcloud.h:1319-1339): the product's host helper against the oracle's restatement"""
+    from oracle import orcbind as O
+    from rescan_b200 import posegrid
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 1000, 50_000):
+        p = (rng.standard_normal((n, 3)) * 3 + 1).astype(np.float32)
+        assert (posegrid.cloud_centroid(p) == O.centroid(p)).all()
+    assert (posegrid.cloud_centroid(np.zeros((0, 3), np.float32)) == 0).all()

@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=None, help="objects in flight at once (default RSGPU_LANES or 4); 1 = serial object loop")
     ap.add_argument("--nms", type=int, default=1, help="1: the two NMS passes of main.cpp:161/205 run on the GPU inside the step; 0: top-k only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -217,22 +218,22 @@ def main():
     hp = {k: v.numpy() for k, v in pinned.items()}
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
 
-    def step(resident):
+    def step(resident, lanes=None):
         flush.zero_()
         return pipeline.run_step((hp["p1"], hp["n1"]), (hp["p2"], hp["n2"]), models, rotations, translations, top_k=64, rank=rank,
                                  world=world, dist=dist if world > 1 else None, device=device, scan_dev=scan_dev if resident else None,
-                                 nms_dist=0.2 if args.nms else None)
+                                 nms_dist=0.2 if args.nms else None, lanes=args.lanes if lanes is None else lanes)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(resident, k):
+    def timed(resident, k, lanes=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = [step(resident) for _ in range(k)]
+        res = [step(resident, lanes) for _ in range(k)]
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -252,17 +253,20 @@ def main():
         step(True)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    api.profile_reset()
-    api.profile_enable(True)
     l0 = api.launch_count()
     ms_value, res = timed(True, args.steps)
     launches = api.launch_count() - l0
-    api.profile_enable(False)
-    dense_ms, dense_launches = api.profile_get("score_dense")
-    prof = {n: api.profile_get(n) for n in ("grid_build", "score_dense", "score", "icp", "overlap")}  # ms over the timed steps, launches
     for _ in range(1):
         step(False)
     ms_e2e, res_e2e = timed(False, args.steps)
+    # per-kernel device times for the roofline line: the same steps with ONE object in flight, so that the CUDA-event
+    # interval around a launch (taken on its launch stream) is that kernel's own duration and not a share of the device
+    api.profile_reset()
+    api.profile_enable(True)
+    ms_serial, _ = timed(True, args.steps, lanes=1)
+    api.profile_enable(False)
+    dense_ms, dense_launches = api.profile_get("score_dense")
+    prof = {n: api.profile_get(n) for n in ("grid_build", "score_dense", "score", "icp", "overlap")}  # ms over those steps, launches
     clk = clocks.stop()
 
     def total(x):
@@ -293,14 +297,15 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "score_kernel<GRID> (dense level-4 pose scoring)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dense_bytes / max(len(census), 1),
-                             "launches_timed": dense_launches, "avg_launch_ms": dense_ms / max(dense_launches, 1),
+                             "launches_timed": dense_launches, "timed_in": "a separate pass of the same steps with one object in flight (lanes=1)", "avg_launch_ms": dense_ms / max(dense_launches, 1),
                              "dense_nn_queries_per_sec": dense_queries * args.steps / (dense_ms * 1e-3) if dense_ms > 0 else 0.0,
                              "note": "algorithmic bytes = what the reference's search reads for the same poses: 8B/cell + 16B/point + "
                                      "12B/normal per query + 68B/pose (SURVEY.md 8d, no early-out credit), rank 0 shard. The kernel "
                                      "prunes cells by distance and normal cone and skips poses that cannot pass the level threshold, "
                                      "and the 5 MB working set is L2/L1-resident (traffic = DRAM bytes of one launch), so achieved "
                                      "exceeds the HBM peak: it is an algorithmic-throughput figure, not DRAM utilisation"},
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                "kernel_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()}, step_one_object_in_flight=ms_serial / args.steps),
+                "lanes": args.lanes if args.lanes is not None else pipeline.default_lanes(),
                 "clocks": clk}
         if world == 1 and not args.no_cpu_baseline:
             rate, info, _ = cpu_reference_rate(scene, rotations, translations, target_seconds=15.0)

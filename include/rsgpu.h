@@ -13,7 +13,10 @@
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with RSGPU_ERR_NO_DEVICE.
  *   - handles are opaque and own device memory; destroy them with the matching *_destroy.
  *   - all work is enqueued on one stream per process (legacy default stream unless rsgpu_set_stream
- *     was called); host-buffer calls synchronise that stream before returning.
+ *     was called); host-buffer calls synchronise that stream before returning.  A host thread that called
+ *     rsgpu_thread_attach( lane ) uses that lane's own stream instead, so independent call chains issued from
+ *     different threads (one per object, say) overlap on the device.  Handles may be shared between threads
+ *     for reading; the library keeps no other cross-call state.
  */
 #ifndef RSGPU_H
 #define RSGPU_H
@@ -46,6 +49,12 @@ int rsgpu_device_count( void );
 int rsgpu_set_device( int device );       /* cudaSetDevice for this process; default 0 */
 int rsgpu_set_stream( void* cuda_stream );/* cudaStream_t to enqueue on; NULL = legacy default stream */
 int rsgpu_synchronize( void );
+/* lanes: rsgpu_thread_attach( lane ), 0 <= lane < rsgpu_lane_count(), binds the CALLING host thread to the lane's
+   stream (created on first use, non-blocking) and to the process's device; lane < 0 detaches.  The reference is
+   single-threaded (SURVEY.md 8b "Threading"); lanes are how a caller overlaps its per-object loops
+   (apps/pose_proposal/main.cpp:175-204, pose_proposal.cpp:190-250) on one GPU. */
+int rsgpu_lane_count( void );
+int rsgpu_thread_attach( int lane );
 const char* rsgpu_last_error( void );
 const char* rsgpu_version( void );
 

@@ -69,6 +69,8 @@ SIGNATURES = {
     "rsgpu_set_device": (_int, [_int]),
     "rsgpu_set_stream": (_int, [_vp]),
     "rsgpu_synchronize": (_int, []),
+    "rsgpu_lane_count": (_int, []),
+    "rsgpu_thread_attach": (_int, [_int]),
     "rsgpu_last_error": (C.c_char_p, []),
     "rsgpu_version": (C.c_char_p, []),
     "rsgpu_set_option": (_int, [C.c_char_p, C.c_char_p]),
@@ -150,6 +152,15 @@ def set_device(i):
 
 def synchronize():
     _check(lib().rsgpu_synchronize())
+
+
+def lane_count():
+    return int(lib().rsgpu_lane_count())
+
+
+def thread_attach(lane):
+    """bind the calling host thread to a lane (its own stream); lane < 0 detaches"""
+    _check(lib().rsgpu_thread_attach(int(lane)))
 
 
 def launch_count():

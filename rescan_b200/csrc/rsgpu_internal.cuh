@@ -29,6 +29,7 @@ int ensure_device();
 std::string option( const char* key );   // value set by rsgpu_set_option, else environment RSGPU_<KEY>, else ""
 void set_option( const char* key, const char* value );
 int aux_streams( int n, cudaStream_t** out ); // helper streams (non-blocking) for internally overlapped work
+cudaStream_t bulk_stream();                   // where long throughput launches go: low priority inside a lane, else rt().stream
 void prof_add_pending( const char* name, cudaEvent_t a, cudaEvent_t b, bool own_a, bool own_b );
 void count_launch(); // one of OUR kernels was launched (library kernels such as CUB are not counted)
 
@@ -60,8 +61,10 @@ struct DevBuf
 struct ProfScope
 {
   const char* name;
+  cudaStream_t st = nullptr;
   cudaEvent_t a = nullptr, b = nullptr;
-  explicit ProfScope( const char* n );
+  explicit ProfScope( const char* n );          // on the calling thread's stream
+  ProfScope( const char* n, cudaStream_t s );
   ~ProfScope();
 };
 } // namespace rs

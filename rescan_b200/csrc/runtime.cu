@@ -43,22 +43,45 @@ void set_option( const char* key, const char* value )
   if( value && *value ) { g_opts[key] = value; } else { g_opts.erase( key ); }
 }
 
-Runtime& rt()
-{
-  static Runtime r;
-  return r;
-}
+// Lanes: a host thread that called rsgpu_thread_attach( lane ) enqueues everything on that lane's own stream (and
+// helper streams), so independent call chains - one object's propose -> NMS -> ICP -> rescoring next to another's -
+// overlap on the device.  Threads that never attached share the process-wide runtime (lane -1).
+constexpr int N_LANES = 8;
+static Runtime g_rt;
+static Runtime g_lane_rt[N_LANES];
+static cudaStream_t g_lane_stream[N_LANES];
+static cudaStream_t g_lane_bulk[N_LANES];
+static thread_local int tl_lane = -1;
+static std::mutex g_lane_mu;
 
-// helper streams for work the library overlaps internally (ICP partitions); created once per process
+Runtime& rt() { return tl_lane >= 0 ? g_lane_rt[tl_lane] : g_rt; }
+
+// Stream priorities inside a lane: the lane's own stream and its helper streams carry the latency-bound launches
+// (verification, NMS rounds, ICP iterations) at the highest priority; the long throughput launches (dense pose
+// search) go to the lane's bulk stream at the lowest one, so a small launch of one object never queues behind the
+// pending blocks of another object's dense search.
+static void priority_range( int* least, int* greatest )
+{
+  *least = 0; *greatest = 0;
+  if( cudaDeviceGetStreamPriorityRange( least, greatest ) != cudaSuccess ) { cudaGetLastError(); *least = 0; *greatest = 0; }
+}
+cudaStream_t bulk_stream() { return tl_lane >= 0 && g_lane_bulk[tl_lane] ? g_lane_bulk[tl_lane] : rt().stream; }
+
+// helper streams for work the library overlaps internally (ICP partitions); created once per lane
 int aux_streams( int n, cudaStream_t** out )
 {
-  static cudaStream_t streams[4] = { nullptr, nullptr, nullptr, nullptr };
+  static cudaStream_t streams[N_LANES + 1][4];
+  static std::mutex mu;
   if( n > 4 ) { return fail( RSGPU_ERR_INVALID, "rsgpu: at most 4 helper streams" ); }
+  std::lock_guard<std::mutex> lk( mu );
+  cudaStream_t* mine = streams[tl_lane + 1];
+  int least, greatest;
+  priority_range( &least, &greatest );
   for( int i = 0; i < n; ++i )
   {
-    if( !streams[i] ) { RS_CUDA( cudaStreamCreateWithFlags( &streams[i], cudaStreamNonBlocking ) ); }
+    if( !mine[i] ) { RS_CUDA( cudaStreamCreateWithPriority( &mine[i], cudaStreamNonBlocking, greatest ) ); }
   }
-  *out = streams;
+  *out = mine;
   return RSGPU_OK;
 }
 
@@ -134,16 +157,17 @@ void prof_add_pending( const char* name, cudaEvent_t a, cudaEvent_t b, bool own_
   g_pending->push_back( Pending{ name, a, b, own_a, own_b } );
 }
 
-ProfScope::ProfScope( const char* n ) : name( n )
+ProfScope::ProfScope( const char* n ) : ProfScope( n, rt().stream ) {}
+ProfScope::ProfScope( const char* n, cudaStream_t s ) : name( n ), st( s )
 {
   if( !rt().profile ) { return; }
   cudaEventCreate( &a ); cudaEventCreate( &b );
-  cudaEventRecord( a, rt().stream );
+  cudaEventRecord( a, st );
 }
 ProfScope::~ProfScope()
 {
   if( !a ) { return; }
-  cudaEventRecord( b, rt().stream );
+  cudaEventRecord( b, st );
   std::lock_guard<std::mutex> lk( g_prof_mu );
   if( !g_pending ) { g_pending = new std::vector<Pending>(); }
   g_pending->push_back( Pending{ name, a, b, true, true } );
@@ -179,6 +203,32 @@ int rsgpu_set_device( int device )
   return RSGPU_OK;
 }
 
+int rsgpu_lane_count( void ) { return N_LANES; }
+
+int rsgpu_thread_attach( int lane )
+{
+  if( lane >= N_LANES ) { return fail( RSGPU_ERR_INVALID, "rsgpu_thread_attach: lane out of range" ); }
+  if( lane < 0 ) { tl_lane = -1; return RSGPU_OK; }
+  tl_lane = -1;
+  RS_TRY( ensure_device() );
+  RS_CUDA( cudaSetDevice( g_rt.device ) ); // the current device is per host thread
+  {
+    std::lock_guard<std::mutex> lk( g_lane_mu );
+    if( !g_lane_stream[lane] )
+    {
+      int least, greatest;
+      priority_range( &least, &greatest );
+      RS_CUDA( cudaStreamCreateWithPriority( &g_lane_stream[lane], cudaStreamNonBlocking, greatest ) );
+      RS_CUDA( cudaStreamCreateWithPriority( &g_lane_bulk[lane], cudaStreamNonBlocking, least ) );
+    }
+    g_lane_rt[lane].stream = g_lane_stream[lane];
+    g_lane_rt[lane].device = g_rt.device;
+    g_lane_rt[lane].profile = g_rt.profile;
+  }
+  tl_lane = lane;
+  return RSGPU_OK;
+}
+
 int rsgpu_set_stream( void* s )
 {
   rt().stream = (cudaStream_t)s;
@@ -199,7 +249,8 @@ int64_t rsgpu_launch_count( void ) { return (int64_t)rs::launches(); }
 
 int rsgpu_profile_enable( int on )
 {
-  rt().profile = on != 0;
+  g_rt.profile = on != 0;
+  for( int i = 0; i < N_LANES; ++i ) { g_lane_rt[i].profile = on != 0; }
   return RSGPU_OK;
 }
 

@@ -298,8 +298,20 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
   long long blocks = ( warps + 3 ) / 4;
   if( blocks > 2147483647ll ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu score: too many poses for one launch" ); }
   GridView g = scene->view();
+  // the dense search is the throughput launch of the path: inside a lane it runs on the lane's low-priority stream
+  // (runtime.cu), so the short launches of other objects' chains are dispatched ahead of its pending blocks
+  const cudaStream_t lane_st = st;
+  if( grid_mode && bulk_stream() != st )
   {
-    ProfScope prof( grid_mode ? "score_dense" : "score" );
+    cudaEvent_t fork = nullptr;
+    RS_CUDA( cudaEventCreateWithFlags( &fork, cudaEventDisableTiming ) );
+    cudaEventRecord( fork, lane_st );
+    st = bulk_stream();
+    cudaStreamWaitEvent( st, fork, 0 );
+    cudaEventDestroy( fork );
+  }
+  {
+    ProfScope prof( grid_mode ? "score_dense" : "score", st );
     if( group_impl )
     {
       // lanes per query and resident blocks per SM (register cap) of the group kernel; the defaults are the measured best
@@ -333,6 +345,15 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
       else { score_kernel<false, false><<<(unsigned)blocks, 128, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, partial.p, nullptr ); }
     }
     RS_CHECK_LAUNCH();
+  }
+  if( st != lane_st )
+  {
+    cudaEvent_t join = nullptr;
+    RS_CUDA( cudaEventCreateWithFlags( &join, cudaEventDisableTiming ) );
+    cudaEventRecord( join, st );
+    st = lane_st;
+    cudaStreamWaitEvent( st, join, 0 );
+    cudaEventDestroy( join );
   }
   finalize_kernel<<<(unsigned)( ( n_poses + 255 ) / 256 ), 256, 0, st>>>( partial.p, n_poses, n_split, obj->n, ps.gate, d_scores );
   RS_CHECK_LAUNCH();

@@ -130,21 +130,61 @@ def exchange_rows(upd_list, n_list, world, dist, device):
     return out
 
 
+_POOLS = {}
+
+
+def lane_pool(n_lanes):
+    """persistent host threads, each bound to its own rsgpu lane (stream): per-object call chains submitted to the
+    pool overlap on the device (ctypes releases the GIL for the duration of every library call)"""
+    import concurrent.futures
+    import itertools
+    import threading
+    n_lanes = max(1, min(int(n_lanes), api.lane_count()))
+    if n_lanes not in _POOLS:
+        counter, lock = itertools.count(), threading.Lock()
+
+        def attach():
+            with lock:
+                lane = next(counter)
+            api.thread_attach(lane)
+        _POOLS[n_lanes] = concurrent.futures.ThreadPoolExecutor(max_workers=n_lanes, initializer=attach)
+    return _POOLS[n_lanes]
+
+
+def _run(pool, fn, items, order=None):
+    """fn(*item) for every item, results in item order; with a pool the items are SUBMITTED in `order` (the exposed tail
+    of a step is the chain that finishes last, so the cheapest chain should start last)"""
+    if pool is None:
+        return [fn(*it) for it in items]
+    order = range(len(items)) if order is None else order
+    futs = {i: pool.submit(fn, *items[i]) for i in order}
+    return [futs[i].result() for i in range(len(items))]
+
+
+def default_lanes():
+    import os
+    return int(os.environ.get("RSGPU_LANES", "4"))
+
+
 def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, icp_max_dist=0.10,
              icp_max_angle=np.float32(np.deg2rad(60.0)), rank=0, world=1, dist=None, device=None,
-             scan_dev=None, do_icp=True, nms_dist=None, previous=None):
+             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None):
     """scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
     {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead.
     nms_dist: centroid-distance threshold of the two NMS passes (the reference passes 0.2, main.cpp:161/205); None
     skips both.  previous: per dynamic object, float32 [n,16] placements of earlier arrangements, appended with
-    score 10.0 and pose id -1 before the ICP (main.cpp:163-173)."""
-    h2d = d2h = 0
+    score 10.0 and pose id -1 before the ICP (main.cpp:163-173).
+    lanes: how many objects are in flight at once (default RSGPU_LANES or 4; 1 = the reference's serial object loop).
+    The objects are independent (pose_proposal.cpp:190-250, main.cpp:175-204), so every object's chain runs on its own
+    lane: the latency-bound stages of one object (verification, NMS rounds, ICP iterations) fill the device next to the
+    dense search of another.  Results do not depend on the number of lanes."""
+    stats = dict(h2d=0, d2h=0, n_eval=0, n_query=0)
     p1, n1 = scan_lvl1
     p2, n2 = scan_lvl2
     if scan_dev is None:
         g1 = api.HashGrid(p1, 0.05, normals=n1)
         g2 = api.HashGrid(p2, 0.05, normals=n2) if do_icp else None
-        h2d += p1.nbytes + n1.nbytes + (p2.nbytes + n2.nbytes if do_icp else 0)
+        stats["h2d"] += p1.nbytes + n1.nbytes + (p2.nbytes + n2.nbytes if do_icp else 0)
     else:
         g1 = api.HashGrid(device_ptr=scan_dev["p1"], n_pts=len(p1), radius=0.05)
         api._check(api.lib().rsgpu_grid_set_normals_dev(g1.h, scan_dev["n1"]))
@@ -155,73 +195,87 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     n_rot = len(rotations)
     lo, hi = shard_range(len(translations), rank, world)
     my_trans = np.ascontiguousarray(translations[lo:hi])
-    h2d += rotations.nbytes + my_trans.nbytes
-    n_eval = n_query = 0
+    stats["h2d"] += rotations.nbytes + my_trans.nbytes
     dyn = [m for m in models if not m.is_static]  # pose_proposal.cpp:198
-    out_props, out_ids = [], []
-    # ---- dense search + verification per object on this rank's block of translations
-    for m in dyn:
+    lanes = default_lanes() if lanes is None else lanes
+    pool = lane_pool(lanes) if lanes > 1 and len(dyn) > 1 else None
+    nms = nms_dist is not None
+    big_first = sorted(range(len(dyn)), key=lambda i: -len(dyn[i].levels[2]))  # ICP cost grows with the level-2 size
+
+    def add(**kw):  # called from the lane threads: the GIL makes the += atomic enough, the totals are order-free
+        for k, v in kw.items():
+            stats[k] += int(v)
+
+    def search(m):
+        """dense search + verification on this rank's block of translations"""
         props, ids = api.propose_poses(m.levels[4], m.levels[3], m.levels[2], g1, rotations, my_trans, top_k=top_k)
-        d2h += props.nbytes + ids.nbytes
-        n_eval += n_rot * len(my_trans)
-        n_query += n_rot * len(my_trans) * len(m.levels[4])
-        out_props.append(props)
-        out_ids.append(ids + lo * n_rot)
-    # ---- the only exchange of the search: one all-gather of every object's top-k, identical merge on every rank
-    if world > 1:
-        out_props, out_ids = exchange_topk(out_props, out_ids, top_k, dist, device)
-    # ---- NMS (every rank suppresses the same merged lists: no exchange), then the previous placements join
-    if nms_dist is not None:
-        for k, m in enumerate(dyn):
-            if len(out_props[k]):
-                keep = api.non_maxima_suppression(m.levels[3], m.levels[1], m.centroid, out_props[k], nms_dist)
-                h2d += out_props[k].nbytes
-                d2h += keep.nbytes
-                out_props[k], out_ids[k] = out_props[k][keep], out_ids[k][keep]
-    if previous is not None:
-        for k, prev in enumerate(previous):
-            prev = np.asarray(prev, np.float32).reshape(-1, 16)
+        add(d2h=props.nbytes + ids.nbytes, n_eval=n_rot * len(my_trans), n_query=n_rot * len(my_trans) * len(m.levels[4]))
+        return props, ids + lo * n_rot
+
+    def suppress(m, props, ids):
+        if nms and len(props):
+            keep = api.non_maxima_suppression(m.levels[3], m.levels[1], m.centroid, props, nms_dist)
+            add(h2d=props.nbytes, d2h=keep.nbytes)
+            return props[keep], ids[keep]
+        return props, ids
+
+    def candidates(k, m, props, ids):
+        """first NMS, the previous placements, and which entries get refined"""
+        props, ids = suppress(m, props, ids)
+        if previous is not None:
+            prev = np.asarray(previous[k], np.float32).reshape(-1, 16)
             if len(prev):
-                add = np.concatenate([prev, np.full((len(prev), 1), 10.0, np.float32)], axis=1)
-                out_props[k] = np.concatenate([out_props[k], add])
-                out_ids[k] = np.concatenate([out_ids[k], np.full(len(prev), -1, np.int64)])
-    # ---- ICP refinement of every surviving proposal of every object in ONE launch, then rescoring
-    if do_icp:
+                props = np.concatenate([props, np.concatenate([prev, np.full((len(prev), 1), 10.0, np.float32)], axis=1)])
+                ids = np.concatenate([ids, np.full(len(prev), -1, np.int64)])
         # without NMS the -1 verification failures (pose_proposal.cpp:292) are not worth refining; with it the list is
         # what the reference's main refines: every survivor (main.cpp:175-204)
-        cands = [np.arange(len(p)) if nms_dist is not None else np.nonzero(p[:, 16] > 0)[0] for p in out_props]
-        shares = [c[rank::world] for c in cands]
-        jobs = [(m, p[s, :16]) for m, p, s in zip(dyn, out_props, shares) if len(s)]
-        refined = api.icp_align_multi([m.levels[2] for m, _ in jobs], g2, [t for _, t in jobs], icp_max_dist, icp_max_angle) if jobs else []
-        ri = 0
-        updates = []
-        for m, mine in zip(dyn, shares):
-            if len(mine):
-                T, err, it = refined[ri]
-                ri += 1
-                sc = api.compute_object_alignment_scores(m.levels[1], g1, T, 32, 0.10)  # main.cpp:199
-                h2d += 2 * T.nbytes
-                d2h += T.nbytes + err.nbytes + it.nbytes + sc.nbytes
-                n_eval += len(mine)
-                n_query += len(mine) * len(m.levels[1])
-                updates.append(np.concatenate([T, sc[:, None]], axis=1).astype(np.float32))
-            else:
-                updates.append(np.zeros((0, api.POSE_FLOATS), np.float32))
-        if world > 1:  # second (and last) exchange: the refined rows of every object in one all-gather
-            updates = exchange_rows(updates, [len(c) for c in cands], world, dist, device)
-        for k, (m, c, upd) in enumerate(zip(dyn, cands, updates)):
-            props, ids = out_props[k], out_ids[k]
-            if len(c):
-                props[c] = upd
-            if nms_dist is not None and len(props):
-                keep = api.non_maxima_suppression(m.levels[3], m.levels[1], m.centroid, props, nms_dist)
-                props, ids = props[keep], ids[keep]
-            order = np.lexsort((ids, -props[:, 16].astype(np.float64)))  # mgs_sort_poses: descending score
-            out_props[k], out_ids[k] = props[order], ids[order]
+        cand = np.arange(len(props)) if nms else np.nonzero(props[:, 16] > 0)[0]
+        return props, ids, cand
+
+    def refine(m, props, mine):
+        """ICP at level 2 + rescoring at level 1 with k = 32 of the entries `mine` (main.cpp:195-201) -> rows [len(mine), 17]"""
+        if not len(mine):
+            return np.zeros((0, api.POSE_FLOATS), np.float32)
+        T, err, it = api.icp_align(m.levels[2], g2, props[mine, :16], icp_max_dist, icp_max_angle)
+        sc = api.compute_object_alignment_scores(m.levels[1], g1, T, 32, 0.10)
+        add(h2d=2 * T.nbytes, d2h=T.nbytes + err.nbytes + it.nbytes + sc.nbytes, n_eval=len(mine), n_query=len(mine) * len(m.levels[1]))
+        return np.concatenate([T, sc[:, None]], axis=1).astype(np.float32)
+
+    def finish(m, props, ids, cand, upd):
+        if len(cand):
+            props[cand] = upd
+        props, ids = suppress(m, props, ids)
+        order = np.lexsort((ids, -props[:, 16].astype(np.float64)))  # mgs_sort_poses: descending score
+        return props[order], ids[order]
+
+    if world == 1:
+        def chain(k, m):
+            props, ids = search(m)
+            if not do_icp:
+                return suppress(m, props, ids) if nms else (props, ids)
+            props, ids, cand = candidates(k, m, props, ids)
+            return finish(m, props, ids, cand, refine(m, props, cand))
+        res = _run(pool, chain, list(enumerate(dyn)), big_first)
+        out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
+    else:
+        res = _run(pool, lambda m: search(m), [(m,) for m in dyn])
+        # the only exchange of the search: ONE all-gather of every object's top-k, identical merge on every rank
+        out_props, out_ids = exchange_topk([r[0] for r in res], [r[1] for r in res], top_k, dist, device)
+        if do_icp:
+            def middle(k, m):  # every rank suppresses the same merged list (no exchange) and refines its interleaved share
+                props, ids, cand = candidates(k, m, out_props[k], out_ids[k])
+                return props, ids, cand, refine(m, props, cand[rank::world])
+            mid = _run(pool, middle, list(enumerate(dyn)), big_first)
+            # second (and last) exchange: the refined rows of every object in one all-gather
+            updates = exchange_rows([r[3] for r in mid], [len(r[2]) for r in mid], world, dist, device)
+            res = _run(pool, finish, [(m, r[0], r[1], r[2], u) for m, r, u in zip(dyn, mid, updates)])
+        else:
+            res = _run(pool, suppress, [(m, p, i) for m, p, i in zip(dyn, out_props, out_ids)])
+        out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
     g1.close()
     if g2 is not None:
         g2.close()
-    return StepResult(out_props, out_ids, n_eval, n_query, h2d, d2h)
+    return StepResult(out_props, out_ids, stats["n_eval"], stats["n_query"], stats["h2d"], stats["d2h"])
 
 
 def make_workload(name):

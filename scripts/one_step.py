@@ -1,6 +1,6 @@
 """a few pose_proposal steps of a named workload (ncu captures, A/B runs of kernel variants via RSGPU_* env vars):
    python scripts/one_step.py [C2] [n_steps]   -> per-kernel ms/step and a digest of the proposals
-   STEP_NMS=1 adds the two NMS passes of main.cpp:161/205 to the step (bench.py's default)"""
+   STEP_LANES=n runs n objects at once on their own lanes (bench.py's default is 4); STEP_NMS=1 adds the two NMS passes of main.cpp:161/205 to the step (bench.py's default)"""
 import hashlib
 import os
 import sys
@@ -14,17 +14,18 @@ from rescan_b200 import api, pipeline  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 api.set_device(0)
+LANES = int(os.environ.get("STEP_LANES", "1"))
 NMS = 0.2 if os.environ.get("STEP_NMS", "0") == "1" else None
 scene, rotations, translations = pipeline.make_workload(name)
 models = pipeline.upload_objects(scene.objects)
 args = ((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rotations, translations)
 if n_steps > 1:
-    pipeline.run_step(*args, top_k=64, nms_dist=NMS)  # warm-up
+    pipeline.run_step(*args, top_k=64, nms_dist=NMS, lanes=LANES)  # warm-up
 api.profile_reset()
 api.profile_enable(True)
 t0 = time.perf_counter()
 for _ in range(n_steps):
-    res = pipeline.run_step(*args, top_k=64, nms_dist=NMS)
+    res = pipeline.run_step(*args, top_k=64, nms_dist=NMS, lanes=LANES)
 dt = (time.perf_counter() - t0) / n_steps
 api.profile_enable(False)
 h = hashlib.sha1()

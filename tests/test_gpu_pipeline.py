@@ -92,3 +92,21 @@ def test_step_without_nms_is_a_superset():
     b = pipeline.run_step(scan1, scan2, models, rots, trans, top_k=16, nms_dist=0.2)
     for ia, ib in zip(a.pose_ids, b.pose_ids):
         assert set(ib.tolist()) <= set(ia.tolist())
+
+
+def test_lanes_do_not_change_results():
+    """per-object chains on concurrent lanes (streams) give bit-identical lists to the serial object loop"""
+    scene = common.small_scene()
+    rots, _ = common.rotation_xforms(12)
+    trans = synth.translation_seeds(scene.scan, 192, seed=3)
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    models = pipeline.upload_objects(scene.objects)
+    scan1, scan2 = (scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2))
+    ref = pipeline.run_step(scan1, scan2, models, rots, trans, top_k=16, nms_dist=0.2, lanes=1)
+    for lanes in (2, 4, 8):
+        for _ in range(2):
+            got = pipeline.run_step(scan1, scan2, models, rots, trans, top_k=16, nms_dist=0.2, lanes=lanes)
+            assert got.n_evaluations == ref.n_evaluations and got.n_queries == ref.n_queries
+            for a, b, ia, ib in zip(got.proposals, ref.proposals, got.pose_ids, ref.pose_ids):
+                assert a.shape == b.shape and (a == b).all() and (ia == ib).all()

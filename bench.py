@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=None, help="objects in flight at once (default RSGPU_LANES or 4); 1 = serial object loop")
+    ap.add_argument("--lanes", type=int, default=None, help="objects in flight at once (default RSGPU_LANES or 8); 1 = serial object loop")
     ap.add_argument("--nms", type=int, default=1, help="1: the two NMS passes of main.cpp:161/205 run on the GPU inside the step; 0: top-k only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

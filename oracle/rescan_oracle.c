@@ -875,3 +875,40 @@ void orc_nms( const float* pos3, int32_t n3, const float* pos1, int32_t n1, cons
   for( int32_t i = 0; i < n; ++i ) { keep[i] = mark[i] == 1; }
   free( mark );
 }
+
+/* ------------------------------------------------------------------------------------------------ level building */
+/* rs_pointcloud__compute_level_poisson (lib/rs/rs_pointcloud.h:984-1037): greedy Poisson-disk subsampling of level 0.
+   A grid is built over level 0 with radius 2.5 * voxel (:989-990); then, in ascending index order, the first point not
+   yet marked becomes a sample and every point its radius search returns (r = voxel, the max_n_neigh NEAREST points
+   with dist^2 < r^2, the sample itself included, :1017-1035) is marked.  max_n_neigh = (size_t)(1024 * (level / 4.0f)),
+   256 if that is 0 (:994-995).  out_idx: the samples' level-0 indices, ascending (the level's arrays are copies of those
+   rows, :1077-1086).  Returns the number of samples. */
+int32_t orc_poisson_level( const float* pos0, int32_t n, float voxel, int32_t level, int32_t* out_idx )
+{
+  if( n <= 0 ) { return 0; }
+  orc_grid_t* g = orc_grid_build( pos0, n, 2.5f * voxel );
+  size_t k = (size_t)( 1024 * ( ( level ) / (float)( 5 - 1 ) ) );
+  if( !k ) { k = 256; }
+  uint8_t* unmarked = (uint8_t*)malloc( (size_t)n );
+  float* d2 = (float*)malloc( k * sizeof( float ) );
+  int32_t* id = (int32_t*)malloc( k * sizeof( int32_t ) );
+  memset( unmarked, 1, (size_t)n );
+  double r = voxel;
+  float r2f = (float)( r * r );
+  size_t n_marked = 0;
+  int32_t n_out = 0, cur = 0;
+  while( n_marked < (size_t)n )
+  {
+    while( !unmarked[cur] ) { cur++; }
+    out_idx[n_out++] = cur;
+    size_t c = orc_radius_query( g, pos0 + 3 * (size_t)cur, r, r2f, k, d2, id );
+    for( size_t i = 0; i < c; ++i )
+    {
+      if( unmarked[id[i]] ) { n_marked++; }
+      unmarked[id[i]] = 0;
+    }
+  }
+  free( unmarked ); free( d2 ); free( id );
+  orc_grid_free( g );
+  return n_out;
+}

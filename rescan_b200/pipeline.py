@@ -41,6 +41,7 @@ class StepResult:
     n_queries: int           # object points searched by THIS rank
     h2d_bytes: int
     d2h_bytes: int
+    trace: list = None       # with trace=True: (object index, stage, t_begin, t_end) host times in seconds since the step began
 
 
 def upload_objects(objects, levels=(4, 3, 2, 1)):
@@ -163,24 +164,35 @@ def _run(pool, fn, items, order=None):
 
 def default_lanes():
     import os
-    return int(os.environ.get("RSGPU_LANES", "4"))
+    return int(os.environ.get("RSGPU_LANES", "8"))
 
 
 def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, icp_max_dist=0.10,
              icp_max_angle=np.float32(np.deg2rad(60.0)), rank=0, world=1, dist=None, device=None,
-             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None):
+             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None, trace=False):
     """scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
     {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead.
     nms_dist: centroid-distance threshold of the two NMS passes (the reference passes 0.2, main.cpp:161/205); None
     skips both.  previous: per dynamic object, float32 [n,16] placements of earlier arrangements, appended with
     score 10.0 and pose id -1 before the ICP (main.cpp:163-173).
-    lanes: how many objects are in flight at once (default RSGPU_LANES or 4; 1 = the reference's serial object loop).
+    lanes: how many objects are in flight at once (default RSGPU_LANES or 8; 1 = the reference's serial object loop).
     The objects are independent (pose_proposal.cpp:190-250, main.cpp:175-204), so every object's chain runs on its own
     lane: the latency-bound stages of one object (verification, NMS rounds, ICP iterations) fill the device next to the
     dense search of another.  Results do not depend on the number of lanes."""
+    import time
     stats = dict(h2d=0, d2h=0, n_eval=0, n_query=0)
+    t_step, events = time.perf_counter(), []
+
+    def staged(k, stage, fn, *a):
+        if not trace:
+            return fn(*a)
+        t0 = time.perf_counter()
+        out = fn(*a)
+        events.append((k, stage, t0 - t_step, time.perf_counter() - t_step))
+        return out
     p1, n1 = scan_lvl1
     p2, n2 = scan_lvl2
+    t_g = time.perf_counter()
     if scan_dev is None:
         g1 = api.HashGrid(p1, 0.05, normals=n1)
         g2 = api.HashGrid(p2, 0.05, normals=n2) if do_icp else None
@@ -192,6 +204,8 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         if do_icp:
             g2 = api.HashGrid(device_ptr=scan_dev["p2"], n_pts=len(p2), radius=0.05)
             api._check(api.lib().rsgpu_grid_set_normals_dev(g2.h, scan_dev["n2"]))
+    if trace:
+        events.append((-1, "grids", t_g - t_step, time.perf_counter() - t_step))
     n_rot = len(rotations)
     lo, hi = shard_range(len(translations), rank, world)
     my_trans = np.ascontiguousarray(translations[lo:hi])
@@ -250,11 +264,12 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
 
     if world == 1:
         def chain(k, m):
-            props, ids = search(m)
+            props, ids = staged(k, "search", search, m)
             if not do_icp:
                 return suppress(m, props, ids) if nms else (props, ids)
-            props, ids, cand = candidates(k, m, props, ids)
-            return finish(m, props, ids, cand, refine(m, props, cand))
+            props, ids, cand = staged(k, "nms1", candidates, k, m, props, ids)
+            upd = staged(k, "refine", refine, m, props, cand)
+            return staged(k, "nms2", finish, m, props, ids, cand, upd)
         res = _run(pool, chain, list(enumerate(dyn)), big_first)
         out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
     else:
@@ -275,7 +290,9 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     g1.close()
     if g2 is not None:
         g2.close()
-    return StepResult(out_props, out_ids, stats["n_eval"], stats["n_query"], stats["h2d"], stats["d2h"])
+    if trace:
+        events.append((-1, "step", 0.0, time.perf_counter() - t_step))
+    return StepResult(out_props, out_ids, stats["n_eval"], stats["n_query"], stats["h2d"], stats["d2h"], sorted(events, key=lambda e: e[2]) if trace else None)
 
 
 def make_workload(name):

@@ -35,3 +35,7 @@ for p, i in zip(res.proposals, res.pose_ids):
 prof = {n: round(api.profile_get(n)[0] / n_steps, 3) for n in ("grid_build", "score_dense", "score", "icp", "icp_search", "icp_solve", "overlap")}
 env = {k: v for k, v in os.environ.items() if k.startswith("RSGPU_")}
 print(f"env {env} wall {dt * 1e3:.2f} ms/step kernels {prof} evaluations {res.n_evaluations} launches {api.launch_count()} digest {h.hexdigest()[:12]}")
+if os.environ.get("STEP_TRACE") == "1":
+    tr = pipeline.run_step(*args, top_k=64, nms_dist=NMS, lanes=LANES, trace=True).trace
+    for k, stage, a, b in tr:
+        print(f"  obj {k:2d} {stage:7s} {a * 1e3:7.2f} -> {b * 1e3:7.2f} ms  ({(b - a) * 1e3:6.2f})")

@@ -237,6 +237,17 @@ int rsgpu_overlap_factors( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1,
 int rsgpu_nms( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1, const float centroid[3], const float* proposals, int32_t n,
                float dist_threshold, uint8_t* keep );
 
+/* ---- level building ---------------------------------------------------------------------------
+   rsgpu_poisson_level replaces the sampling loop of rs_pointcloud__compute_level_poisson (lib/rs/rs_pointcloud.h:984-1037):
+   pts = the n level-0 points, voxel = pc->voxel_size[level] (the disk radius), max_n_neigh = the k of the reference's
+   search, (size_t)(1024 * (level / 4.0f)) or 256 when that is 0 (:994-995).  out_indices (room for n) receives the
+   ascending level-0 indices of the samples - the level's arrays are copies of those rows (:1077-1086) - and *n_out
+   their number; *n_rounds (nullable) the number of propagation rounds.  The result equals the reference's sequential
+   greedy selection exactly as long as no sample has more than max_n_neigh points inside its disk (the reference then
+   marks only the nearest max_n_neigh); such an input fails with RSGPU_ERR_UNSUPPORTED. */
+int rsgpu_poisson_level( const float* pts, int32_t n, float voxel, int32_t max_n_neigh, int32_t* out_indices, int32_t* n_out,
+                         int32_t* n_rounds );
+
 #ifdef __cplusplus
 }
 #endif

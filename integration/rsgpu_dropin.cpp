@@ -1,21 +1,30 @@
 // Drop-in replacement of the hot-path symbols of mhalber/Rescan's pose_proposal executable, on top of the
 // rsgpu C ABI (include/rsgpu.h).  Linked together with the reference's UNMODIFIED apps/pose_proposal/main.cpp
 // (see integration/Makefile and INTEGRATION.md) it gives a `pose_proposal` binary whose dense pose search,
-// verification, ICP refinement and rescoring run on the GPU while loading, NMS, sorting and saving stay
-// reference host code.  Nothing here is copied from the reference: the reference headers are included in place
+// verification, non-maxima suppression, ICP refinement and rescoring run on the GPU while loading, sorting and saving
+// stay reference host code.  Nothing here is copied from the reference: the reference headers are included in place
 // for their TYPES only (no *_IMPLEMENTATION define), exactly like apps/pose_proposal/pose_proposal.cpp:1-17 does.
 //
 //   replaces                                   (reference)                               with
 //   mgs_propose_poses                          apps/pose_proposal/pose_proposal.cpp:325  rsgpu_propose_poses
 //   mgs_compute_object_alignment_score         apps/pose_proposal/pose_proposal.cpp:93   rsgpu_score_poses
+//   mgs_non_maxima_suppresion                  apps/pose_proposal/pose_proposal.cpp:371  rsgpu_nms
 //   icp_align                                  lib/rs/icp.h:416                          rsgpu_icp_align_batch
+//
+// The reference loops over the objects serially (pose_proposal.cpp:190-250, :377); the objects are independent, so the
+// two per-object loops replaced here hand every object to a host thread bound to its own rsgpu lane (stream): the
+// latency-bound stages of one object run next to the dense search of another.  Results do not depend on that.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <cassert>
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -45,9 +54,29 @@ void die( const char* what )
 typedef std::pair<const void*, size_t> key_t;
 std::map<key_t, rsgpu_grid_t*> g_grids;    // grids over (positions pointer, count): the scan levels never change in a run
 std::map<key_t, rsgpu_cloud_t*> g_clouds;
+std::mutex g_cache_mu;                     // the caches are filled from the lane threads too
+
+// fn( i ) for i in [0, n) on up to rsgpu_lane_count() host threads, each bound to its own lane
+template <class F>
+void for_each_object_on_lanes( int32_t n, F fn )
+{
+  const int n_threads = std::min<int>( rsgpu_lane_count(), n );
+  if( n_threads <= 1 ) { for( int32_t i = 0; i < n; ++i ) { fn( i ); } return; }
+  std::atomic<int32_t> next( 0 );
+  std::vector<std::thread> pool;
+  for( int t = 0; t < n_threads; ++t )
+  {
+    pool.emplace_back( [&, t]() {
+      RSGPU_OR_DIE( rsgpu_thread_attach( t ) );
+      for( int32_t i = next.fetch_add( 1 ); i < n; i = next.fetch_add( 1 ) ) { fn( i ); }
+    } );
+  }
+  for( size_t t = 0; t < pool.size(); ++t ) { pool[t].join(); }
+}
 
 rsgpu_grid_t* grid_for( const msh_vec3_t* pos, const msh_vec3_t* nor, size_t n )
 {
+  std::lock_guard<std::mutex> lk( g_cache_mu );
   key_t k( pos, n );
   std::map<key_t, rsgpu_grid_t*>::iterator it = g_grids.find( k );
   if( it != g_grids.end() ) { return it->second; }
@@ -61,6 +90,7 @@ rsgpu_grid_t* grid_for( const msh_vec3_t* pos, const msh_vec3_t* nor, size_t n )
 
 rsgpu_cloud_t* cloud_for( const msh_vec3_t* pos, const msh_vec3_t* nor, size_t n )
 {
+  std::lock_guard<std::mutex> lk( g_cache_mu );
   key_t k( pos, n );
   std::map<key_t, rsgpu_cloud_t*>::iterator it = g_clouds.find( k );
   if( it != g_clouds.end() ) { return it->second; }
@@ -116,32 +146,72 @@ mgs_propose_poses( rsdb_t* rsdb, rs_pointcloud_t* input_scan, msh_array( msh_arr
 
   rsgpu_propose_opts_t po;
   rsgpu_propose_default_opts( &po ); // k = 64, r = 0.10, thresholds 0.25 / 0.35 / 0.40, every survivor kept
-  std::vector<float> out( (size_t)( n_trans > 0 ? n_trans : 1 ) * RSGPU_POSE_FLOATS );
   int32_t n_objects = (int32_t)msh_array_len( rsdb->objects );
+  std::vector<std::vector<float> > found( n_objects );
+  std::vector<char> is_static( n_objects );
+  for( int32_t i = 0; i < n_objects; ++i ) { is_static[i] = (char)rsdb_is_object_static( rsdb, i ); } // caches class ids in function statics: keep it on this thread
+  for_each_object_on_lanes( n_objects, [&]( int32_t i ) {
+    if( is_static[i] ) { return; } // pose_proposal.cpp:198
+    rs_pointcloud_t* shape = rsdb->objects[i].shape;
+    rsgpu_cloud_t* lv[3];
+    for( int l = 0; l < 3; ++l ) { lv[l] = cloud_for( shape->positions[4 - l], shape->normals[4 - l], shape->n_pts[4 - l] ); }
+    std::vector<float> out( (size_t)( n_trans > 0 ? n_trans : 1 ) * RSGPU_POSE_FLOATS );
+    int64_t n_out = 0;
+    RSGPU_OR_DIE( rsgpu_propose_poses( lv[0], lv[1], lv[2], scn, rotations.data(), n_rot, translations.data(), n_trans, &po,
+                                       out.data(), NULL, n_trans, &n_out ) );
+    out.resize( (size_t)n_out * RSGPU_POSE_FLOATS );
+    found[i].swap( out );
+  } );
   for( int32_t i = 0; i < n_objects; ++i )
   {
     msh_array( pose_proposal_t ) cur = NULL;
-    if( !rsdb_is_object_static( rsdb, i ) ) // pose_proposal.cpp:198
+    const size_t n_out = found[i].size() / RSGPU_POSE_FLOATS;
+    for( size_t j = 0; j < n_out; ++j )
     {
-      rs_pointcloud_t* shape = rsdb->objects[i].shape;
-      rsgpu_cloud_t* lv[3];
-      for( int l = 0; l < 3; ++l ) { lv[l] = cloud_for( shape->positions[4 - l], shape->normals[4 - l], shape->n_pts[4 - l] ); }
-      int64_t n_out = 0;
-      RSGPU_OR_DIE( rsgpu_propose_poses( lv[0], lv[1], lv[2], scn, rotations.data(), n_rot, translations.data(), n_trans, &po,
-                                         out.data(), NULL, n_trans, &n_out ) );
-      for( int64_t j = 0; j < n_out; ++j )
-      {
-        pose_proposal_t p;
-        memcpy( p.xform.data, &out[(size_t)j * RSGPU_POSE_FLOATS], 64 );
-        p.score = out[(size_t)j * RSGPU_POSE_FLOATS + 16];
-        msh_array_push( cur, p );
-      }
-      msh_cprintf( verbose, "POSE_PROPOSAL:      object %d: %d potential poses (GPU)\n", i, (int)n_out );
+      pose_proposal_t p;
+      memcpy( p.xform.data, &found[i][j * RSGPU_POSE_FLOATS], 64 );
+      p.score = found[i][j * RSGPU_POSE_FLOATS + 16];
+      msh_array_push( cur, p );
     }
+    if( !is_static[i] ) { msh_cprintf( verbose, "POSE_PROPOSAL:      object %d: %d potential poses (GPU)\n", i, (int)n_out ); }
     msh_array_push( *proposed_poses, cur );
   }
   msh_cprintf( verbose, "POSE PROPOSAL: Done in %fs (rsgpu: %d rotations x %d translations per object)\n",
                msh_time_diff_sec( msh_time_now(), t0 ), (int)n_rot, (int)n_trans );
+}
+
+// mgs_non_maxima_suppresion (pose_proposal.cpp:371-452): per object, greedy keep-the-best / discard by voxel overlap > 0.5,
+// centroid distance < dist_threshold or score < 0.01; survivors keep their order (:440-447)
+void
+mgs_non_maxima_suppresion( rsdb_t* rsdb, msh_array( msh_array( pose_proposal_t ) ) * proposed_poses, int32_t verbose, float dist_threshold )
+{
+  const int32_t n_objects = (int32_t)msh_array_len( *proposed_poses );
+  std::vector<msh_vec3_t> centroid( n_objects );
+  for( int32_t i = 0; i < n_objects; ++i ) { centroid[i] = rs_pointcloud_centroid( rsdb->objects[i].shape, 0 ); } // cached in the cloud (:1321)
+  std::vector<std::vector<uint8_t> > keep( n_objects );
+  for_each_object_on_lanes( n_objects, [&]( int32_t i ) {
+    msh_array( pose_proposal_t ) cur = ( *proposed_poses )[i];
+    const int32_t n = (int32_t)msh_array_len( cur );
+    if( n == 0 ) { return; }
+    rs_pointcloud_t* shape = rsdb->objects[i].shape;
+    rsgpu_cloud_t* l3 = cloud_for( shape->positions[3], shape->normals[3], shape->n_pts[3] );
+    rsgpu_cloud_t* l1 = cloud_for( shape->positions[1], shape->normals[1], shape->n_pts[1] );
+    static_assert( sizeof( pose_proposal_t ) == RSGPU_POSE_FLOATS * sizeof( float ), "pose_proposal_t is 16 + 1 floats" );
+    keep[i].resize( (size_t)n );
+    RSGPU_OR_DIE( rsgpu_nms( l3, l1, &centroid[i].x, (const float*)cur, n, dist_threshold, keep[i].data() ) );
+  } );
+  for( int32_t i = 0; i < n_objects; ++i )
+  {
+    msh_array( pose_proposal_t ) cur = ( *proposed_poses )[i];
+    const int32_t n = (int32_t)msh_array_len( cur );
+    if( n == 0 ) { continue; }
+    msh_array( pose_proposal_t ) kept = NULL;
+    int32_t n_keep = 0;
+    for( int32_t j = 0; j < n; ++j ) { if( keep[i][j] ) { msh_array_push( kept, cur[j] ); ++n_keep; } }
+    msh_cprintf( verbose, "POSE_PROPOSAL: Non-max suppress. --> object %d keep: %5d discard: %5d (GPU)\n", i, n_keep, n - n_keep );
+    ( *proposed_poses )[i] = kept;
+    msh_array_free( cur );
+  }
 }
 
 extern "C" float

@@ -58,6 +58,7 @@ def load():
         "orc_posed_bbox": (None, [_f32p, i32, _f32p, _f32p]),
         "orc_overlap_factor": (f32, [_f32p, i32, _f32p, i32, _f32p, _f32p, f32, C.c_int, C.c_int]),
         "orc_nms": (None, [_f32p, i32, _f32p, i32, _f32p, _f32p, i32, f32, _u8p]),
+        "orc_poisson_level": (i32, [_f32p, i32, f32, i32, _i32p]),
         "orc_neighborhood": (None, [vp, _f32p, _f32p, i32, i32, f32, f32, f32, _i32p, _f32p]),
     }
     for name, (res, args) in sig.items():
@@ -237,3 +238,14 @@ def nms(pos3, pos1, centroid_xyz, proposals, dist_threshold=0.2):
     load().orc_nms(p3.reshape(-1), len(p3), p1.reshape(-1), len(p1), _f32(centroid_xyz).reshape(3), pr.reshape(-1), len(pr),
                    dist_threshold, keep)
     return keep.astype(bool)
+
+
+LEVEL_VOXEL = (0.005, 0.01, 0.02, 0.04, 0.08)  # rs_pointcloud_init (rs_pointcloud.h:145)
+
+
+def poisson_level(pos0, level):
+    """rs_pointcloud__compute_level_poisson (rs_pointcloud.h:984-1037) -> ascending level-0 indices of the level's points"""
+    p = _f32(pos0).reshape(-1, 3)
+    out = np.zeros(len(p), np.int32)
+    n = load().orc_poisson_level(p.reshape(-1), len(p), np.float32(LEVEL_VOXEL[level]), level, out)
+    return out[:n].copy()

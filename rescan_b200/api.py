@@ -108,6 +108,7 @@ SIGNATURES = {
     "rsgpu_unary_costs": (_int, [_vp, _vp, _i32, _i32, _vp]),
     "rsgpu_overlap_factors": (_int, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp]),
     "rsgpu_nms": (_int, [_vp, _vp, _vp, _vp, _i32, _f32, _vp]),
+    "rsgpu_poisson_level": (_int, [_vp, _i32, _f32, _i32, _vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
 }
 
@@ -394,3 +395,36 @@ def non_maxima_suppression(obj_lvl3: PointCloud, obj_lvl1: PointCloud, centroid,
     keep = np.zeros(len(pr), np.uint8)
     _check(lib().rsgpu_nms(obj_lvl3.h, obj_lvl1.h, _ptr(c), _ptr(pr), len(pr), dist_threshold, _ptr(keep)))
     return keep.astype(bool)
+
+
+# ------------------------------------------------------------------------------------------------ level building
+LEVEL_VOXEL = (0.005, 0.01, 0.02, 0.04, 0.08)  # rs_pointcloud_init (reference lib/rs/rs_pointcloud.h:145)
+
+
+def level_max_n_neigh(level):
+    """the k of the reference's sampling search: (size_t)(1024 * (level / 4.0f)), 256 when 0 (rs_pointcloud.h:994-995)"""
+    k = int(np.float32(1024.0) * (np.float32(level) / np.float32(4.0)))
+    return k if k else 256
+
+
+def poisson_level(pos0, level, voxel=None, max_n_neigh=None, return_rounds=False):
+    """rs_pointcloud__compute_level_poisson's sample selection -> ascending level-0 indices of the level's points"""
+    p = _f32(pos0).reshape(-1, 3)
+    voxel = np.float32(LEVEL_VOXEL[level] if voxel is None else voxel)
+    k = level_max_n_neigh(level) if max_n_neigh is None else int(max_n_neigh)
+    out = np.zeros(len(p), np.int32)
+    n, rounds = C.c_int32(0), C.c_int32(0)
+    _check(lib().rsgpu_poisson_level(_ptr(p), len(p), voxel, k, _ptr(out), C.byref(n), C.byref(rounds)))
+    idx = out[: n.value].copy()
+    return (idx, rounds.value) if return_rounds else idx
+
+
+def compute_levels(pos0, nor0):
+    """rs_pointcloud_compute_levels (rs_pointcloud.h:1305-1316) without the per-level grids: levels 1-4 are the rows of
+    level 0 picked by poisson_level -> list of five (pos, nor) pairs"""
+    p, n = _f32(pos0).reshape(-1, 3), _f32(nor0).reshape(-1, 3)
+    levels = [(p, n)]
+    for lvl in range(1, 5):
+        idx = poisson_level(p, lvl)
+        levels.append((np.ascontiguousarray(p[idx]), np.ascontiguousarray(n[idx])))
+    return levels

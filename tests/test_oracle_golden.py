@@ -152,3 +152,14 @@ def test_overlap_and_nms_match_golden():
         assert (gotb == g[f"nms{i}_overlap_boundary"]).all()
         keep = O.nms(o.pos(3), o.pos(1), c, props, 0.2)
         assert (props[keep] == g[f"nms{i}_kept"]).all() and len(g[f"nms{i}_kept"]) == keep.sum()
+
+
+def test_poisson_levels_match_golden():
+    """rs_pointcloud__compute_level_poisson (rs_pointcloud.h:984-1037): the oracle's sample indices of levels 1-4 against
+    the reference's (tests/golden/levels_golden.npz, written by make_golden_levels.py from oracle/_ref)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(common.GOLDEN), "levels_golden.npz"))
+    for name in ("a", "b"):
+        pos = g[f"{name}_pos0"]
+        for lvl in range(1, 5):
+            assert (O.poisson_level(pos, lvl) == g[f"{name}_idx{lvl}"]).all(), (name, lvl)

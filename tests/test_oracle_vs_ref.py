@@ -119,3 +119,24 @@ def test_overlap_factor_and_nms(S):
         assert len(kept_ref) == keep.sum() and (kept_ref == props[keep]).all()
         assert 0 < keep.sum() < len(props)
     assert n_pos > n_pairs // 3
+
+
+def _match_rows(pos0, rows):
+    key = {p.tobytes(): i for i, p in enumerate(pos0)}
+    return np.array([key[p.tobytes()] for p in rows], np.int32)
+
+
+def test_poisson_levels_against_reference():
+    """level building: rs_pointcloud_compute_levels of the compiled reference against the oracle's restatement, on a scan,
+    and on a patch dense enough that the reference's max_n_neigh cap binds at level 4 (a ball of 8 cm holds > 1024 points)"""
+    scene = common.tiny_scene()
+    rng = np.random.default_rng(8)
+    u, v = np.meshgrid(np.arange(0, 0.32, 0.0035), np.arange(0, 0.32, 0.0035), indexing="ij")
+    dense = np.stack([u.reshape(-1), np.zeros(u.size), v.reshape(-1)], axis=1) + rng.normal(0, 0.0004, (u.size, 3))
+    for pos0 in (scene.scan.pos(0), dense.astype(np.float32)):
+        pos0 = np.ascontiguousarray(pos0, np.float32)
+        nor0 = np.tile(np.array([0, 1, 0], np.float32), (len(pos0), 1))
+        rc = R.RefCloud.from_level0(pos0, nor0)
+        for lvl in range(1, 5):
+            want = _match_rows(pos0, rc.level(lvl)[0])
+            assert (O.poisson_level(pos0, lvl) == want).all(), lvl

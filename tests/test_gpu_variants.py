@@ -21,7 +21,7 @@ def scene():
 @pytest.fixture(autouse=True)
 def _restore_options():
     yield
-    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb"):
+    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps"):
         api.set_option(name, None)
 
 
@@ -77,7 +77,7 @@ def test_scoring_variants_bit_identical(scene):
     base_scores = api.score_pose_grid(c4, grid, rots, trans)
     base_props = _propose_all(scene, grid, rots, trans)
     assert sum(len(pr) for pr, _ in base_props) > 0
-    for opts in ({"score_impl": "coop"}, {"prune": "0"}, {"score_g": "8"}, {"score_minb": "4"}, {"search": "lane"}):
+    for opts in ({"score_impl": "coop"}, {"prune": "0"}, {"score_g": "8"}, {"score_minb": "4", "score_warps": "4"}, {"score_warps": "4"}, {"score_warps": "2"}, {"score_warps": "1", "score_minb": "16"}, {"search": "lane"}):
         for k, v in opts.items():
             api.set_option(k, v)
         s = api.score_pose_grid(c4, grid, rots, trans)

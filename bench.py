@@ -31,14 +31,14 @@ UNIT = "pose evaluations/s"
 L2_FLUSH_BYTES = 256 << 20
 
 
-def workload_config(name, world, nms=True):
+def workload_config(name, world, nms=True, exchange="host"):
     from rescan_b200 import synth
     cfg = synth.CONFIGS[name]
     sc = cfg["scene"]
     return {"workload": f"{name}: pose_proposal on one synthetic scene pair", "scan_points_target": sc.get("target_points"),
             "objects": sc["n_objects"], "static_objects": sc["n_static"], "rotations": cfg["n_rot"],
             "translation_seeds_per_gpu": cfg["n_seeds"], "translation_seeds_total": cfg["n_seeds"] * world,
-            "top_k": 64, "parallelism": f"pose-sharded x{world}",
+            "top_k": 64, "parallelism": f"pose-sharded x{world}", "exchange": exchange if world > 1 else None,
             "stages": "grid build, dense search lvl 4, verification lvl 3/2, top-k" + (", NMS" if nms else "") + ", ICP, rescoring lvl 1"
                       + (", NMS" if nms else "") + ", sort",
             "l2": "flushed between steps (256 MiB write inside the timed region); working set is L2-resident within a step"}
@@ -184,6 +184,9 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=None, help="objects in flight at once (default RSGPU_LANES or 8); 1 = serial object loop")
+    ap.add_argument("--exchange", default="host", choices=["host", "nccl"],
+                    help="N > 1: transport of the two per-step list exchanges (host = gloo all-gather of the host-resident lists; "
+                         "nccl = staged through HBM, NCCL all-gather)")
     ap.add_argument("--nms", type=int, default=1, help="1: the two NMS passes of main.cpp:161/205 run on the GPU inside the step; 0: top-k only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -203,9 +206,18 @@ def main():
     torch.cuda.set_device(local_rank)
     api.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+        if args.exchange == "host":
+            # the per-object top-k lists are host-resident and a few KB: exchanged over a gloo group next to the NCCL one
+            try:
+                os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+                host_group = dist.new_group(backend="gloo")
+            except Exception as e:  # no usable host transport: NCCL carries the lists (staged through HBM)
+                print(f"bench.py: gloo group unavailable ({e}); exchanging over NCCL", file=sys.stderr)
+                host_group = None
 
     scene, rotations, translations = build_workload(args.workload, world)
     models = pipeline.upload_objects(scene.objects)
@@ -222,7 +234,7 @@ def main():
         flush.zero_()
         return pipeline.run_step((hp["p1"], hp["n1"]), (hp["p2"], hp["n2"]), models, rotations, translations, top_k=64, rank=rank,
                                  world=world, dist=dist if world > 1 else None, device=device, scan_dev=scan_dev if resident else None,
-                                 nms_dist=0.2 if args.nms else None, lanes=args.lanes if lanes is None else lanes)
+                                 nms_dist=0.2 if args.nms else None, lanes=args.lanes if lanes is None else lanes, host_group=host_group)
 
     def barrier():
         if world > 1:
@@ -289,7 +301,8 @@ def main():
         achieved = steps_dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
         line = {"metric": METRIC, "value": evals / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world, bool(args.nms)),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world, bool(args.nms),
+                                                                          "host (gloo)" if host_group is not None else "nccl"),
                 "nn_queries_per_sec": queries / (ms_value * 1e-3),
                 "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

@@ -201,11 +201,15 @@ class PointCloud:
         return len(self.pos)
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().rsgpu_cloud_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:  # at interpreter shutdown the module globals may already be gone
+            _lib.rsgpu_cloud_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HashGrid:

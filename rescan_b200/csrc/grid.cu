@@ -213,7 +213,7 @@ int build_from_device( const float* d_pts, int32_t n, float radius, rsgpu_grid_t
   }
   uint32_t hb[8];
   RS_CUDA( cudaMemcpyAsync( hb, d_box.p, sizeof( hb ), cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   float mn[3], mx[3], ext[3];
   for( int a = 0; a < 3; ++a )
   {
@@ -289,11 +289,11 @@ int build_from_device( const float* d_pts, int32_t n, float radius, rsgpu_grid_t
     RS_CUDA( g->occ27.alloc( n_cells ) );
     occ27_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->cell_start.p, (int)dim[0], (int)dim[1], (int)dim[2], g->occ27.p );
     RS_CHECK_LAUNCH();
-    RS_CUDA( cudaStreamSynchronize( st ) ); // temporaries die here
+    RS_CUDA( rs::stream_sync( st ) ); // temporaries die here
   }
   uint32_t hs[2] = { 0, 0 };
   RS_CUDA( cudaMemcpyAsync( hs, stats.p, 8, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   g->info.n_bins = hs[0]; g->info.max_n_pts_in_bin = hs[1];
   guard.g = nullptr;
   *out = g;
@@ -318,7 +318,7 @@ int rsgpu_grid_create( const float* pts, int32_t n, float radius, rsgpu_grid_t**
   RS_CUDA( d.alloc( (size_t)( n > 0 ? n : 0 ) * 3 ) );
   if( n > 0 ) { RS_CUDA( cudaMemcpyAsync( d.p, pts, sizeof( float ) * 3 * (size_t)n, cudaMemcpyHostToDevice, rt().stream ) ); }
   int s = build_from_device( d.p, n, radius, out );
-  cudaStreamSynchronize( rt().stream );
+  rs::stream_sync( rt().stream );
   return s;
 }
 
@@ -353,7 +353,7 @@ int rsgpu_grid_set_normals_dev( rsgpu_grid_t* g, const float* d_nor )
     RS_CHECK_LAUNCH();
     uint32_t h = 0;
     RS_CUDA( cudaMemcpyAsync( &h, flag.p, 4, cudaMemcpyDeviceToHost, rt().stream ) );
-    RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+    RS_CUDA( rs::stream_sync( rt().stream ) );
     g->has_cone = h == 0; // any non-unit normal disables the culling for this grid
   }
   return RSGPU_OK;
@@ -368,7 +368,7 @@ int rsgpu_grid_set_normals( rsgpu_grid_t* g, const float* nor )
   RS_CUDA( d.alloc( n * 3 ) );
   if( n ) { RS_CUDA( cudaMemcpyAsync( d.p, nor, sizeof( float ) * 3 * n, cudaMemcpyHostToDevice, rt().stream ) ); }
   int s = rsgpu_grid_set_normals_dev( g, d.p );
-  cudaStreamSynchronize( rt().stream );
+  rs::stream_sync( rt().stream );
   return s;
 }
 
@@ -391,7 +391,7 @@ int rsgpu_grid_get_data( const rsgpu_grid_t* g, float* xyz, int32_t* idx )
   RS_CHECK_LAUNCH();
   RS_CUDA( cudaMemcpyAsync( xyz, dx.p, sizeof( float ) * 3 * (size_t)n, cudaMemcpyDeviceToHost, rt().stream ) );
   RS_CUDA( cudaMemcpyAsync( idx, di.p, sizeof( int32_t ) * (size_t)n, cudaMemcpyDeviceToHost, rt().stream ) );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   return RSGPU_OK;
 }
 

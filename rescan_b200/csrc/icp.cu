@@ -833,7 +833,7 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
           for( int p = 0; p < NPART; ++p )
           {
             if( done[p] ) { continue; }
-            if( cudaStreamSynchronize( aux[p] ) != cudaSuccess ) { status = cuda_fail( cudaGetLastError(), "icp partition", __FILE__, __LINE__ ); }
+            if( rs::stream_sync( aux[p] ) != cudaSuccess ) { status = cuda_fail( cudaGetLastError(), "icp partition", __FILE__, __LINE__ ); }
             if( running[p] == 0 ) { done[p] = 1; } else { all_done = false; }
           }
           if( all_done ) { break; }
@@ -845,7 +845,7 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
     for( int p = 0; p < NPART; ++p ) { cudaEventDestroy( join[p] ); }
     RS_TRY( status );
     RS_CUDA( cudaMemcpyAsync( hs.data(), dS.p, sizeof( IcpState ) * total, cudaMemcpyDeviceToHost, st ) );
-    RS_CUDA( cudaStreamSynchronize( st ) );
+    RS_CUDA( rs::stream_sync( st ) );
     for( size_t i = 0; i < total; ++i ) { memcpy( &hT[i * 16], hs[i].T, 64 ); herr[i] = hs[i].err; hit[i] = hs[i].steps; }
   }
   else
@@ -864,7 +864,7 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
     RS_CUDA( cudaMemcpyAsync( hT.data(), dT.p, sizeof( float ) * 16 * total, cudaMemcpyDeviceToHost, st ) );
     RS_CUDA( cudaMemcpyAsync( herr.data(), derr.p, sizeof( float ) * total, cudaMemcpyDeviceToHost, st ) );
     RS_CUDA( cudaMemcpyAsync( hit.data(), dit.p, sizeof( int ) * total, cudaMemcpyDeviceToHost, st ) );
-    RS_CUDA( cudaStreamSynchronize( st ) );
+    RS_CUDA( rs::stream_sync( st ) );
   }
   bi = 0;
   for( int j = 0; j < n_jobs; ++j )

@@ -218,7 +218,7 @@ int rsgpu_poisson_level( const float* pts, int32_t n, float voxel, int32_t max_n
   unsigned hc[8]; int32_t nsel = 0;
   RS_CUDA( cudaMemcpyAsync( hc, counters.p, sizeof( hc ), cudaMemcpyDeviceToHost, st ) );
   RS_CUDA( cudaMemcpyAsync( &nsel, d_nsel.p, sizeof( int32_t ), cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   if( hc[2] )
   {
     return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_poisson_level: a sample's ball holds more than max_n_neigh points; the reference then marks only the "
@@ -226,7 +226,7 @@ int rsgpu_poisson_level( const float* pts, int32_t n, float voxel, int32_t max_n
   }
   if( hc[4] ) { return fail( RSGPU_ERR_CUDA, "rsgpu_poisson_level: internal: undecided points left after propagation" ); }
   RS_CUDA( cudaMemcpyAsync( out_indices, d_out.p, sizeof( int32_t ) * (size_t)nsel, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   *n_out = nsel;
   if( n_rounds ) { *n_rounds = (int32_t)hc[3]; }
   return RSGPU_OK;

@@ -186,7 +186,7 @@ struct OverlapBatch
     RS_CHECK_LAUNCH();
     boxes.resize( (size_t)n * 6 );
     RS_CUDA( cudaMemcpyAsync( boxes.data(), d_boxes.p, sizeof( float ) * 6 * (size_t)n, cudaMemcpyDeviceToHost, st ) );
-    RS_CUDA( cudaStreamSynchronize( st ) );
+    RS_CUDA( rs::stream_sync( st ) );
     return RSGPU_OK;
   }
 
@@ -233,7 +233,7 @@ struct OverlapBatch
     }
     std::vector<float> h( pairs.size() );
     RS_CUDA( cudaMemcpyAsync( h.data(), d_out.p, sizeof( float ) * pairs.size(), cudaMemcpyDeviceToHost, st ) );
-    RS_CUDA( cudaStreamSynchronize( st ) );
+    RS_CUDA( rs::stream_sync( st ) );
     for( size_t p = 0; p < pairs.size(); ++p ) { out[slot[p]] = h[p]; }
     return RSGPU_OK;
   }

@@ -29,6 +29,7 @@ int ensure_device();
 std::string option( const char* key );   // value set by rsgpu_set_option, else environment RSGPU_<KEY>, else ""
 void set_option( const char* key, const char* value );
 int aux_streams( int n, cudaStream_t** out ); // helper streams (non-blocking) for internally overlapped work
+cudaError_t stream_sync( cudaStream_t s, bool long_wait = false ); // host wait; long waits sleep on a blocking event (runtime.cu)
 cudaStream_t bulk_stream();                   // where long throughput launches go: low priority inside a lane, else rt().stream
 void prof_add_pending( const char* name, cudaEvent_t a, cudaEvent_t b, bool own_a, bool own_b );
 void count_launch(); // one of OUR kernels was launched (library kernels such as CUB are not counted)

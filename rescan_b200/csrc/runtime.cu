@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cctype>
+#include <chrono>
 
 namespace rs
 {
@@ -83,6 +84,40 @@ int aux_streams( int n, cudaStream_t** out )
   }
   *out = mine;
   return RSGPU_OK;
+}
+
+// Host wait for a stream.  cudaStreamSynchronize spins on a CPU core for as long as the stream is busy; with one host
+// thread per lane and one process per GPU that is (lanes + 1) x GPUs spinning threads, and once they outnumber the
+// cores the threads that hold the next launch get descheduled (measured: 100 ms freezes of a whole rank at 2 ranks x 9
+// threads on 16 cores).  Sleeping on a blocking event instead costs a wake-up per wait, which the latency-bound chains
+// (an ICP batch syncs every four iterations) feel: + 4.5 ms per C2 step when every wait sleeps.  So a wait the caller
+// knows to be long (the dense search, milliseconds) always sleeps, and the short ones spin unless the option
+// "sync" = "block" says the host is oversubscribed (rescan_b200/pipeline.py sets it from the core count).
+cudaError_t stream_sync( cudaStream_t s, bool long_wait )
+{
+  static std::atomic<int> mode{ -1 }; // 0 spin on short waits, 1 always sleep
+  int m = mode.load( std::memory_order_relaxed );
+  const std::string o = option( "sync" );
+  const int want = o == "block" ? 1 : 0;
+  if( m != want ) { mode.store( want ); m = want; }
+  if( !long_wait && m == 0 ) { return cudaStreamSynchronize( s ); }
+  static thread_local cudaEvent_t ev = nullptr;
+  cudaError_t e;
+  if( !ev )
+  {
+    e = cudaEventCreateWithFlags( &ev, cudaEventBlockingSync | cudaEventDisableTiming );
+    if( e != cudaSuccess ) { ev = nullptr; return e; }
+  }
+  e = cudaEventRecord( ev, s );
+  if( e != cudaSuccess ) { return e; }
+  const auto t0 = std::chrono::steady_clock::now();
+  for( ;; )
+  {
+    e = cudaEventQuery( ev );
+    if( e != cudaErrorNotReady ) { return e; }
+    if( std::chrono::steady_clock::now() - t0 > std::chrono::microseconds( 50 ) ) { break; }
+  }
+  return cudaEventSynchronize( ev );
 }
 
 int fail( int code, const std::string& msg )
@@ -238,7 +273,7 @@ int rsgpu_set_stream( void* s )
 int rsgpu_synchronize( void )
 {
   RS_TRY( ensure_device() );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   return RSGPU_OK;
 }
 
@@ -283,7 +318,7 @@ int rsgpu_cloud_create( const float* pos, const float* nor, int32_t n, rsgpu_clo
   if( e == cudaSuccess ) { e = c->nor.alloc( (size_t)n * 3 ); }
   if( e == cudaSuccess && n ) { e = cudaMemcpyAsync( c->pos.p, pos, sizeof( float ) * 3 * n, cudaMemcpyHostToDevice, rt().stream ); }
   if( e == cudaSuccess && n ) { e = cudaMemcpyAsync( c->nor.p, nor, sizeof( float ) * 3 * n, cudaMemcpyHostToDevice, rt().stream ); }
-  if( e == cudaSuccess ) { e = cudaStreamSynchronize( rt().stream ); }
+  if( e == cudaSuccess ) { e = rs::stream_sync( rt().stream ); }
   if( e != cudaSuccess ) { delete c; return cuda_fail( e, "rsgpu_cloud_create", __FILE__, __LINE__ ); }
   *out = c;
   return RSGPU_OK;

@@ -362,7 +362,7 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
   }
   finalize_kernel<<<(unsigned)( ( n_poses + 255 ) / 256 ), 256, 0, st>>>( partial.p, n_poses, n_split, obj->n, ps.gate, d_scores );
   RS_CHECK_LAUNCH();
-  RS_CUDA( cudaStreamSynchronize( st ) ); // partial dies here
+  RS_CUDA( rs::stream_sync( st, grid_mode ) ); // partial dies here; the dense launch runs for milliseconds: sleep, do not spin
   return RSGPU_OK;
 }
 
@@ -502,7 +502,7 @@ int rsgpu_score_poses( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, cons
   RS_CUDA( cudaMemcpyAsync( dx.p, xforms, sizeof( float ) * 16 * (size_t)n_poses, cudaMemcpyHostToDevice, rt().stream ) );
   RS_TRY( rsgpu_score_poses_dev( obj, scene, dx.p, n_poses, k, radius, ds.p ) );
   RS_CUDA( cudaMemcpyAsync( scores, ds.p, sizeof( float ) * (size_t)n_poses, cudaMemcpyDeviceToHost, rt().stream ) );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   return RSGPU_OK;
 }
 
@@ -537,7 +537,7 @@ int rsgpu_score_pose_grid( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, 
   RS_CUDA( ds.alloc( (size_t)n ) );
   RS_TRY( rsgpu_score_pose_grid_dev( obj, scene, dr.p, n_rot, dt.p, n_trans, k, radius, ds.p ) );
   RS_CUDA( cudaMemcpyAsync( scores, ds.p, sizeof( float ) * (size_t)n, cudaMemcpyDeviceToHost, rt().stream ) );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   return RSGPU_OK;
 }
 
@@ -560,7 +560,7 @@ int rsgpu_score_pose_grid_count( const rsgpu_cloud_t* obj, const rsgpu_grid_t* s
   RS_TRY( s );
   unsigned long long h[4];
   RS_CUDA( cudaMemcpyAsync( h, dc.p, 32, cudaMemcpyDeviceToHost, rt().stream ) );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   for( int i = 0; i < 4; ++i ) { counts[i] = (int64_t)h[i]; }
   return RSGPU_OK;
 }
@@ -612,7 +612,7 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   int last_off = 0, last_flag = 0;
   RS_CUDA( cudaMemcpyAsync( &last_off, offs.p + ( n_trans - 1 ), 4, cudaMemcpyDeviceToHost, st ) );
   RS_CUDA( cudaMemcpyAsync( &last_flag, flag.p + ( n_trans - 1 ), 4, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   int n_prop = last_off + last_flag;
   if( n_prop == 0 ) { return RSGPU_OK; }
   DevBuf<float> px, psc, fresh; DevBuf<long long> pid;
@@ -649,7 +649,7 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   RS_CHECK_LAUNCH();
   int n_sel = 0;
   RS_CUDA( cudaMemcpyAsync( &n_sel, nsel.p, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   const int64_t n_copy = std::min<int64_t>( n_sel, out_cap );
   if( n_copy > 0 )
   {
@@ -659,7 +659,7 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
       static_assert( sizeof( long long ) == sizeof( int64_t ), "pose ids are 64-bit" );
       RS_CUDA( cudaMemcpyAsync( out_pose_id, dids.p, sizeof( int64_t ) * (size_t)n_copy, cudaMemcpyDeviceToHost, st ) );
     }
-    RS_CUDA( cudaStreamSynchronize( st ) );
+    RS_CUDA( rs::stream_sync( st ) );
   }
   *n_out = (int64_t)n_sel; // may exceed out_cap: the caller then knows how much room a retry needs
   return RSGPU_OK;

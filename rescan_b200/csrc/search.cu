@@ -382,7 +382,7 @@ int search_dev( bool knn, const rsgpu_grid_t* grid, const float* d_q, size_t nq,
   else if( d_nn && nq > 0 ) { RS_CUDA( cudaMemsetAsync( d_nn, 0, sizeof( unsigned long long ) * nq, rt().stream ) ); }
   unsigned long long h = 0;
   RS_CUDA( cudaMemcpyAsync( &h, d_total.p, 8, cudaMemcpyDeviceToHost, rt().stream ) );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   if( total ) { *total = (size_t)h; }
   return RSGPU_OK;
 }
@@ -411,7 +411,7 @@ int search_host( bool knn, const rsgpu_grid_t* grid, rsgpu_search_desc_t* d, siz
       static_assert( sizeof( size_t ) == sizeof( unsigned long long ), "size_t must be 64-bit" );
       RS_CUDA( cudaMemcpyAsync( d->n_neighbors, dn.p, sizeof( size_t ) * nq, cudaMemcpyDeviceToHost, st ) );
     }
-    RS_CUDA( cudaStreamSynchronize( st ) );
+    RS_CUDA( rs::stream_sync( st ) );
   }
   return RSGPU_OK;
 }
@@ -451,7 +451,7 @@ int rsgpu_grid_search_census_dev( const rsgpu_grid_t* g, const float* d_query_pt
   RS_CHECK_LAUNCH();
   unsigned long long h[2];
   RS_CUDA( cudaMemcpyAsync( h, dc.p, 16, cudaMemcpyDeviceToHost, rt().stream ) );
-  RS_CUDA( cudaStreamSynchronize( rt().stream ) );
+  RS_CUDA( rs::stream_sync( rt().stream ) );
   counts[0] = (int64_t)h[0]; counts[1] = (int64_t)h[1];
   return RSGPU_OK;
 }
@@ -479,7 +479,7 @@ int rsgpu_neighborhood( const rsgpu_grid_t* grid, const float* pos, const float*
   }
   RS_CUDA( cudaMemcpyAsync( neighbors, di.p, sizeof( int32_t ) * (size_t)n * max_nn, cudaMemcpyDeviceToHost, st ) );
   RS_CUDA( cudaMemcpyAsync( weights, dw.p, sizeof( float ) * (size_t)n * max_nn, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   return RSGPU_OK;
 }
 

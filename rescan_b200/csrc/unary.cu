@@ -152,7 +152,7 @@ int rsgpu_assign_labels( const float* scan_pos, const float* scan_nor, int32_t n
   }
   RS_CUDA( cudaMemcpyAsync( min_dists, dmin.p, sizeof( float ) * (size_t)n, cudaMemcpyDeviceToHost, st ) );
   RS_CUDA( cudaMemcpyAsync( labels, dlab.p, (size_t)n, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   return RSGPU_OK;
 }
 
@@ -178,7 +178,7 @@ int rsgpu_unary_costs( const int32_t* labels, const uint8_t* label_is_static, in
     RS_CHECK_LAUNCH();
   }
   RS_CUDA( cudaMemcpyAsync( data_cost, dc.p, sizeof( int32_t ) * total, cudaMemcpyDeviceToHost, st ) );
-  RS_CUDA( cudaStreamSynchronize( st ) );
+  RS_CUDA( rs::stream_sync( st ) );
   return RSGPU_OK;
 }
 

@@ -70,17 +70,18 @@ def merge_topk(per_rank_props, per_rank_ids, top_k):
     return props[order], ids[order]
 
 
-def _allgather_bytes(buf, dist, device):
-    """ONE all-gather of equally sized byte buffers (NCCL over NVLink on GPU, gloo on CPU) -> uint8 [world, nbytes]"""
+def _allgather_bytes(buf, dist, device, group=None):
+    """ONE all-gather of equally sized byte buffers -> uint8 [world, nbytes].  device = a CUDA device: staged through
+    HBM and moved by NCCL over NVLink; device = cpu (with a gloo `group`): the host-resident bytes never touch the GPU"""
     import torch
     world = dist.get_world_size()
     send = torch.from_numpy(np.ascontiguousarray(buf).view(np.uint8).reshape(-1)).to(device, non_blocking=True)
     recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(recv.view(-1), send)
+    dist.all_gather_into_tensor(recv.view(-1), send, group=group)
     return recv.cpu().numpy()
 
 
-def exchange_topk(props_list, ids_list, top_k, dist, device):
+def exchange_topk(props_list, ids_list, top_k, dist, device, group=None):
     """The per-object top-k exchange of the pose-sharded search as ONE collective for all objects: every rank packs
     its lists into {counts int64 [O], ids int64 [O, cap], rows float32 [O, cap, 17]}, one all-gather moves them, and the
     same deterministic merge (descending score, ties by pose id) runs on every rank.  cap = top_k, or the largest list
@@ -89,7 +90,7 @@ def exchange_topk(props_list, ids_list, top_k, dist, device):
     cap = int(top_k)
     if cap <= 0:
         mine = np.array([max([len(p) for p in props_list], default=0)], np.int64)
-        cap = max(int(_allgather_bytes(mine, dist, device).view(np.int64).max()), 1)
+        cap = max(int(_allgather_bytes(mine, dist, device, group).view(np.int64).max()), 1)
     counts = np.array([len(p) for p in props_list], np.int64)
     ids = np.zeros((n_obj, cap), np.int64)
     rows = np.zeros((n_obj, cap, api.POSE_FLOATS), np.float32)
@@ -97,7 +98,7 @@ def exchange_topk(props_list, ids_list, top_k, dist, device):
         ids[k, : len(i)] = i
         rows[k, : len(p)] = p
     buf = np.concatenate([counts.view(np.uint8), ids.reshape(-1).view(np.uint8), rows.reshape(-1).view(np.uint8)])
-    got = _allgather_bytes(buf, dist, device)
+    got = _allgather_bytes(buf, dist, device, group)
     o1, o2 = 8 * n_obj, 8 * n_obj + 8 * n_obj * cap
     out_p, out_i = [], []
     for k in range(n_obj):
@@ -112,7 +113,7 @@ def exchange_topk(props_list, ids_list, top_k, dist, device):
     return out_p, out_i
 
 
-def exchange_rows(upd_list, n_list, world, dist, device):
+def exchange_rows(upd_list, n_list, world, dist, device, group=None):
     """Second exchange: object k's list has n_list[k] entries on every rank and rank r refined entries r, r + world, ...;
     ONE all-gather of the padded [sum_k ceil(n_k / world), 17] rows returns, per object, the rows in list order."""
     caps = [-(-n // world) for n in n_list]
@@ -120,7 +121,7 @@ def exchange_rows(upd_list, n_list, world, dist, device):
     rows = np.zeros((max(int(off[-1]), 1), api.POSE_FLOATS), np.float32)
     for k, u in enumerate(upd_list):
         rows[off[k]: off[k] + len(u)] = u
-    got = _allgather_bytes(rows, dist, device).view(np.float32).reshape(world, -1, api.POSE_FLOATS)
+    got = _allgather_bytes(rows, dist, device, group).view(np.float32).reshape(world, -1, api.POSE_FLOATS)
     out = []
     for k, n in enumerate(n_list):
         full = np.zeros((n, api.POSE_FLOATS), np.float32)
@@ -167,14 +168,28 @@ def default_lanes():
     return int(os.environ.get("RSGPU_LANES", "8"))
 
 
+def configure_host_waits(lanes, local_world=None):
+    """every lane thread of every rank on this host can be waiting on its stream at the same time; when they outnumber the
+    cores, all waits sleep on blocking events instead of spinning (csrc/runtime.cu stream_sync)"""
+    import os
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1")) if local_world is None else local_world
+    oversubscribed = (lanes + 2) * local_world > (os.cpu_count() or 1)
+    api.set_option("sync", "block" if oversubscribed else None)
+    return oversubscribed
+
+
 def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, icp_max_dist=0.10,
              icp_max_angle=np.float32(np.deg2rad(60.0)), rank=0, world=1, dist=None, device=None,
-             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None, trace=False):
+             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None, trace=False, host_group=None):
     """scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
     {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead.
     nms_dist: centroid-distance threshold of the two NMS passes (the reference passes 0.2, main.cpp:161/205); None
     skips both.  previous: per dynamic object, float32 [n,16] placements of earlier arrangements, appended with
     score 10.0 and pose id -1 before the ICP (main.cpp:163-173).
+    host_group: optional gloo process group: the two exchanges then run over the host.  The lists are host-resident
+    (they come back through the C ABI) and a few KB; an NCCL kernel issued while the dense search saturates the GPU is
+    not dispatched before the pending dense blocks drain (measured 14 ms at N = 2), a host all-gather of
+    the same bytes takes 0.3 ms.  Without it the exchanges use `dist` / `device` as given (NCCL staged through HBM).
     lanes: how many objects are in flight at once (default RSGPU_LANES or 8; 1 = the reference's serial object loop).
     The objects are independent (pose_proposal.cpp:190-250, main.cpp:175-204), so every object's chain runs on its own
     lane: the latency-bound stages of one object (verification, NMS rounds, ICP iterations) fill the device next to the
@@ -213,6 +228,7 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     dyn = [m for m in models if not m.is_static]  # pose_proposal.cpp:198
     lanes = default_lanes() if lanes is None else lanes
     pool = lane_pool(lanes) if lanes > 1 and len(dyn) > 1 else None
+    configure_host_waits(lanes if pool is not None else 1)
     nms = nms_dist is not None
     big_first = sorted(range(len(dyn)), key=lambda i: -len(dyn[i].levels[2]))  # ICP cost grows with the level-2 size
 
@@ -273,20 +289,57 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         res = _run(pool, chain, list(enumerate(dyn)), big_first)
         out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
     else:
-        res = _run(pool, lambda m: search(m), [(m,) for m in dyn])
-        # the only exchange of the search: ONE all-gather of every object's top-k, identical merge on every rank
-        out_props, out_ids = exchange_topk([r[0] for r in res], [r[1] for r in res], top_k, dist, device)
-        if do_icp:
-            def middle(k, m):  # every rank suppresses the same merged list (no exchange) and refines its interleaved share
-                props, ids, cand = candidates(k, m, out_props[k], out_ids[k])
-                return props, ids, cand, refine(m, props, cand[rank::world])
-            mid = _run(pool, middle, list(enumerate(dyn)), big_first)
-            # second (and last) exchange: the refined rows of every object in one all-gather
-            updates = exchange_rows([r[3] for r in mid], [len(r[2]) for r in mid], world, dist, device)
-            res = _run(pool, finish, [(m, r[0], r[1], r[2], u) for m, r, u in zip(dyn, mid, updates)])
+        # Pose-sharded: the per-translation arg-max and the verification are rank-local, the per-object top-k lists are
+        # merged across ranks.  The objects go through in groups so that the refinement of one group overlaps the dense
+        # search of the next: every collective is issued by THIS thread in a fixed order (top-k of group 0, 1, ..., then
+        # the refined rows of group 0, 1, ...), identical on every rank whatever the timing of the lanes.
+        n_groups = min(4, max(1, len(dyn)))
+        groups = [big_first[j::n_groups] for j in range(n_groups)]  # big objects spread over the groups, in submission order
+        groups = [g for g in groups if g]
+        order = [k for g in groups for k in g]
+        out_props, out_ids = [None] * len(dyn), [None] * len(dyn)
+        if pool is not None:
+            sf = {k: pool.submit(staged, k, "search", search, dyn[k]) for k in order}
+            get_search = lambda k: sf[k].result()
         else:
-            res = _run(pool, suppress, [(m, p, i) for m, p, i in zip(dyn, out_props, out_ids)])
-        out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
+            get_search = lambda k: staged(k, "search", search, dyn[k])
+
+        def middle_(k, props, ids):
+            return staged(k, "middle", middle, k, props, ids)
+
+        def finish_(k, *a):
+            return staged(k, "finish", finish, *a)
+
+        def middle(k, props, ids):  # every rank suppresses the same merged list (no exchange) and refines its interleaved share
+            props, ids, cand = candidates(k, dyn[k], props, ids)
+            return props, ids, cand, refine(dyn[k], props, cand[rank::world])
+        mids = []
+        for g in groups:
+            res = [get_search(k) for k in g]
+            # one all-gather for the group's top-k lists, identical merge on every rank
+            gp, gi = staged(-2, "xchg_topk", exchange_topk, [r[0] for r in res], [r[1] for r in res], top_k, dist,
+                            device if host_group is None else "cpu", host_group)
+            if not do_icp:
+                mids.append([(pool.submit(suppress, dyn[k], p, i) if pool is not None else suppress(dyn[k], p, i)) for k, p, i in zip(g, gp, gi)])
+            elif pool is not None:
+                mids.append([pool.submit(middle_, k, p, i) for k, p, i in zip(g, gp, gi)])
+            else:
+                mids.append([middle_(k, p, i) for k, p, i in zip(g, gp, gi)])
+        fins = []
+        for g, mf in zip(groups, mids):
+            mid = [f.result() if pool is not None else f for f in mf]
+            if not do_icp:
+                fins.append(mid)
+                continue
+            # the refined rows of the group's objects in one all-gather
+            updates = staged(-2, "xchg_rows", exchange_rows, [r[3] for r in mid], [len(r[2]) for r in mid], world, dist,
+                             device if host_group is None else "cpu", host_group)
+            args = [(k, dyn[k], r[0], r[1], r[2], u) for k, r, u in zip(g, mid, updates)]
+            fins.append([pool.submit(finish_, *a) for a in args] if pool is not None else [finish_(*a) for a in args])
+        for g, ff in zip(groups, fins):
+            for k, f in zip(g, ff):
+                r = f.result() if (pool is not None and do_icp) else f
+                out_props[k], out_ids[k] = r[0], r[1]
     g1.close()
     if g2 is not None:
         g2.close()

@@ -110,3 +110,52 @@ def test_lanes_do_not_change_results():
             assert got.n_evaluations == ref.n_evaluations and got.n_queries == ref.n_queries
             for a, b, ia, ib in zip(got.proposals, ref.proposals, got.pose_ids, ref.pose_ids):
                 assert a.shape == b.shape and (a == b).all() and (ia == ib).all()
+
+
+def _rank_worker(rank, world, port, out_dir, lanes):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0; the exchange itself runs over gloo
+    api.set_device(0)
+    scene = common.small_scene()
+    rots, _ = common.rotation_xforms(12)
+    trans = synth.translation_seeds(scene.scan, 192, seed=3)
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    models = pipeline.upload_objects(scene.objects)
+    res = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans, top_k=16,
+                            nms_dist=0.2, rank=rank, world=world, dist=dist, device=torch.device("cpu"), lanes=lanes)
+    np.savez(os.path.join(out_dir, f"r{rank}_{lanes}.npz"), **{f"p{k}": p for k, p in enumerate(res.proposals)},
+             **{f"i{k}": i for k, i in enumerate(res.pose_ids)}, n_eval=res.n_evaluations)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_pose_sharded_step_equals_single_rank(tmp_path, lanes):
+    """two ranks (sharing the one GPU, exchanging over gloo) through the pose-sharded step: every rank ends with the
+    single-rank lists, bit for bit"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_rank_worker, args=(2, port, str(tmp_path), lanes), nprocs=2, join=True)
+    scene = common.small_scene()
+    rots, _ = common.rotation_xforms(12)
+    trans = synth.translation_seeds(scene.scan, 192, seed=3)
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    models = pipeline.upload_objects(scene.objects)
+    ref = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans, top_k=16,
+                            nms_dist=0.2, lanes=1)
+    total_eval = 0
+    for rank in range(2):
+        z = np.load(tmp_path / f"r{rank}_{lanes}.npz")
+        total_eval += int(z["n_eval"])
+        for k, (p, i) in enumerate(zip(ref.proposals, ref.pose_ids)):
+            assert z[f"p{k}"].shape == p.shape and (z[f"p{k}"] == p).all() and (z[f"i{k}"] == i).all(), (rank, k)
+    assert total_eval == ref.n_evaluations

@@ -1,6 +1,7 @@
 """C4 — temporal rescan sequence (BASELINE.json configs[3]): 5 synthetic scans of one room, 40 objects; every scan runs
-pose_proposal (dense search + verification + ICP + rescoring) and then segment_transfer's unary path (label transfer,
-data_cost, 8-NN edge weights) on the GPU.  The arrangement handed to the label transfer is the best refined proposal
+level building (the reference's Poisson-disk levels 1-4 of the new scan, on the GPU), pose_proposal (dense search +
+verification + NMS + previous placements + ICP + rescoring + NMS, apps/pose_proposal/main.cpp:159-206) and then
+segment_transfer's unary path (label transfer, data_cost, 8-NN edge weights) on the GPU.  The arrangement handed to the label transfer is the best refined proposal
 of every dynamic object plus the static objects at their known poses (the reference's arrangement optimisation is
 host code outside the path).  Prints one JSON line per scan and a summary.
 
@@ -29,6 +30,7 @@ def main():
     ap.add_argument("--room", default="12.0,2.6,9.0")
     ap.add_argument("--spacing", type=float, default=0.024)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--host-levels", action="store_true", help="keep the generator's voxel-thinned stand-in levels instead of building them on the GPU")
     args = ap.parse_args()
     api.set_device(0)
     room = tuple(float(x) for x in args.room.split(","))
@@ -38,21 +40,29 @@ def main():
     obj_grids = pipeline.upload_object_grids(scene.objects)
     is_static = [o.is_static for o in scene.objects]
     dyn_idx = [i for i, s in enumerate(is_static) if not s]
-    totals = dict(evals=0, queries=0, ms_propose=0.0, ms_unary=0.0, vertices=0)
+    totals = dict(evals=0, queries=0, ms_levels=0.0, ms_propose=0.0, ms_unary=0.0, vertices=0)
+    previous = None  # best refined placement of every dynamic object in the previous scan (main.cpp:163-173 appends those)
     for s in range(args.scans):
         if s > 0:  # the next rescan: same objects, fresh poses (30 % unmoved)
             scene = synth.make_scene(n_objects=args.objects, n_static=args.static, room=room, spacing=args.spacing,
                                      seed=synth.SEED + 40 + s, objects=scene.objects)
+        api.synchronize()
+        tl = time.perf_counter()
+        if not args.host_levels:  # rs_pointcloud_compute_levels of the new scan (rs_pointcloud.h:1305), sampling on the GPU
+            lv = api.compute_levels(scene.scan.pos(0), scene.scan.nor(0))
+            scene.scan = synth.make_cloud(scene.scan.pos(0), scene.scan.nor(0), levels=lv)
         translations = synth.translation_seeds(scene.scan, args.seeds, seed=synth.SEED + 100 + s)
         p1, n1, p2, n2 = scene.scan.pos(1), scene.scan.nor(1), scene.scan.pos(2), scene.scan.nor(2)
         api.synchronize()
         t0 = time.perf_counter()
-        res = pipeline.run_step((p1, n1), (p2, n2), models, rotations, translations, top_k=64)
+        res = pipeline.run_step((p1, n1), (p2, n2), models, rotations, translations, top_k=64, nms_dist=0.2, previous=previous)
         api.synchronize()
         t1 = time.perf_counter()
         placements, recovered = [], 0
+        previous = []
         for k, i in enumerate(dyn_idx):
             props = res.proposals[k]
+            previous.append(props[:1, :16].copy() if len(props) and props[0, 16] > 0 else np.zeros((0, 16), np.float32))
             if len(props) and props[0, 16] > 0:
                 placements.append((i, props[0, :16]))
                 best = props[0, :16].reshape(4, 4).T
@@ -66,7 +76,7 @@ def main():
         api.synchronize()
         t3 = time.perf_counter()
         line = dict(scan=s, scan_points_lvl1=len(p1), objects=args.objects, dynamic=len(dyn_idx), evaluations=res.n_evaluations,
-                    propose_ms=(t1 - t0) * 1e3, unary_ms=(t3 - t2) * 1e3, recovered_within_5cm=recovered,
+                    levels_ms=(t0 - tl) * 1e3, propose_ms=(t1 - t0) * 1e3, unary_ms=(t3 - t2) * 1e3, recovered_within_5cm=recovered,
                     labelled_vertices=int((un.labels > 0).sum()), labels=int(un.data_cost.shape[1]),
                     data_cost_bytes=int(un.data_cost.nbytes), edges=int((un.neighbors >= 0).sum()))
         if args.check:
@@ -89,6 +99,7 @@ def main():
         print(json.dumps(line), flush=True)
         totals["evals"] += res.n_evaluations
         totals["queries"] += res.n_queries
+        totals["ms_levels"] += (t0 - tl) * 1e3
         totals["ms_propose"] += (t1 - t0) * 1e3
         totals["ms_unary"] += (t3 - t2) * 1e3
         totals["vertices"] += len(p1)

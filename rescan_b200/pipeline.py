@@ -208,17 +208,27 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     p1, n1 = scan_lvl1
     p2, n2 = scan_lvl2
     t_g = time.perf_counter()
+    import threading
     if scan_dev is None:
         g1 = api.HashGrid(p1, 0.05, normals=n1)
-        g2 = api.HashGrid(p2, 0.05, normals=n2) if do_icp else None
         stats["h2d"] += p1.nbytes + n1.nbytes + (p2.nbytes + n2.nbytes if do_icp else 0)
     else:
         g1 = api.HashGrid(device_ptr=scan_dev["p1"], n_pts=len(p1), radius=0.05)
         api._check(api.lib().rsgpu_grid_set_normals_dev(g1.h, scan_dev["n1"]))
-        g2 = None
-        if do_icp:
-            g2 = api.HashGrid(device_ptr=scan_dev["p2"], n_pts=len(p2), radius=0.05)
-            api._check(api.lib().rsgpu_grid_set_normals_dev(g2.h, scan_dev["n2"]))
+    g2_box, g2_lock = [None], threading.Lock()
+
+    def scan_grid_lvl2():
+        """the level-2 grid the ICP searches: built by the first chain that needs it, on its lane, next to the dense launches
+        of the other objects (it is not needed before the first refinement)"""
+        with g2_lock:
+            if g2_box[0] is None:
+                if scan_dev is None:
+                    g2_box[0] = api.HashGrid(p2, 0.05, normals=n2)
+                else:
+                    g = api.HashGrid(device_ptr=scan_dev["p2"], n_pts=len(p2), radius=0.05)
+                    api._check(api.lib().rsgpu_grid_set_normals_dev(g.h, scan_dev["n2"]))
+                    g2_box[0] = g
+            return g2_box[0]
     if trace:
         events.append((-1, "grids", t_g - t_step, time.perf_counter() - t_step))
     n_rot = len(rotations)
@@ -266,7 +276,7 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         """ICP at level 2 + rescoring at level 1 with k = 32 of the entries `mine` (main.cpp:195-201) -> rows [len(mine), 17]"""
         if not len(mine):
             return np.zeros((0, api.POSE_FLOATS), np.float32)
-        T, err, it = api.icp_align(m.levels[2], g2, props[mine, :16], icp_max_dist, icp_max_angle)
+        T, err, it = api.icp_align(m.levels[2], scan_grid_lvl2(), props[mine, :16], icp_max_dist, icp_max_angle)
         sc = api.compute_object_alignment_scores(m.levels[1], g1, T, 32, 0.10)
         add(h2d=2 * T.nbytes, d2h=T.nbytes + err.nbytes + it.nbytes + sc.nbytes, n_eval=len(mine), n_query=len(mine) * len(m.levels[1]))
         return np.concatenate([T, sc[:, None]], axis=1).astype(np.float32)
@@ -341,8 +351,8 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
                 r = f.result() if (pool is not None and do_icp) else f
                 out_props[k], out_ids[k] = r[0], r[1]
     g1.close()
-    if g2 is not None:
-        g2.close()
+    if g2_box[0] is not None:
+        g2_box[0].close()
     if trace:
         events.append((-1, "step", 0.0, time.perf_counter() - t_step))
     return StepResult(out_props, out_ids, stats["n_eval"], stats["n_query"], stats["h2d"], stats["d2h"], sorted(events, key=lambda e: e[2]) if trace else None)

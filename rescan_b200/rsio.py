@@ -73,3 +73,16 @@ def read_proposals(path):
         out.append(body[o:o + c].copy())
         o += c
     return out
+
+
+def write_proposals(path, per_object):
+    """list (per database object, static ones included) of float32 [n, 17] -> proposal .bin as save_pose_proposals writes it
+    (reference apps/pose_proposal/main.cpp:61-89; readers: apps/segment_transfer/main.cpp:143-193, rsdb_viewer):
+    int32 n_objects, int32 count[n_objects], then per object count x {16 float32 column-major xform, float32 score}"""
+    per_object = [np.ascontiguousarray(p, "<f4").reshape(-1, 17) for p in per_object]
+    with open(path, "wb") as f:
+        f.write(np.array([len(per_object)], "<i4").tobytes())
+        f.write(np.array([len(p) for p in per_object], "<i4").tobytes())
+        for p in per_object:
+            f.write(p.tobytes())
+    return path

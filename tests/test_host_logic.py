@@ -86,3 +86,26 @@ def test_cloud_centroid_matches_oracle():
         p = (rng.standard_normal((n, 3)) * 3 + 1).astype(np.float32)
         assert (posegrid.cloud_centroid(p) == O.centroid(p)).all()
     assert (posegrid.cloud_centroid(np.zeros((0, 3), np.float32)) == 0).all()
+
+
+def test_proposal_bin_round_trip(tmp_path):
+    """the proposal wire format (apps/pose_proposal/main.cpp:61-89): re-writing the file the reference's CPU executable
+    wrote (tests/golden/dropin_pp.bin) reproduces it byte for byte"""
+    from rescan_b200 import rsio
+    src = os.path.join(ROOT, "tests", "golden", "dropin_pp.bin")
+    props = rsio.read_proposals(src)
+    out = rsio.write_proposals(str(tmp_path / "pp.bin"), props)
+    assert open(out, "rb").read() == open(src, "rb").read()
+    empty = rsio.write_proposals(str(tmp_path / "e.bin"), [np.zeros((0, 17), np.float32)] * 3)
+    assert [len(p) for p in rsio.read_proposals(empty)] == [0, 0, 0]
+
+
+def test_host_wait_policy():
+    """lane threads spin on short waits unless lanes x local ranks outnumber the cores"""
+    pytest.importorskip("ctypes")
+    if not os.path.exists(api.LIB_PATH):
+        pytest.skip("librsgpu.so not built")
+    cores = os.cpu_count() or 1
+    assert pipeline.configure_host_waits(1, local_world=1) == ((1 + 2) > cores)
+    assert pipeline.configure_host_waits(8, local_world=cores) is True
+    api.set_option("sync", None)

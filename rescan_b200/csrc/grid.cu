@@ -111,63 +111,6 @@ __global__ void relay_normals_kernel( const float* __restrict__ nor, int n, cons
   out[i] = make_float4( nor[3 * (size_t)src], nor[3 * (size_t)src + 1], nor[3 * (size_t)src + 2], 0.f );
 }
 
-// ---- octant layout (fused scoring / ICP only): the records of every cell once more, ordered by octant (the eight
-// half-size sub-cells) and by original index inside an octant, with their normals; sub_off[cell] holds the eight
-// octant END offsets relative to the cell's first record as 16-bit numbers.  The nearest-compatible search prunes by
-// octant instead of by cell: at level-1 density a cell holds ~100 points, the winner usually sits 1-3 cm away.
-// octant bit of an axis = floor(2 t) - 2 floor(t), t = (x - min) * inv_cell evaluated like the cell itself.
-__global__ void sub_key_kernel( const float4* __restrict__ recs, int n, float mnx, float mny, float mnz, double inv_cell,
-                                int W, int H, int D, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals )
-{
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if( p >= n ) { return; }
-  const float4 r = recs[p];
-  const double t[3] = { __dmul_rn( (double)__fsub_rn( r.x, mnx ), inv_cell ), __dmul_rn( (double)__fsub_rn( r.y, mny ), inv_cell ),
-                        __dmul_rn( (double)__fsub_rn( r.z, mnz ), inv_cell ) };
-  const int dim[3] = { W, H, D };
-  long long c[3]; int bit[3];
-#pragma unroll
-  for( int a = 0; a < 3; ++a )
-  {
-    c[a] = __double2ll_rz( t[a] );
-    long long h = __double2ll_rz( __dmul_rn( t[a], 2.0 ) );
-    bit[a] = (int)( h - 2 * c[a] );
-    bit[a] = bit[a] < 0 ? 0 : ( bit[a] > 1 ? 1 : bit[a] );
-    if( c[a] < 0 ) { c[a] = 0; bit[a] = 0; }                       // same clamp as cell_key_kernel (NaN / inf guard)
-    if( c[a] >= dim[a] ) { c[a] = dim[a] - 1; bit[a] = 1; }
-  }
-  keys[p] = (uint32_t)( ( ( c[2] * H + c[1] ) * W + c[0] ) * 8 + ( bit[0] | ( bit[1] << 1 ) | ( bit[2] << 2 ) ) );
-  vals[p] = (uint32_t)p;
-}
-
-// frecs / fnrm in octant order; the last record of every (cell, octant) run writes the run's end offset
-__global__ void sub_relay_kernel( const float4* __restrict__ recs, const float4* __restrict__ nrm, int n, const uint32_t* __restrict__ keys,
-                                  const uint32_t* __restrict__ vals, const uint32_t* __restrict__ cell_start, float4* __restrict__ frecs,
-                                  float4* __restrict__ fnrm, unsigned short* __restrict__ sub_end, uint32_t* __restrict__ overflow )
-{
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if( j >= n ) { return; }
-  const uint32_t src = vals[j], key = keys[j];
-  frecs[j] = recs[src]; fnrm[j] = nrm[src];
-  if( j == n - 1 || keys[j + 1] != key )
-  {
-    const uint32_t rel = (uint32_t)( j + 1 ) - cell_start[key >> 3];
-    if( rel > 65535u ) { atomicExch( overflow, 1u ); }
-    sub_end[key] = (unsigned short)rel;
-  }
-}
-
-// empty octants inherit the end of the octant before them (sub_end starts zeroed)
-__global__ void sub_fill_kernel( unsigned short* __restrict__ sub_end, size_t n_cells )
-{
-  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if( c >= n_cells ) { return; }
-  unsigned short* e = sub_end + 8 * c;
-  unsigned short run = 0;
-#pragma unroll
-  for( int s = 0; s < 8; ++s ) { run = e[s] > run ? e[s] : run; e[s] = run; }
-}
-
 // per-cell normal cone (see ConeCull in nearest.cuh): unit mean normal and the cosine of the widest angle to it,
 // shrunk by a safety margin; flags[0] is raised when some normal is not unit length to 1e-4
 __global__ void cone_kernel( const float4* __restrict__ nrm, const uint32_t* __restrict__ cell_start, size_t n_cells,
@@ -412,36 +355,6 @@ int rsgpu_grid_set_normals_dev( rsgpu_grid_t* g, const float* d_nor )
     RS_CUDA( cudaMemcpyAsync( &h, flag.p, 4, cudaMemcpyDeviceToHost, rt().stream ) );
     RS_CUDA( rs::stream_sync( rt().stream ) );
     g->has_cone = h == 0; // any non-unit normal disables the culling for this grid
-  }
-  // octant layout for the fused searches (skipped when the keys would not fit 32 bits; a cell beyond 65535 points disables it)
-  g->has_sub = false;
-  if( n > 0 && n_cells <= ( (size_t)1 << 28 ) && option( "sub" ) != "0" )
-  {
-    cudaStream_t st = rt().stream;
-    DevBuf<uint32_t> k0, k1, v0, v1, ovf;
-    RS_CUDA( k0.alloc( n ) ); RS_CUDA( k1.alloc( n ) ); RS_CUDA( v0.alloc( n ) ); RS_CUDA( v1.alloc( n ) ); RS_CUDA( ovf.alloc( 1 ) );
-    RS_CUDA( cudaMemsetAsync( ovf.p, 0, 4, st ) );
-    const int blocks = ( n + 255 ) / 256;
-    sub_key_kernel<<<blocks, 256, 0, st>>>( g->recs.p, n, g->info.min_pt[0], g->info.min_pt[1], g->info.min_pt[2], g->info.inv_cell_size,
-                                            (int)g->info.width, (int)g->info.height, (int)g->info.depth, k0.p, v0.p );
-    RS_CHECK_LAUNCH();
-    int end_bit = 4;
-    while( end_bit < 32 && ( (size_t)1 << end_bit ) < n_cells * 8 ) { ++end_bit; }
-    size_t tmp_bytes = 0;
-    RS_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, st ) );
-    DevBuf<unsigned char> tmp;
-    RS_CUDA( tmp.alloc( tmp_bytes ) );
-    RS_CUDA( cub::DeviceRadixSort::SortPairs( tmp.p, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, st ) );
-    RS_CUDA( g->frecs.alloc( n ) ); RS_CUDA( g->fnrm.alloc( n ) ); RS_CUDA( g->sub_end.alloc( n_cells * 8 ) );
-    RS_CUDA( cudaMemsetAsync( g->sub_end.p, 0, sizeof( unsigned short ) * 8 * n_cells, st ) );
-    sub_relay_kernel<<<blocks, 256, 0, st>>>( g->recs.p, g->nrm.p, n, k1.p, v1.p, g->cell_start.p, g->frecs.p, g->fnrm.p, g->sub_end.p, ovf.p );
-    RS_CHECK_LAUNCH();
-    sub_fill_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->sub_end.p, n_cells );
-    RS_CHECK_LAUNCH();
-    uint32_t h = 0;
-    RS_CUDA( cudaMemcpyAsync( &h, ovf.p, 4, cudaMemcpyDeviceToHost, st ) );
-    RS_CUDA( rs::stream_sync( st ) ); // temporaries die here
-    g->has_sub = h == 0;
   }
   return RSGPU_OK;
 }

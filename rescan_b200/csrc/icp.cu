@@ -291,15 +291,12 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
   if( fastq && warm )
   {
     const uint32_t prev = cm[i].x;
-    // a position found in the octant layout (RS_POS_FINE) seeds only a search of that layout, and vice versa
-    const bool prev_fine = ( prev & RS_POS_FINE ) != 0u, use_sub = g.sub_off != nullptr;
-    if( prev != 0xffffffffu && prev_fine == use_sub )
+    if( prev != 0xffffffffu )
     {
-      const uint32_t pidx = prev & ~RS_POS_FINE;
-      const float4 rec = __ldg( ( prev_fine ? g.frecs : g.recs ) + pidx ), mm = __ldg( ( prev_fine ? g.fnrm : g.nrm ) + pidx );
+      const float4 rec = __ldg( g.recs + prev ), mm = __ldg( g.nrm + prev );
       const float d2 = dist2_exact( rec, q.px, q.py, q.pz );
       const float dot = dot3_exact( mm.x, mm.y, mm.z, q.nx, q.ny, q.nz );
-      if( d2 < r2f && dot >= dot_thr && dot <= 1.0f ) { seedkey = ( (unsigned long long)__float_as_uint( d2 ) << 32 ) | pidx; seeddot = dot; }
+      if( d2 < r2f && dot >= dot_thr && dot <= 1.0f ) { seedkey = ( (unsigned long long)__float_as_uint( d2 ) << 32 ) | prev; seeddot = dot; }
     }
   }
   const unsigned fastm = __ballot_sync( RS_FULL, fastq );
@@ -313,9 +310,7 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
     sk = __shfl_sync( RS_FULL, seedkey, src ); sd = __shfl_sync( RS_FULL, seeddot, src );
     return true;
   };
-  // octant layout when the grid has one (launch-uniform)
-  const NearestHit hr = g.sub_off ? rsg::group_round<ICP_G, true>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, cand )
-                                  : rsg::group_round<ICP_G, false>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, cand );
+  const NearestHit hr = rsg::group_round<ICP_G>( g, __popc( fastm ), query_of, radius, r2f, dot_thr, 16, cand );
   // lane L of the round holds the result of the query with rank L
   NearestHit h;
   h.d2 = __shfl_sync( RS_FULL, hr.d2, rank ); h.dot = __shfl_sync( RS_FULL, hr.dot, rank );
@@ -331,12 +326,7 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
     float dot = h.dot > 0.0f ? h.dot : 0.0f;
     cm[i] = make_uint2( h.found ? h.pos : 0xffffffffu, __float_as_uint( dot ) );
     // the correspondent's point and normal travel with the correspondence: the sums then read four plain streams
-    if( h.found )
-    {
-      const bool fine = ( h.pos & RS_POS_FINE ) != 0u;
-      const uint32_t idx = h.pos & ~RS_POS_FINE;
-      cp[i] = __ldg( ( fine ? g.frecs : g.recs ) + idx ); cn[i] = __ldg( ( fine ? g.fnrm : g.nrm ) + idx );
-    }
+    if( h.found ) { cp[i] = __ldg( g.recs + h.pos ); cn[i] = __ldg( g.nrm + h.pos ); }
   }
   __syncwarp();
 }
@@ -738,9 +728,6 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   // RSGPU_ICP_IMPL=block selects one resident block per alignment instead of the iteration-synchronous split
   const bool split = option( "icp_impl" ) != "block";
   cudaStream_t st = rt().stream;
-  // "icp_sub" = 0: correspondences are searched in the plain cell layout even when the grid has the octant layout
-  GridView gview = scan->view();
-  if( option( "icp_sub" ) == "0" ) { gview.sub_off = nullptr; gview.frecs = nullptr; gview.fnrm = nullptr; }
   float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
   mat4_inverse_ref( T2 ? T2 : ident, T2i );
   std::vector<IcpBlock> hb( total );
@@ -829,11 +816,11 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
           // "icp_phases" = 1: time the two kinds of launches separately (rsgpu_profile_get "icp_search" / "icp_solve")
           cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
           if( phase_prof ) { cudaEventCreate( &e0 ); cudaEventCreate( &e1 ); cudaEventCreate( &e2 ); cudaEventRecord( e0, aux[p] ); }
-          icp_search_kernel<<<search_blocks, ICP_THREADS, 0, aux[p]>>>( gview, dB.p, dS.p, dids[p].p, dtask[p].p, np, TPT, dT2i.p, dot_thr, sq.p, sm.p, sp.p, sn.p );
+          icp_search_kernel<<<search_blocks, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, dtask[p].p, np, TPT, dT2i.p, dot_thr, sq.p, sm.p, sp.p, sn.p );
           count_launch();
           if( phase_prof ) { cudaEventRecord( e1, aux[p] ); }
-          if( exact ) { icp_solve_kernel<true><<<(unsigned)np, ICP_THREADS, tile_bytes, aux[p]>>>( gview, dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
-          else { icp_solve_kernel<false><<<(unsigned)np, ICP_THREADS, 0, aux[p]>>>( gview, dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
+          if( exact ) { icp_solve_kernel<true><<<(unsigned)np, ICP_THREADS, tile_bytes, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
+          else { icp_solve_kernel<false><<<(unsigned)np, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
           count_launch();
           if( phase_prof ) { cudaEventRecord( e2, aux[p] ); prof_add_pending( "icp_search", e0, e1, true, false ); prof_add_pending( "icp_solve", e1, e2, true, true ); }
         }
@@ -869,9 +856,9 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
       if( exact )
       {
         RS_CUDA( cudaFuncSetAttribute( icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
-        icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( gview, dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, sp.p, sn.p, derr.p, dit.p );
+        icp_kernel<true><<<(unsigned)total, ICP_THREADS, tile_bytes, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, sp.p, sn.p, derr.p, dit.p );
       }
-      else { icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( gview, dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, sp.p, sn.p, derr.p, dit.p ); }
+      else { icp_kernel<false><<<(unsigned)total, ICP_THREADS, 0, st>>>( scan->view(), dB.p, dT.p, dT2i.p, max_dist, dot_thr, max_iter, sq.p, sm.p, sp.p, sn.p, derr.p, dit.p ); }
       RS_CHECK_LAUNCH();
     }
     RS_CUDA( cudaMemcpyAsync( hT.data(), dT.p, sizeof( float ) * 16 * total, cudaMemcpyDeviceToHost, st ) );

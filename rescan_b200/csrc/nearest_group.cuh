@@ -126,9 +126,7 @@ __device__ __forceinline__ unsigned group_sum32( unsigned v, unsigned gmask )
 
 // All 32 lanes call this; the G lanes of a group pass the same query (qv false: the group idles).  `cand` is
 // this warp's table of GroupCfg<G>::CAND_WORDS uint4 in shared memory.  The result is replicated in the group.
-// SUB: search the octant layout (g.frecs / g.fnrm / g.sub_off, grid.cu) and prune by octant; the returned position then
-// indexes that layout and carries RS_POS_FINE.
-template <int G, bool SUB = false>
+template <int G>
 __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, float px, float py, float pz, float nx, float ny, float nz,
                                                     double radius, float r2f, float dot_thr, int k, uint4* __restrict__ cand,
                                                     unsigned long long seedkey = ~0ull, float seeddot = 0.f )
@@ -145,30 +143,17 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
   CellWindow w; w.n_cells = 0;
   if( qv ) { w = make_window( g, px, py, pz, radius ); qv = w.n_cells != 0; }
   float glx2 = 0.f, ghx2 = 0.f, gly2 = 0.f, ghy2 = 0.f, glz2 = 0.f, ghz2 = 0.f;
-  // SUB: the unsquared distances to the own cell's two walls and to its mid-planes, and the query's own octant
-  float glx = 0.f, ghx = 0.f, gly = 0.f, ghy = 0.f, glz = 0.f, ghz = 0.f, mdx = 0.f, mdy = 0.f, mdz = 0.f;
-  int qoct = 0;
   int oxc = 0, oyc = 0, ozc = 0;
   bool cap = true;
   if( qv )
   {
     float a;
-    a = (float)__dsub_rn( (double)w.qx, __dmul_rn( (double)w.c0x, g.cell ) ); glx2 = __fmul_rn( a, a ); glx = a;
-    a = (float)__dsub_rn( __dmul_rn( (double)( w.c0x + 1 ), g.cell ), (double)w.qx ); ghx2 = __fmul_rn( a, a ); ghx = a;
-    a = (float)__dsub_rn( (double)w.qy, __dmul_rn( (double)w.c0y, g.cell ) ); gly2 = __fmul_rn( a, a ); gly = a;
-    a = (float)__dsub_rn( __dmul_rn( (double)( w.c0y + 1 ), g.cell ), (double)w.qy ); ghy2 = __fmul_rn( a, a ); ghy = a;
-    a = (float)__dsub_rn( (double)w.qz, __dmul_rn( (double)w.c0z, g.cell ) ); glz2 = __fmul_rn( a, a ); glz = a;
-    a = (float)__dsub_rn( __dmul_rn( (double)( w.c0z + 1 ), g.cell ), (double)w.qz ); ghz2 = __fmul_rn( a, a ); ghz = a;
-    if( SUB )
-    {
-      // signed distance to the mid-planes; the sign gives the query's octant (a last-bit disagreement with the octant
-      // rule of grid.cu can only happen for |m| ~ 1e-9 m, where it changes a claimed gap from 0 to ~1e-9)
-      const float mx = (float)__dsub_rn( (double)w.qx, __dmul_rn( (double)w.c0x + 0.5, g.cell ) );
-      const float my = (float)__dsub_rn( (double)w.qy, __dmul_rn( (double)w.c0y + 0.5, g.cell ) );
-      const float mz = (float)__dsub_rn( (double)w.qz, __dmul_rn( (double)w.c0z + 0.5, g.cell ) );
-      qoct = ( mx >= 0.f ? 1 : 0 ) | ( my >= 0.f ? 2 : 0 ) | ( mz >= 0.f ? 4 : 0 );
-      mdx = fabsf( mx ); mdy = fabsf( my ); mdz = fabsf( mz );
-    }
+    a = (float)__dsub_rn( (double)w.qx, __dmul_rn( (double)w.c0x, g.cell ) ); glx2 = __fmul_rn( a, a );
+    a = (float)__dsub_rn( __dmul_rn( (double)( w.c0x + 1 ), g.cell ), (double)w.qx ); ghx2 = __fmul_rn( a, a );
+    a = (float)__dsub_rn( (double)w.qy, __dmul_rn( (double)w.c0y, g.cell ) ); gly2 = __fmul_rn( a, a );
+    a = (float)__dsub_rn( __dmul_rn( (double)( w.c0y + 1 ), g.cell ), (double)w.qy ); ghy2 = __fmul_rn( a, a );
+    a = (float)__dsub_rn( (double)w.qz, __dmul_rn( (double)w.c0z, g.cell ) ); glz2 = __fmul_rn( a, a );
+    a = (float)__dsub_rn( __dmul_rn( (double)( w.c0z + 1 ), g.cell ), (double)w.qz ); ghz2 = __fmul_rn( a, a );
     oxc = min( max( w.c0x - w.lox, 0 ), 2 ); oyc = min( max( w.c0y - w.loy, 0 ), 2 ); ozc = min( max( w.c0z - w.loz, 0 ), 2 );
     const bool inside = w.c0x >= 0 && w.c0x < g.W && w.c0y >= 0 && w.c0y < g.H && w.c0z >= 0 && w.c0z < g.D;
     if( inside && g.occ27 )
@@ -204,9 +189,7 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
         const uint32_t s = __ldg( g.cell_start + id ), t = __ldg( g.cell_start + id + 1 );
         if( s < t )
         {
-          // the 5 dropped mantissa bits carry the cell's offset from the query's own cell (SUB needs it for the octant gaps)
-          const uint32_t dcode = (uint32_t)( ( cx - w.c0x + 1 ) + 3 * ( cy - w.c0y + 1 ) + 9 * ( cz - w.c0z + 1 ) );
-          cand[j * 32 + lane] = make_uint4( s, t, SUB ? ( gapc | dcode ) : gapc, id );
+          cand[j * 32 + lane] = make_uint4( s, t, gapc, id );
           cmask |= 1u << e;
           if( cone_possible( g.cone, cull, (size_t)id, nx, ny, nz ) ) { smask |= 1u << e; }
         }
@@ -229,85 +212,41 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
     limkey = seedkey;
     if( sub == 0 ) { mykey = seedkey; mydot = seeddot; }
   }
-  const float4* __restrict__ recs = SUB ? g.frecs : g.recs;
-  const float4* __restrict__ nrm = SUB ? g.fnrm : g.nrm;
-  // octant o (bit 0 x, 1 y, 2 z) of the cell at offset code dcode: record range relative to the cell's first record and
-  // the squared gap between the query and the octant, rounded DOWN (conservative pruning)
-  const float half_rd = (float)__dmul_rd( g.cell, 0.5 );
-  auto octant = [&]( const uint4& so, uint32_t dcode, int o, uint32_t& r0, uint32_t& r1 ) -> uint32_t {
-    const uint32_t wlo = o < 4 ? ( o < 2 ? so.x : so.y ) : ( o < 6 ? so.z : so.w );
-    r1 = ( wlo >> ( 16 * ( o & 1 ) ) ) & 0xffffu;
-    const int om = o - 1;
-    const uint32_t wprev = om < 4 ? ( om < 2 ? so.x : so.y ) : ( om < 6 ? so.z : so.w );
-    r0 = o == 0 ? 0u : ( ( wprev >> ( 16 * ( om & 1 ) ) ) & 0xffffu );
-    const int dx = (int)( dcode % 3u ) - 1, dy = (int)( ( dcode / 3u ) % 3u ) - 1, dz = (int)( dcode / 9u ) - 1;
-    const int bx = o & 1, by = ( o >> 1 ) & 1, bz = o >> 2;
-    const float gx = dx == 0 ? ( bx == ( qoct & 1 ) ? 0.f : mdx ) : ( dx > 0 ? ( bx == 0 ? ghx : __fadd_rd( ghx, half_rd ) ) : ( bx == 1 ? glx : __fadd_rd( glx, half_rd ) ) );
-    const float gy = dy == 0 ? ( by == ( ( qoct >> 1 ) & 1 ) ? 0.f : mdy ) : ( dy > 0 ? ( by == 0 ? ghy : __fadd_rd( ghy, half_rd ) ) : ( by == 1 ? gly : __fadd_rd( gly, half_rd ) ) );
-    const float gz = dz == 0 ? ( bz == ( qoct >> 2 ) ? 0.f : mdz ) : ( dz > 0 ? ( bz == 0 ? ghz : __fadd_rd( ghz, half_rd ) ) : ( bz == 1 ? glz : __fadd_rd( glz, half_rd ) ) );
-    return __float_as_uint( __fadd_rd( __fadd_rd( __fmul_rd( gz, gz ), __fmul_rd( gy, gy ) ), __fmul_rd( gx, gx ) ) ) & 0xffffffe0u;
-  };
-  // the octant of a cell nearest to the query: the query's own octant mirrored into the neighbour
-  auto nearest_octant = [&]( uint32_t dcode ) -> int {
-    const int dx = (int)( dcode % 3u ) - 1, dy = (int)( ( dcode / 3u ) % 3u ) - 1, dz = (int)( dcode / 9u ) - 1;
-    return ( dx > 0 ? 0 : ( dx < 0 ? 1 : ( qoct & 1 ) ) ) | ( dy > 0 ? 0 : ( dy < 0 ? 2 : ( qoct & 2 ) ) ) | ( dz > 0 ? 0 : ( dz < 0 ? 4 : ( qoct & 4 ) ) );
-  };
-  // sweep of one record range for the nearest compatible point (two records per step, both loads issued before either
-  // is used; the normal test is rare once a near point is known: an out-of-line call keeps it a real branch)
-  auto sweep = [&]( uint32_t p0, uint32_t p1, unsigned long long& lk ) {
-    for( uint32_t p = p0 + sub; p < p1; p += 2 * G )
-    {
-      const bool two = p + G < p1;
-      const float4 rec0 = __ldg( recs + p );
-      const float4 rec1 = __ldg( recs + ( two ? p + G : p ) );
-      const unsigned long long key0 = ( (unsigned long long)__float_as_uint( dist2_exact( rec0, px, py, pz ) ) << 32 ) | p;
-      const unsigned long long key1 = ( (unsigned long long)__float_as_uint( dist2_exact( rec1, px, py, pz ) ) << 32 ) | ( p + G );
-      if( key0 < lk )
-      {
-        const float dot = normal_dot_call( nrm, p, nx, ny, nz );
-        if( dot >= dot_thr && dot <= 1.0f ) { lk = key0; mykey = key0; mydot = dot; }
-      }
-      if( two && key1 < lk )
-      {
-        const float dot = normal_dot_call( nrm, p + G, nx, ny, nz );
-        if( dot >= dot_thr && dot <= 1.0f ) { lk = key1; mykey = key1; mydot = dot; }
-      }
-    }
-  };
   for( unsigned m = smask; m; )
   {
     const int e = __ffs( m ) - 1; m &= m - 1;
     const uint4 c = cand[( e / G ) * 32 + gbase + ( e % G )];
-    if( ( c.z & 0xffffffe0u ) >= (uint32_t)( limkey >> 32 ) ) { continue; }
-    if( SUB )
+    if( c.z >= (uint32_t)( limkey >> 32 ) ) { continue; }
+    unsigned long long lk = limkey;
+    for( uint32_t p = c.x + sub; p < c.y; p += 2 * G )
     {
-      const uint4 so = __ldg( g.sub_off + c.w );
-      const uint32_t dcode = c.z & 31u;
-      const int base = nearest_octant( dcode );
-#pragma unroll 1
-      for( int k = 0; k < 8; ++k )
+      // two records per step, both loads issued before either is used
+      const bool two = p + G < c.y;
+      const float4 rec0 = __ldg( g.recs + p );
+      const float4 rec1 = __ldg( g.recs + ( two ? p + G : p ) );
+      const unsigned long long key0 = ( (unsigned long long)__float_as_uint( dist2_exact( rec0, px, py, pz ) ) << 32 ) | p;
+      const unsigned long long key1 = ( (unsigned long long)__float_as_uint( dist2_exact( rec1, px, py, pz ) ) << 32 ) | ( p + G );
+      // the normal test is rare once a near point is known: keep it a real branch (an out-of-line call stops the
+      // compiler from predicating its ~15 instructions into every step)
+      if( key0 < lk )
       {
-        uint32_t r0, r1;
-        const uint32_t ogap = octant( so, dcode, base ^ k, r0, r1 );
-        if( r0 == r1 || ogap >= (uint32_t)( limkey >> 32 ) ) { continue; }
-        unsigned long long lk = limkey;
-        sweep( c.x + r0, c.x + r1, lk );
-        limkey = group_min64<G>( lk, gmask );
+        const float dot = normal_dot_call( g.nrm, p, nx, ny, nz );
+        if( dot >= dot_thr && dot <= 1.0f ) { lk = key0; mykey = key0; mydot = dot; }
+      }
+      if( two && key1 < lk )
+      {
+        const float dot = normal_dot_call( g.nrm, p + G, nx, ny, nz );
+        if( dot >= dot_thr && dot <= 1.0f ) { lk = key1; mykey = key1; mydot = dot; }
       }
     }
-    else
-    {
-      unsigned long long lk = limkey;
-      sweep( c.x, c.y, lk );
-      limkey = group_min64<G>( lk, gmask );
-    }
+    limkey = group_min64<G>( lk, gmask );
   }
   const uint32_t dcb = (uint32_t)( limkey >> 32 );
   if( dcb < r2bits ) // group-uniform
   {
     const unsigned own = __ballot_sync( gmask, mykey == limkey );
     hit.dot = __shfl_sync( gmask, mydot, __ffs( own ) - 1 );
-    hit.d2 = __uint_as_float( dcb ); hit.pos = (uint32_t)limkey | ( SUB ? RS_POS_FINE : 0u );
+    hit.d2 = __uint_as_float( dcb ); hit.pos = (uint32_t)limkey;
     hit.found = true;
     if( cap )
     {
@@ -319,33 +258,13 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
       {
         const int e = __ffs( m ) - 1; m &= m - 1;
         const uint4 c = cand[( e / G ) * 32 + gbase + ( e % G )];
-        if( ( c.z & 0xffffffe0u ) >= dcb ) { continue; }
+        if( c.z >= dcb ) { continue; }
         unsigned local = 0;
-        if( SUB )
-        {
-          const uint4 so = __ldg( g.sub_off + c.w );
-          const uint32_t dcode = c.z & 31u;
-#pragma unroll 1
-          for( int o = 0; o < 8; ++o )
-          {
-            uint32_t r0, r1;
-            const uint32_t ogap = octant( so, dcode, o, r0, r1 );
-            if( r0 == r1 || ogap >= dcb ) { continue; }
-            for( uint32_t p = c.x + r0 + sub; p < c.x + r1; p += G )
-            {
-              const float4 rec = __ldg( recs + p );
-              local += dist2_exact( rec, px, py, pz ) < dcf;
-            }
-          }
-        }
-        else
-        {
 #pragma unroll 4
-          for( uint32_t p = c.x + sub; p < c.y; p += G )
-          {
-            const float4 rec = __ldg( recs + p );
-            local += dist2_exact( rec, px, py, pz ) < dcf;
-          }
+        for( uint32_t p = c.x + sub; p < c.y; p += G )
+        {
+          const float4 rec = __ldg( g.recs + p );
+          local += dist2_exact( rec, px, py, pz ) < dcf;
         }
         cnt += group_sum32<G>( local, gmask );
       }
@@ -360,7 +279,7 @@ __device__ __forceinline__ NearestHit group_search( const GridView& g, bool qv, 
 // callable by all lanes with any r in [0, n_round) and give the r-th query of the round (the lanes of one group
 // ask for the same r); it returns false for a query the group path must not take (left unfound here).  On return
 // lane L holds the result of query L of the round.
-template <int G, bool SUB = false, class QueryOf>
+template <int G, class QueryOf>
 __device__ __forceinline__ NearestHit group_round( const GridView& g, int n_round, QueryOf query_of, double radius, float r2f, float dot_thr,
                                                    int k, uint4* __restrict__ cand )
 {
@@ -373,7 +292,7 @@ __device__ __forceinline__ NearestHit group_round( const GridView& g, int n_roun
     float px, py, pz, nx, ny, nz, seeddot = 0.f;
     unsigned long long seedkey = ~0ull;
     const bool ok = query_of( r < n_round ? r : n_round - 1, px, py, pz, nx, ny, nz, seedkey, seeddot );
-    const NearestHit h = group_search<G, SUB>( g, ok && r < n_round, px, py, pz, nx, ny, nz, radius, r2f, dot_thr, k, cand, seedkey, seeddot );
+    const NearestHit h = group_search<G>( g, ok && r < n_round, px, py, pz, nx, ny, nz, radius, r2f, dot_thr, k, cand, seedkey, seeddot );
     // query L of the round was served in step L / NG by group L % NG
     const int src = ( lane % NG ) * G;
     const float d2 = __shfl_sync( RS_FULL, h.d2, src ), dot = __shfl_sync( RS_FULL, h.dot, src );

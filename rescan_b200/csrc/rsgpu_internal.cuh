@@ -12,7 +12,6 @@
 
 #define RS_FULL 0xffffffffu
 #define RS_INF_BITS 0x7f800000u
-#define RS_POS_FINE 0x80000000u /* a search position that indexes the octant layout (GridView::frecs) instead of recs */
 
 // ---------------------------------------------------------------------------------------------- host runtime
 namespace rs
@@ -93,9 +92,6 @@ struct GridView
   const uint32_t* __restrict__ occ27; // points in the 3x3x3 block of cells centred on each cell (0 = a query there sees nothing)
   const float4* __restrict__ cone;    // per cell {unit mean normal, cos(max angle to it)}; nullptr when normals are not unit
   const float4* __restrict__ ncone;   // the same for all normals in the 3x3x3 block around each cell
-  const float4* __restrict__ frecs;   // octant layout (grid.cu): records of a cell ordered by octant, then original index; nullptr = absent
-  const float4* __restrict__ fnrm;    // normals in the same order
-  const uint4* __restrict__ sub_off;  // per cell: eight 16-bit octant end offsets relative to cell_start
   float mnx, mny, mnz;
   int W, H, D;
   double cell, inv_cell;
@@ -110,9 +106,6 @@ struct rsgpu_grid
   rs::DevBuf<uint32_t> occ27;
   rs::DevBuf<float4> cone;
   rs::DevBuf<float4> ncone;
-  rs::DevBuf<float4> frecs, fnrm;
-  rs::DevBuf<unsigned short> sub_end;
-  bool has_sub = false;
   bool has_cone = false;
   bool has_normals = false;
   rsgpu_grid_info_t info;
@@ -120,8 +113,6 @@ struct rsgpu_grid
   {
     GridView v;
     v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p; v.occ27 = occ27.p; v.cone = ( has_normals && has_cone ) ? cone.p : nullptr; v.ncone = v.cone ? ncone.p : nullptr;
-    const bool sub = has_normals && has_sub;
-    v.frecs = sub ? frecs.p : nullptr; v.fnrm = sub ? fnrm.p : nullptr; v.sub_off = sub ? (const uint4*)sub_end.p : nullptr;
     v.mnx = info.min_pt[0]; v.mny = info.min_pt[1]; v.mnz = info.min_pt[2];
     v.W = (int)info.width; v.H = (int)info.height; v.D = (int)info.depth;
     v.cell = info.cell_size; v.inv_cell = info.inv_cell_size; v.n_pts = (int)info.n_pts;

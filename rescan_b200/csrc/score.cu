@@ -116,9 +116,9 @@ __global__ void __launch_bounds__( 128 ) score_kernel( GridView g, const float* 
 constexpr int SC_LIST_CAP = 1024;
 
 // SC_WARPS warps (poses) per block.  The poses of a block differ a lot in work (free space vs on a surface), but block
-// size turned out not to matter: 4, 2 and 1 warps per block ran the C2 dense launches in 28.8 / 28.5 / 28.6 ms per step
-// (profiles/score_kernel_r01.md), so only 4 is instantiated
-template <bool GRID, int SC_G, int MINB, bool LANE, int SC_WARPS, bool SUB>
+// size turned out not to matter: 4, 2 and 1 warps per block run the C2 dense launches in 28.8 / 28.5 / 28.6 ms per step
+// (knob "score_warps", tests/test_gpu_variants.py)
+template <bool GRID, int SC_G, int MINB, bool LANE, int SC_WARPS>
 __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridView g, const float* __restrict__ obj_pos, const float* __restrict__ obj_nor,
                                                                    int n_obj, PoseSource ps, long long n_poses, int n_split, int chunk,
                                                                    ScoreParams sp, double prune_cnt, double* __restrict__ partial )
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
       const bool qv = lane < n_round && query_of( lane, px, py, pz, nx, ny, nz, sk, sd );
       h = rsg::lane_search( g, qv, px, py, pz, nx, ny, nz, sp.radius, sp.r2f, sp.dot_thr, sp.k );
     }
-    else { h = rsg::group_round<SC_G, SUB>( g, n_round, query_of, sp.radius, sp.r2f, sp.dot_thr, sp.k, cand ); }
+    else { h = rsg::group_round<SC_G>( g, n_round, query_of, sp.radius, sp.r2f, sp.dot_thr, sp.k, cand ); }
     // windows the group path cannot take (last-bit cases, radius > cell size): generic warp-cooperative search
     const bool slow = lane < n_round && ( list[base + lane] & 0x8000 ) != 0;
     if( __any_sync( RS_FULL, slow ) )
@@ -316,24 +316,27 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
     ProfScope prof( grid_mode ? "score_dense" : "score", st );
     if( group_impl )
     {
-      // lanes per query and resident blocks per SM (register cap) of the group kernel; the defaults are the measured best.
-      // "score_sub" = 0 searches the plain cell layout instead of the octant layout (grid.cu).
-      const std::string og = option( "score_g" ), ob = option( "score_minb" );
-      const int cfg_g = og.empty() ? 4 : atoi( og.c_str() ), cfg_b = ob.empty() ? 6 : atoi( ob.c_str() );
+      // lanes per query, warps per block and resident blocks per SM (register cap) of the group kernel; the defaults
+      // are the measured best
+      const std::string og = option( "score_g" ), ob = option( "score_minb" ), ow = option( "score_warps" );
+      const int cfg_g = og.empty() ? 4 : atoi( og.c_str() ), cfg_w = ow.empty() ? 4 : atoi( ow.c_str() );
+      const int cfg_b = ob.empty() ? ( cfg_w == 1 ? 24 : ( cfg_w == 2 ? 12 : 6 ) ) : atoi( ob.c_str() );
       const bool lane_env = option( "search" ) == "lane";
-      const bool use_sub = g.sub_off != nullptr && option( "score_sub" ) != "0";
-#define RS_SCORE_G_LAUNCH( GRIDM, GG, MB, LN, SB ) \
-      score_kernel_g<GRIDM, GG, MB, LN, 4, SB><<<(unsigned)blocks, 32 * 4, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p )
-#define RS_SCORE_G_PICK2( GRIDM, SB ) \
+      blocks = ( warps + cfg_w - 1 ) / cfg_w;
+      if( cfg_w != 1 && cfg_w != 2 ) { blocks = ( warps + 3 ) / 4; }
+      if( blocks > 2147483647ll ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu score: too many poses for one launch" ); }
+#define RS_SCORE_G_LAUNCH( GRIDM, GG, MB, LN, WW ) \
+      score_kernel_g<GRIDM, GG, MB, LN, WW><<<(unsigned)blocks, 32 * WW, 0, st>>>( g, obj->pos.p, obj->nor.p, obj->n, ps, n_poses, n_split, chunk, sp, prune_cnt, partial.p )
+#define RS_SCORE_G_PICK( GRIDM ) \
       do { \
-        if( lane_env ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6, true, false ); } \
-        else if( cfg_g == 8 ) { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 8, false, SB ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 6, false, SB ); } else { RS_SCORE_G_LAUNCH( GRIDM, 8, 4, false, SB ); } } \
-        else { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 8, false, SB ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6, false, SB ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 4, false, SB ); } } \
+        if( lane_env ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6, true, 4 ); } \
+        else if( cfg_w == 1 ) { if( cfg_g == 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 24, false, 1 ); } else if( cfg_b >= 24 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 24, false, 1 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 16, false, 1 ); } } \
+        else if( cfg_w == 2 ) { if( cfg_g == 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 12, false, 2 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 12, false, 2 ); } } \
+        else if( cfg_g == 8 ) { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 8, false, 4 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 8, 6, false, 4 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 8, 4, false, 4 ); } } \
+        else { if( cfg_b >= 8 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 8, false, 4 ); } else if( cfg_b >= 6 ) { RS_SCORE_G_LAUNCH( GRIDM, 4, 6, false, 4 ); } else { RS_SCORE_G_LAUNCH( GRIDM, 4, 4, false, 4 ); } } \
       } while( 0 )
-#define RS_SCORE_G_PICK( GRIDM ) do { if( use_sub ) { RS_SCORE_G_PICK2( GRIDM, true ); } else { RS_SCORE_G_PICK2( GRIDM, false ); } } while( 0 )
       if( grid_mode ) { RS_SCORE_G_PICK( true ); } else { RS_SCORE_G_PICK( false ); }
 #undef RS_SCORE_G_PICK
-#undef RS_SCORE_G_PICK2
 #undef RS_SCORE_G_LAUNCH
     }
     else if( d_counts )

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -115,6 +116,14 @@ __global__ void __launch_bounds__( 128 ) score_kernel( GridView g, const float* 
 // as 0, which never wins the per-translation arg-max and never passes the threshold: pose_proposal.cpp:217-243).
 constexpr int SC_LIST_CAP = 1024;
 
+// -DRS_SCORE_STATS: work census of the group kernel (diagnostic builds only; printed by rsgpu_propose_poses)
+#ifdef RS_SCORE_STATS
+__device__ unsigned long long g_score_stats[12];
+#define RS_STAT( i, v ) do { if( lane == 0 ) { atomicAdd( &g_score_stats[i], (unsigned long long)( v ) ); } } while( 0 )
+#else
+#define RS_STAT( i, v ) do { } while( 0 )
+#endif
+
 // SC_WARPS warps (poses) per block.  The poses of a block differ a lot in work (free space vs on a surface), but block
 // size turned out not to matter: 4, 2 and 1 warps per block run the C2 dense launches in 28.8 / 28.5 / 28.6 ms per step
 // (knob "score_warps", tests/test_gpu_variants.py)
@@ -171,10 +180,11 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
   double sum = 0.0;
   bool pruned = prune_cnt >= 0.0 && (double)n_list < prune_cnt;
   int n_found = 0;
+  RS_STAT( 0, 1 ); RS_STAT( 1, i1 - i0 ); RS_STAT( 2, n_list ); RS_STAT( 3, pruned ? 1 : 0 ); RS_STAT( 4, pruned ? 0 : n_list );
   for( int base = 0; base < n_list && !pruned; base += 32 )
   {
-    // every remaining listed point contributes at most 1
-    if( prune_cnt >= 0.0 && (double)( n_found + ( n_list - base ) ) < prune_cnt ) { pruned = true; break; }
+    // the terms found so far are known, every remaining listed point contributes at most 1
+    if( prune_cnt >= 0.0 && sum + (double)( n_list - base ) < prune_cnt ) { pruned = true; RS_STAT( 5, 1 ); RS_STAT( 6, n_list - base ); break; }
     const int n_round = min( 32, n_list - base );
     // ---- pass B: the searches of this round (:115-148)
     auto query_of = [&]( int r, float& px, float& py, float& pz, float& nx, float& ny, float& nz, unsigned long long& seedkey, float& seeddot ) -> bool {
@@ -214,6 +224,7 @@ __global__ void __launch_bounds__( 32 * SC_WARPS, MINB ) score_kernel_g( GridVie
     }
     unsigned mask = __ballot_sync( RS_FULL, h.found );
     n_found += __popc( mask );
+    RS_STAT( 7, n_round ); RS_STAT( 8, __popc( mask ) );
     while( mask )
     {
       int src = __ffs( mask ) - 1; mask &= mask - 1;
@@ -662,6 +673,14 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
     RS_CUDA( rs::stream_sync( st ) );
   }
   *n_out = (int64_t)n_sel; // may exceed out_cap: the caller then knows how much room a retry needs
+#ifdef RS_SCORE_STATS
+  {
+    unsigned long long h[12];
+    cudaMemcpyFromSymbol( h, g_score_stats, sizeof( h ) );
+    fprintf( stderr, "score stats (cumulative): warps %llu points %llu stage1_survivors %llu pruned_after_A %llu listed_in_unpruned %llu pruned_midway %llu "
+                     "skipped_by_midway %llu searched %llu found %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8] );
+  }
+#endif
   return RSGPU_OK;
 }
 

@@ -307,7 +307,7 @@ def main():
                 "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_all),
-                "roofline": {"bound": "hbm", "kernel": "score_kernel<GRID> (dense level-4 pose scoring)", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "score_kernel_g<GRID> (dense level-4 pose scoring)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dense_bytes / max(len(census), 1),
                              "launches_timed": dense_launches, "timed_in": "a separate pass of the same steps with one object in flight (lanes=1)", "avg_launch_ms": dense_ms / max(dense_launches, 1),

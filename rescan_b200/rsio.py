@@ -86,3 +86,80 @@ def write_proposals(path, per_object):
         for p in per_object:
             f.write(p.tobytes())
     return path
+
+
+_PLY_TYPES = {"char": "i1", "uchar": "u1", "int8": "i1", "uint8": "u1", "short": "i2", "ushort": "u2", "int16": "i2", "uint16": "u2",
+              "int": "i4", "uint": "u4", "int32": "i4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+
+def read_ply(path):
+    """vertex element of a PLY (binary little-endian or ASCII, the two the reference reads and writes:
+    lib/rs/rs_pointcloud.h:598-836) -> structured array with the file's own property names.  Faces are ignored (a scan with
+    faces is area-resampled by the reference, :1268-1281; the fixtures are face-less)."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt, n_vertex, props, in_vertex = None, 0, [], False
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: header without end_header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] == "comment":
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                in_vertex = tok[1] == "vertex"
+                if in_vertex:
+                    n_vertex = int(tok[2])
+            elif tok[0] == "property" and in_vertex:
+                if tok[1] == "list":
+                    raise ValueError(f"{path}: list property on the vertex element")
+                props.append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        if fmt == "binary_little_endian":
+            dt = np.dtype([(n, "<" + t) for n, t in props])
+            return np.frombuffer(f.read(dt.itemsize * n_vertex), dt, n_vertex).copy()
+        if fmt == "ascii":
+            dt = np.dtype([(n, t) for n, t in props])
+            out = np.zeros(n_vertex, dt)
+            for i in range(n_vertex):
+                vals = f.readline().split()
+                for (n, _), v in zip(props, vals):
+                    out[n][i] = float(v)
+            return out
+        raise ValueError(f"{path}: unsupported PLY format {fmt}")
+
+
+def read_database(path):
+    """`.rsdb` text database (parser of the reference: lib/rs/rs_database.h:291-441) -> dict with model_folder, classes
+    [(name, idx)], scenes [(uidx, arrangement_idx, scan ply, proposals .bin or None)], objects [(file, uidx, class_idx,
+    is_shape_prior)], n_arrangements and poses [(placement uidx, arrangement_idx, object_idx, score, 4x4 float32)].
+    The 16 numbers of a pose line are row-major (:601-606); the returned matrix is the mathematical 4x4."""
+    db = dict(version=None, model_folder=None, classes=[], scenes=[], objects=[], n_arrangements=0, poses=[])
+    with open(path) as f:
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            cmd = tok[0]
+            if cmd == "rsdb":
+                db["version"] = tok[1]
+            elif cmd == "model_folder":
+                db["model_folder"] = tok[1]
+            elif cmd == "class":
+                db["classes"].append((tok[1], int(tok[2])))
+            elif cmd == "scene":
+                db["scenes"].append((int(tok[1]), int(tok[2]), tok[3], None if len(tok) < 5 or tok[4] == "none" else tok[4]))
+            elif cmd in ("object", "shape_prior"):
+                db["objects"].append((tok[1], int(tok[2]), int(tok[3]), cmd == "shape_prior"))
+            elif cmd == "n_arrangements":
+                db["n_arrangements"] = int(tok[1])
+            elif cmd == "pose":
+                m = np.array([float(x) for x in tok[5:21]], np.float32).reshape(4, 4)
+                db["poses"].append((int(tok[1]), int(tok[2]), int(tok[3]), float(tok[4]), m))
+    if db["version"] is None:
+        raise ValueError(f"{path}: no 'rsdb <version>' line")
+    return db

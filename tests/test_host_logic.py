@@ -109,3 +109,34 @@ def test_host_wait_policy():
     assert pipeline.configure_host_waits(1, local_world=1) == ((1 + 2) > cores)
     assert pipeline.configure_host_waits(8, local_world=cores) is True
     api.set_option("sync", None)
+
+
+def test_readers_on_reference_written_files(tmp_path):
+    """.rsdb and PLY as the reference's own CPU executable wrote them (tests/golden/dropin_pp.rsdb, dropin_obj_102.ply, from
+    integration/make_dropin_case.py --golden) are read back; our writers' files round-trip through the same readers"""
+    from rescan_b200 import rsio
+    gold = os.path.join(ROOT, "tests", "golden")
+    db = rsio.read_database(os.path.join(gold, "dropin_pp.rsdb"))
+    assert db["version"] == "1.0" and len(db["classes"]) == len(synth.CLASS_NAMES)
+    assert [c[0] for c in db["classes"]] == list(synth.CLASS_NAMES)
+    assert [o[1] for o in db["objects"]] == [100, 101, 102] and db["n_arrangements"] == 1
+    assert len(db["scenes"]) == 2 and db["scenes"][0][3] is None and db["scenes"][1][3].endswith("scan1_pp.bin")
+    assert len(db["poses"]) == 3
+    for _, arr, obj, score, m in db["poses"]:
+        assert arr == 0 and score == 1.0 and (m[3] == [0, 0, 0, 1]).all()
+        assert np.allclose(m[:3, :3] @ m[:3, :3].T, np.eye(3), atol=1e-5) and m[1, 3] == 0.0  # yaw + translation on the floor
+    v = rsio.read_ply(os.path.join(gold, "dropin_obj_102.ply"))
+    assert len(v) == 3069 and set(v.dtype.names) >= {"x", "y", "z", "nx", "ny", "nz", "radius", "class_idx", "instance_idx"}
+    nn = np.stack([v["nx"], v["ny"], v["nz"]], axis=1)
+    assert np.allclose(np.linalg.norm(nn, axis=1), 1.0, atol=1e-4) and (v["instance_idx"] == 102).all()
+    # our writers -> our readers
+    scene = common.tiny_scene()
+    p = str(tmp_path / "scan.ply")
+    rsio.write_ply(p, scene.scan.pos(0), scene.scan.nor(0), scene.scan_class, scene.scan_instance)
+    w = rsio.read_ply(p)
+    assert (np.stack([w["x"], w["y"], w["z"]], axis=1) == scene.scan.pos(0)).all() and (w["class_idx"] == scene.scan_class).all()
+    path = rsio.write_database(str(tmp_path), "db0", scene, p, [(i, o.pose) for i, o in enumerate(scene.objects)])
+    d2 = rsio.read_database(path)
+    assert len(d2["objects"]) == len(scene.objects) and len(d2["poses"]) == len(scene.objects)
+    for (_, _, oi, _, m), o in zip(d2["poses"], scene.objects):
+        assert np.allclose(m, o.pose, atol=1e-6)

@@ -242,9 +242,12 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     nms = nms_dist is not None
     big_first = sorted(range(len(dyn)), key=lambda i: -len(dyn[i].levels[2]))  # ICP cost grows with the level-2 size
 
-    def add(**kw):  # called from the lane threads: the GIL makes the += atomic enough, the totals are order-free
-        for k, v in kw.items():
-            stats[k] += int(v)
+    stats_lock = threading.Lock()
+
+    def add(**kw):  # called from the lane threads; the totals are order-free
+        with stats_lock:
+            for k, v in kw.items():
+                stats[k] += int(v)
 
     def search(m):
         """dense search + verification on this rank's block of translations"""

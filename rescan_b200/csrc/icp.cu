@@ -740,7 +740,12 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   if( (size_t)NPART > total ) { NPART = (int)total; }
   // object points per warp task of the search launches: small tasks shorten the late iterations (few alignments left,
   // the launch is then pure latency), at the price of idle lanes in the cell-window pass
-  int TPT = 16;
+  // the launch is then pure latency), at the price of idle lanes in the cell-window pass.  A small batch (one object's
+  // survivors inside its lane: a few thousand tasks) does not fill the GPU at 16 points per task: 8 there (measured
+  // 52.2 -> 50.9 ms per C2 step with 8 lanes), 16 for the big batches.
+  size_t total_points = 0;
+  for( int j = 0; j < n_jobs; ++j ) { total_points += (size_t)jobs[j].n_batch * (size_t)( jobs[j].object->n > 0 ? jobs[j].object->n : 0 ); }
+  int TPT = total_points / 16 < 8192 ? 8 : 16;
   { const std::string o = option( "icp_tpt" ); if( !o.empty() ) { const int v = atoi( o.c_str() ); if( v == 8 || v == 16 || v == 32 ) { TPT = v; } } }
   std::vector<std::vector<int>> part_ids( NPART );
   std::vector<std::vector<unsigned>> part_task( NPART );

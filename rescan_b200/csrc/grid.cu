@@ -163,7 +163,7 @@ __global__ void ncone_kernel( const float4* __restrict__ cone, const uint32_t* _
         if( !( u.w > 0.0f ) ) { usable = false; }
         sx += u.x * (float)cnt; sy += u.y * (float)cnt; sz += u.z * (float)cnt; ++filled;
       }
-  float4 out = make_float4( 0.f, 0.f, 0.f, -1.f );
+  float4 out = make_float4( 0.f, 0.f, 0.f, filled ? -1.f : RS_NCONE_EMPTY ); // an empty block is marked: one load tells a query so
   float len = sqrtf( sx * sx + sy * sy + sz * sz );
   if( usable && filled && len > 1e-3f )
   {

@@ -61,6 +61,16 @@ __device__ __forceinline__ ConeCull make_cull( const GridView& g, float dot_thr,
   }
   return c;
 }
+// the same test on a cone already loaded: u = {ux, uy, uz, cos(alpha)} (cos(alpha) <= 0: no usable cone)
+__device__ __forceinline__ bool cone_possible_loaded( const float4& u, const ConeCull& c, float nx, float ny, float nz )
+{
+  if( !c.on ) { return true; }
+  if( !( u.w > 0.0f ) ) { return true; }
+  const float s2 = fmaxf( 1e-12f, 1.0f - u.w * u.w );
+  float sa = s2 * rsqrtf( s2 ) + 2e-5f;
+  float ct = u.x * nx + u.y * ny + u.z * nz;
+  return !( ct < u.w * c.cb - sa * c.sb );
+}
 __device__ __forceinline__ bool cone_possible( const float4* __restrict__ cones, const ConeCull& c, size_t cell_id, float nx, float ny, float nz )
 {
   if( !c.on ) { return true; }

@@ -89,12 +89,19 @@ __device__ __forceinline__ Stage1 stage1_test( const GridView& g, double radius,
     // the window is a subset of the 3x3x3 block around the query's own cell: one load decides emptiness, a second
     // one whether any normal of the block can be compatible (nearest.cuh ConeCull)
     const size_t c0id = ( (size_t)w.c0z * g.H + w.c0y ) * g.W + w.c0x;
-    r.active = __ldg( g.occ27 + c0id ) != 0;
-    if( r.active && allow_cull && g.ncone )
+    if( allow_cull && g.ncone )
     {
-      ConeCull cull = make_cull( g, dot_thr, nx, ny, nz );
-      r.active = cone_possible( g.ncone, cull, c0id, nx, ny, nz );
+      // ONE load answers both questions: an empty block is stored as cos = RS_NCONE_EMPTY (grid.cu ncone_kernel), so the
+      // occupancy count does not have to be fetched first
+      const float4 u = __ldg( g.ncone + c0id );
+      if( u.w > 1.5f ) { r.active = false; }
+      else
+      {
+        const ConeCull cull = make_cull( g, dot_thr, nx, ny, nz );
+        r.active = cone_possible_loaded( u, cull, nx, ny, nz );
+      }
     }
+    else { r.active = __ldg( g.occ27 + c0id ) != 0; }
   }
   return r;
 }

@@ -12,6 +12,7 @@
 
 #define RS_FULL 0xffffffffu
 #define RS_INF_BITS 0x7f800000u
+#define RS_NCONE_EMPTY 2.0f /* GridView::ncone[c].w of a 3x3x3 block without points (a cosine never exceeds 1) */
 
 // ---------------------------------------------------------------------------------------------- host runtime
 namespace rs

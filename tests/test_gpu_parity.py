@@ -206,6 +206,39 @@ def test_icp_align_matches_oracle(scene):
     assert n_close >= 0.9 * n_total, f"only {n_close}/{n_total} ICP runs within 1e-5 m / 1e-5 rad (worst {worst})"
 
 
+@pytest.mark.parametrize("lvl,max_dist,max_angle_deg,T2_shift", [
+    (2, 0.075, 50.0, None),   # rsdb_refine_alignment_of_objects_to_scene (lib/rs/rs_database.h:227-229)
+    (0, 0.05, 10.0, None),    # rsdu_augment_database (apps/segment_transfer/database_update.cpp:65-67), level 0
+    (2, 0.10, 60.0, 0.4),     # a non-identity T2 (icp.h:339-347 maps through T2^-1 * T1)
+])
+def test_icp_call_sites_bit_exact(scene, lvl, max_dist, max_angle_deg, T2_shift):
+    """the other icp_align call sites of the reference, with their own levels / distances / angles: refined pose, error and
+    iteration count identical to the oracle's (which is pinned bit-equal to the compiled reference)"""
+    ps, ns = scene.scan.pos(lvl), scene.scan.nor(lvl)
+    grid = api.HashGrid(ps, 0.05, normals=ns)
+    rng = np.random.default_rng(77 + lvl)
+    ang = np.float32(np.deg2rad(max_angle_deg))
+    T2 = None
+    if T2_shift is not None:
+        T2 = common.colmajor(synth.yaw_pose(0.3, T2_shift, -T2_shift, 0.0))
+    n = 0
+    for o in scene.objects[:3]:
+        cloud = api.PointCloud(o.cloud.pos(lvl), o.cloud.nor(lvl))
+        starts = []
+        for _ in range(3):
+            d = synth.yaw_pose(rng.uniform(-0.04, 0.04), rng.uniform(-0.015, 0.015), rng.uniform(-0.015, 0.015), 0.0)
+            m = o.pose.astype(np.float64) @ d.astype(np.float64)
+            if T2_shift is not None:  # T1 is then expressed so that T2^-1 * T1 lands on the scan
+                m = synth.yaw_pose(0.3, T2_shift, -T2_shift, 0.0).astype(np.float64) @ m
+            starts.append(common.colmajor(m.astype(np.float32)))
+        T, err, it = api.icp_align(cloud, grid, np.stack(starts), max_dist, ang, T2=T2)
+        for b, s in enumerate(starts):
+            To, eo, ito = O.icp_align(o.cloud.pos(lvl), o.cloud.nor(lvl), ps, ns, s, max_dist, ang, T2=T2)
+            assert (T[b] == To).all() and err[b] == np.float32(eo) and it[b] == ito
+            n += int(ito > 0)
+    assert n >= 6  # the runs actually iterated
+
+
 def test_icp_degenerate_inputs(scene):
     p2, n2 = scene.scan.pos(2), scene.scan.nor(2)
     grid = api.HashGrid(p2, 0.05, normals=n2)

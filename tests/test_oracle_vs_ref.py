@@ -79,6 +79,26 @@ def test_icp_align(S):
     assert (To == Tr).all() and np.float32(eo) == np.float32(er)
 
 
+@pytest.mark.parametrize("lvl,max_dist,max_angle_deg,with_T2", [(2, 0.075, 50.0, False), (0, 0.05, 10.0, False), (2, 0.10, 60.0, True)])
+def test_icp_align_other_call_sites(S, lvl, max_dist, max_angle_deg, with_T2):
+    """icp_align as rsdb_refine_alignment_of_objects_to_scene (rs_database.h:227) and rsdu_augment_database
+    (database_update.cpp:65) call it, and with a non-identity T2: oracle bit-equal to the compiled reference"""
+    scene, _, _ = S
+    ang = np.float32(np.deg2rad(max_angle_deg))
+    rng = np.random.default_rng(40 + lvl)
+    T2m = synth.yaw_pose(0.3, 0.4, -0.4, 0.0).astype(np.float64)
+    T2 = common.colmajor(T2m.astype(np.float32)) if with_T2 else None
+    for o in scene.objects[:2]:
+        d = synth.yaw_pose(rng.uniform(-0.04, 0.04), rng.uniform(-0.015, 0.015), rng.uniform(-0.015, 0.015), 0.0)
+        m = o.pose.astype(np.float64) @ d.astype(np.float64)
+        if with_T2:
+            m = T2m @ m
+        s = common.colmajor(m.astype(np.float32))
+        To, eo, it = O.icp_align(o.cloud.pos(lvl), o.cloud.nor(lvl), scene.scan.pos(lvl), scene.scan.nor(lvl), s, max_dist, ang, T2=T2)
+        Tr, er = R.icp_align(o.cloud.pos(lvl), o.cloud.nor(lvl), scene.scan.pos(lvl), scene.scan.nor(lvl), s, max_dist, ang, T2_colmajor=T2)
+        assert (To == Tr).all() and np.float32(eo) == np.float32(er) and it > 0
+
+
 def _nms_case(scene, oi, rng, n=40):
     """proposals of one object: jittered copies of its true pose, far-away poses and a few with failed scores"""
     o = scene.objects[oi]

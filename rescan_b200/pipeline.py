@@ -19,6 +19,7 @@ rank refines an interleaved share of the merged list and a second small all-gath
 from __future__ import annotations
 
 import dataclasses
+import os
 import numpy as np
 
 from . import api, posegrid, synth
@@ -306,7 +307,7 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         # merged across ranks.  The objects go through in groups so that the refinement of one group overlaps the dense
         # search of the next: every collective is issued by THIS thread in a fixed order (top-k of group 0, 1, ..., then
         # the refined rows of group 0, 1, ...), identical on every rank whatever the timing of the lanes.
-        n_groups = min(4, max(1, len(dyn)))
+        n_groups = min(int(os.environ.get("RSGPU_GROUPS", "4")), max(1, len(dyn)))
         groups = [big_first[j::n_groups] for j in range(n_groups)]  # big objects spread over the groups, in submission order
         groups = [g for g in groups if g]
         order = [k for g in groups for k in g]

@@ -1,6 +1,7 @@
 """Writes the file set of the drop-in test (a first-scan database + a rescan PLY) into a directory.  With --golden it
 also runs the pure-CPU reference build (integration/_build/pose_proposal_ref) on it and stores the resulting proposal
-.bin as tests/golden/dropin_pp.bin (build container only)."""
+.bin as tests/golden/dropin_pp.bin, together with the .rsdb and one object PLY the reference wrote (build container only;
+the .rsdb holds the absolute paths of the folder it was written in, default /tmp/rsgpu_dropin_case)."""
 import os
 import shutil
 import subprocess
@@ -32,8 +33,12 @@ def main():
     if "--golden" in sys.argv:
         exe = os.path.join(ROOT, "integration", "_build", "pose_proposal_ref")
         subprocess.check_call([exe, db, scan, out, "-v"], stdout=subprocess.DEVNULL)
-        shutil.copy(os.path.join(folder, "scan1_pp", "scan1_pp.bin"), os.path.join(ROOT, "tests", "golden", "dropin_pp.bin"))
-        print("wrote tests/golden/dropin_pp.bin", os.path.getsize(os.path.join(ROOT, "tests", "golden", "dropin_pp.bin")), "bytes")
+        gold = os.path.join(ROOT, "tests", "golden")
+        shutil.copy(os.path.join(folder, "scan1_pp", "scan1_pp.bin"), os.path.join(gold, "dropin_pp.bin"))
+        # the database and one object model exactly as the reference wrote them: fixtures of the rsio readers (tests/test_host_logic.py)
+        shutil.copy(out, os.path.join(gold, "dropin_pp.rsdb"))
+        shutil.copy(os.path.join(folder, "scan1_pp", "obj_102.ply"), os.path.join(gold, "dropin_obj_102.ply"))
+        print("wrote tests/golden/dropin_pp.bin", os.path.getsize(os.path.join(gold, "dropin_pp.bin")), "bytes, dropin_pp.rsdb, dropin_obj_102.ply")
 
 
 if __name__ == "__main__":

@@ -15,10 +15,15 @@ for r in rows:
     except ValueError: continue
     k = (fpath, int(r[0])); src[k] = r[1]
     a = per[fn].setdefault(k, [0.0, 0.0]); a[0] += v; a[1] += s
-REGIONS = [('nearest.cuh', 52, 72, 'cone fns'), ('nearest.cuh', 75, 110, 'lane_query_setup (stage 1)'), ('nearest.cuh', 112, 122, 'shfl_window'),
-           ('nearest.cuh', 132, 150, 'sweep_cell'), ('nearest.cuh', 154, 173, 'phase1_chunk'), ('nearest.cuh', 176, 192, 'phase2_chunk'),
-           ('nearest.cuh', 198, 274, 'nearest_w body'), ('nearest.cuh', 279, 322, 'batch loop'), ('rsgpu_internal.cuh', 125, 143, 'exact math'),
-           ('rsgpu_internal.cuh', 156, 185, 'make_window'), ('rsgpu_internal.cuh', 188, 208, 'axis_gap/window_cell')]
+# (file, first line, last line, name) - line ranges of the sources as of the end of round 1; adjust after edits
+REGIONS = [('nearest_group.cuh', 70, 100, 'stage1_test (pass A)'), ('nearest_group.cuh', 102, 106, 'normal_dot_call'),
+           ('nearest_group.cuh', 108, 125, 'group_min / group_sum'), ('nearest_group.cuh', 130, 166, 'group_search: window + gaps'),
+           ('nearest_group.cuh', 167, 205, 'phase 1: cell table'), ('nearest_group.cuh', 206, 243, 'phase 2: sweeps'),
+           ('nearest_group.cuh', 244, 276, 'phase 3: rank count'), ('nearest_group.cuh', 278, 305, 'group_round glue'),
+           ('rsgpu_internal.cuh', 130, 138, 'xf_apply'), ('rsgpu_internal.cuh', 140, 145, 'dist2_exact'), ('rsgpu_internal.cuh', 147, 150, 'dot3_exact'),
+           ('rsgpu_internal.cuh', 152, 195, 'make_window'), ('nearest.cuh', 40, 80, 'cone tests'),
+           ('score.cu', 120, 175, 'score: setup + pass A loop'), ('score.cu', 176, 210, 'score: pass B glue / query_of'),
+           ('score.cu', 211, 235, 'score: pass C terms + sum')]
 for fn, lines in per.items():
     if pick not in fn: continue
     tot = sum(v[0] for v in lines.values()); ts = sum(v[1] for v in lines.values())

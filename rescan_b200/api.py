@@ -57,7 +57,8 @@ class IcpJob(C.Structure):
 
 
 class ProposeOpts(C.Structure):
-    _fields_ = [("max_n_neigh", C.c_int32), ("radius", C.c_float), ("thresholds", C.c_float * 3), ("top_k", C.c_int32)]
+    _fields_ = [("max_n_neigh", C.c_int32), ("radius", C.c_float), ("thresholds", C.c_float * 3), ("top_k", C.c_int32),
+                ("translation_ids", C.c_void_p)]
 
 
 _lib = None
@@ -313,10 +314,13 @@ def score_pose_grid_count(obj: PointCloud, scene: HashGrid, rotations, translati
 
 
 def propose_poses(obj_lvl4: PointCloud, obj_lvl3: PointCloud, obj_lvl2: PointCloud, scene: HashGrid, rotations,
-                  translations, max_n_neigh=64, radius=0.10, thresholds=(0.25, 0.35, 0.40), top_k=0, cap=None):
-    """mgs_propose_poses for one object -> (proposals float32 [n,17] = 16 xform + score, pose_ids int64 [n])"""
+                  translations, max_n_neigh=64, radius=0.10, thresholds=(0.25, 0.35, 0.40), top_k=0, cap=None, translation_ids=None):
+    """mgs_propose_poses for one object -> (proposals float32 [n,17] = 16 xform + score, pose_ids int64 [n]).
+    translation_ids: the callers' numbering of the translations when they are passed in another order (see rsgpu.h)."""
     r, t = _f32(rotations).reshape(-1, 16), _f32(translations).reshape(-1, 3)
-    opts = ProposeOpts(max_n_neigh, radius, (C.c_float * 3)(*thresholds), top_k)
+    tid = np.ascontiguousarray(translation_ids, np.int64) if translation_ids is not None else None
+    assert tid is None or len(tid) == len(t)
+    opts = ProposeOpts(max_n_neigh, radius, (C.c_float * 3)(*thresholds), top_k, tid.ctypes.data if tid is not None else None)
     cap = int(cap if cap is not None else max(len(t), 1))
     while True:
         out = np.zeros((cap, POSE_FLOATS), np.float32)

@@ -398,7 +398,7 @@ __global__ void select_kernel( const float* __restrict__ scores, long long n_tra
 __global__ void emit_kernel( const int* __restrict__ flag, const int* __restrict__ offs, const int* __restrict__ best_r,
                              const float* __restrict__ best_s, const float* __restrict__ rots, const float* __restrict__ trans,
                              long long n_trans, int n_rot, float* __restrict__ xforms, float* __restrict__ scores,
-                             long long* __restrict__ pose_id )
+                             long long* __restrict__ pose_id, const long long* __restrict__ trans_ids )
 {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if( t >= n_trans || !flag[t] ) { return; }
@@ -407,7 +407,23 @@ __global__ void emit_kernel( const int* __restrict__ flag, const int* __restrict
   xforms[16 * (size_t)o + 12] = trans[3 * t]; xforms[16 * (size_t)o + 13] = trans[3 * t + 1];
   xforms[16 * (size_t)o + 14] = trans[3 * t + 2]; xforms[16 * (size_t)o + 15] = 1.0f;
   scores[o] = best_s[t];
-  pose_id[o] = t * n_rot + r;
+  pose_id[o] = ( trans_ids ? trans_ids[t] : t ) * n_rot + r; // the caller's numbering of the translations
+}
+
+// proposals re-ordered by ascending pose id (translations passed in another order than the caller numbers them)
+__global__ void reorder_kernel( const int* __restrict__ src, int n, const float* __restrict__ xf_in, const float* __restrict__ sc_in,
+                                float* __restrict__ xf_out, float* __restrict__ sc_out )
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if( j >= n ) { return; }
+  const int i = src[j];
+  for( int c = 0; c < 16; ++c ) { xf_out[16 * (size_t)j + c] = xf_in[16 * (size_t)i + c]; }
+  sc_out[j] = sc_in[i];
+}
+__global__ void iota_kernel( int* __restrict__ v, int n )
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if( j < n ) { v[j] = j; }
 }
 
 // verification outcome (:289-292): new score if above the level's threshold, else -1; gate <= 0 untouched
@@ -628,8 +644,31 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   if( n_prop == 0 ) { return RSGPU_OK; }
   DevBuf<float> px, psc, fresh; DevBuf<long long> pid;
   RS_CUDA( px.alloc( (size_t)n_prop * 16 ) ); RS_CUDA( psc.alloc( n_prop ) ); RS_CUDA( fresh.alloc( n_prop ) ); RS_CUDA( pid.alloc( n_prop ) );
-  emit_kernel<<<tb, 256, 0, st>>>( flag.p, offs.p, best_r.p, best_s.p, dr.p, dt.p, n_trans, n_rot, px.p, psc.p, pid.p );
+  DevBuf<long long> d_tids;
+  if( opts.translation_ids )
+  {
+    RS_CUDA( d_tids.alloc( n_trans ) );
+    RS_CUDA( cudaMemcpyAsync( d_tids.p, opts.translation_ids, sizeof( long long ) * (size_t)n_trans, cudaMemcpyHostToDevice, st ) );
+  }
+  emit_kernel<<<tb, 256, 0, st>>>( flag.p, offs.p, best_r.p, best_s.p, dr.p, dt.p, n_trans, n_rot, px.p, psc.p, pid.p, opts.translation_ids ? d_tids.p : nullptr );
   RS_CHECK_LAUNCH();
+  DevBuf<float> px2, psc2; DevBuf<long long> pid2; DevBuf<int> src0, src1; DevBuf<unsigned char> sort_tmp;
+  if( opts.translation_ids && n_prop > 1 )
+  {
+    // survivors in the caller's translation order (= ascending pose id: one rotation per translation), so that the
+    // verification, the emission order and every tie below are what they would be for the caller's own order
+    RS_CUDA( px2.alloc( (size_t)n_prop * 16 ) ); RS_CUDA( psc2.alloc( n_prop ) ); RS_CUDA( pid2.alloc( n_prop ) );
+    RS_CUDA( src0.alloc( n_prop ) ); RS_CUDA( src1.alloc( n_prop ) );
+    iota_kernel<<<( n_prop + 255 ) / 256, 256, 0, st>>>( src0.p, n_prop );
+    RS_CHECK_LAUNCH();
+    size_t sort_bytes = 0;
+    RS_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, sort_bytes, (const unsigned long long*)pid.p, (unsigned long long*)pid2.p, src0.p, src1.p, n_prop, 0, 64, st ) );
+    RS_CUDA( sort_tmp.alloc( sort_bytes ) );
+    RS_CUDA( cub::DeviceRadixSort::SortPairs( sort_tmp.p, sort_bytes, (const unsigned long long*)pid.p, (unsigned long long*)pid2.p, src0.p, src1.p, n_prop, 0, 64, st ) );
+    reorder_kernel<<<( n_prop + 255 ) / 256, 256, 0, st>>>( src1.p, n_prop, px.p, psc.p, px2.p, psc2.p );
+    RS_CHECK_LAUNCH();
+    std::swap( px.p, px2.p ); std::swap( psc.p, psc2.p ); std::swap( pid.p, pid2.p );
+  }
   // levels 3 and 2: verification of the survivors
   const rsgpu_cloud_t* lv[2] = { o3, o2 };
   for( int l = 0; l < 2; ++l )

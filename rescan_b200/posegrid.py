@@ -125,3 +125,22 @@ def cloud_centroid(pos0):
         return np.zeros(3, np.float32)
     c = np.array([np.cumsum(p[:, a].astype(np.float64))[-1] for a in range(3)])
     return (c / float(len(p))).astype(np.float32)
+
+
+def spatial_order(translations, cell=0.1):
+    """permutation that walks the translations along a Z-order curve over (x, z) in steps of `cell`: consecutive poses of a
+    dense launch then search neighbouring scan cells (cache locality); used with rsgpu_propose_opts_t.translation_ids, which
+    keeps ids, order and ties in the caller's numbering"""
+    t = np.asarray(translations, np.float32).reshape(-1, 3)
+    if len(t) == 0:
+        return np.zeros(0, np.int64)
+    q = np.floor((t[:, [0, 2]].astype(np.float64) - t[:, [0, 2]].astype(np.float64).min(0)) / cell)
+    q = np.clip(q, 0, 65535).astype(np.uint64)
+
+    def spread(v):
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+        return v
+    return np.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)), kind="stable").astype(np.int64)

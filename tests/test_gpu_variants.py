@@ -103,3 +103,28 @@ def test_icp_variants_bit_identical(scene):
     for (Ta, ea, ia), (Tb, eb, ib) in zip(base, alt):
         assert (ia == ib).all() and (ea == eb).all() and (Ta == Tb).all()
     assert max(int(i.max()) for _, _, i in base) > 6
+
+
+def test_translation_order_does_not_change_proposals():
+    """rsgpu_propose_opts_t.translation_ids: the translations handed over along a space-filling curve (or in any other
+    order) with the caller's numbering give bit for bit the proposals, ids and order of the caller's own order"""
+    from rescan_b200 import posegrid
+    scene = common.small_scene()
+    grid = api.HashGrid(scene.scan.pos(1), 0.05, normals=scene.scan.nor(1))
+    rots, _ = common.rotation_xforms(12)
+    trans = synth.translation_seeds(scene.scan, 300, seed=13)
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    rng = np.random.default_rng(3)
+    n_checked = 0
+    for o in scene.objects:
+        if o.is_static:
+            continue
+        c4, c3, c2 = (api.PointCloud(o.cloud.pos(l), o.cloud.nor(l)) for l in (4, 3, 2))
+        for top_k in (0, 5, 64):
+            base, bid = api.propose_poses(c4, c3, c2, grid, rots, trans, top_k=top_k)
+            for perm in (posegrid.spatial_order(trans), rng.permutation(len(trans)).astype(np.int64)):
+                got, gid = api.propose_poses(c4, c3, c2, grid, rots, np.ascontiguousarray(trans[perm]), top_k=top_k, translation_ids=perm)
+                assert (gid == bid).all() and (got == base).all()
+                n_checked += len(base)
+    assert n_checked > 0

@@ -140,3 +140,14 @@ def test_readers_on_reference_written_files(tmp_path):
     assert len(d2["objects"]) == len(scene.objects) and len(d2["poses"]) == len(scene.objects)
     for (_, _, oi, _, m), o in zip(d2["poses"], scene.objects):
         assert np.allclose(m, o.pose, atol=1e-6)
+
+
+def test_spatial_order_is_a_permutation_that_shortens_the_walk():
+    rng = np.random.default_rng(0)
+    t = rng.uniform(0, 7, (3000, 3)).astype(np.float32)
+    o = posegrid.spatial_order(t)
+    assert sorted(o.tolist()) == list(range(len(t)))
+    step = lambda a: np.linalg.norm(np.diff(a[:, [0, 2]], axis=0), axis=1).mean()
+    assert step(t[o]) < 0.2 * step(t)
+    assert len(posegrid.spatial_order(np.zeros((0, 3), np.float32))) == 0
+    assert list(posegrid.spatial_order(np.zeros((1, 3), np.float32))) == [0]

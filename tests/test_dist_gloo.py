@@ -68,3 +68,55 @@ def test_two_rank_allgather_merge(tmp_path):
         assert (p0 == p1).all() and (i0 == i1).all()
         sp, si = pipeline.merge_topk([props[keep]], [ids[keep]], top_k)
         assert (sp == p0).all() and (si == i0).all()
+
+
+def _step_worker(rank, world, port, out, lanes):
+    """the whole pose-sharded run_step on CPU: rescan_b200.api replaced by tests/fake_api.py (input-determined fake kernels)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = _fake_step(rank, world, dist, lanes)
+    np.savez(os.path.join(out, f"s{rank}_{lanes}.npz"), **{f"p{k}": p for k, p in enumerate(res.proposals)},
+             **{f"i{k}": i for k, i in enumerate(res.pose_ids)}, n_eval=res.n_evaluations)
+    dist.destroy_process_group()
+
+
+def _fake_step(rank, world, dist_mod, lanes):
+    from tests import fake_api
+    pipeline.api = fake_api
+    pipeline._POOLS.clear()
+    rng = np.random.default_rng(11)
+    models = [pipeline.ObjectModel(100 + k, 5, k == 2, {l: fake_api.PointCloud(np.zeros((10 * (k + 1) + l, 3)), None) for l in (1, 2, 3, 4)},
+                                   np.zeros(3, np.float32)) for k in range(7)]
+    trans = rng.uniform(0, 6, (501, 3)).astype(np.float32)
+    rots = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (9, 1))
+    scan = (np.zeros((50, 3), np.float32), np.zeros((50, 3), np.float32))
+    prev = [rng.uniform(0, 6, (1, 16)).astype(np.float32) for _ in range(6)]
+    return pipeline.run_step(scan, scan, models, rots, trans, top_k=16, nms_dist=0.2, previous=prev, rank=rank, world=world,
+                             dist=dist_mod, device=torch.device("cpu"), lanes=lanes)
+
+
+def test_pose_sharded_step_host_logic_on_cpu(tmp_path):
+    """lanes, object groups, the fixed order of the collectives and both exchanges of pipeline.run_step, world_size 2 over gloo on
+    the CPU: every rank must end with the single-rank lists"""
+    import importlib
+    try:
+        ref = _fake_step(0, 1, None, 1)
+        ref4 = _fake_step(0, 1, None, 4)
+        for a, b, ia, ib in zip(ref.proposals, ref4.proposals, ref.pose_ids, ref4.pose_ids):
+            assert (a == b).all() and (ia == ib).all()
+        assert any(len(p) for p in ref.proposals)
+        for lanes in (1, 4):
+            world, port = 2, _free_port()
+            mp.spawn(_step_worker, args=(world, port, str(tmp_path), lanes), nprocs=world, join=True)
+            total = 0
+            for rank in range(world):
+                z = np.load(tmp_path / f"s{rank}_{lanes}.npz")
+                total += int(z["n_eval"])
+                for k, (p, i) in enumerate(zip(ref.proposals, ref.pose_ids)):
+                    assert z[f"p{k}"].shape == p.shape and (z[f"p{k}"] == p).all() and (z[f"i{k}"] == i).all(), (lanes, rank, k)
+            assert total == ref.n_evaluations
+    finally:
+        import rescan_b200.api as real_api
+        pipeline.api = real_api
+        pipeline._POOLS.clear()

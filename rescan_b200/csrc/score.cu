@@ -598,6 +598,7 @@ void rsgpu_propose_default_opts( rsgpu_propose_opts_t* o )
   o->max_n_neigh = 64; o->radius = 0.1f;
   o->thresholds[0] = 0.25f; o->thresholds[1] = 0.35f; o->thresholds[2] = 0.40f;
   o->top_k = 0;
+  o->translation_ids = nullptr;
 }
 
 int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const rsgpu_cloud_t* o2, const rsgpu_grid_t* scene,

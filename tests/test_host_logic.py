@@ -151,3 +151,42 @@ def test_spatial_order_is_a_permutation_that_shortens_the_walk():
     assert step(t[o]) < 0.2 * step(t)
     assert len(posegrid.spatial_order(np.zeros((0, 3), np.float32))) == 0
     assert list(posegrid.spatial_order(np.zeros((1, 3), np.float32))) == [0]
+
+
+def test_header_is_plain_c_and_library_fails_loudly_without_a_device(tmp_path):
+    """include/rsgpu.h compiles as C99, a C program links against librsgpu.so, and - in this container, which has no GPU -
+    a compute entry point reports RSGPU_ERR_NO_DEVICE instead of falling back to anything"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.exists(api.LIB_PATH):
+        pytest.skip("gcc or librsgpu.so missing")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "rsgpu.h"
+int main( void )
+{
+  float pts[9] = { 0, 0, 0, 1, 0, 0, 0, 1, 0 };
+  rsgpu_grid_t* g = NULL;
+  rsgpu_propose_opts_t o;
+  rsgpu_propose_default_opts( &o );
+  if( strncmp( rsgpu_version(), "rsgpu", 5 ) != 0 || o.max_n_neigh != 64 || o.translation_ids != NULL ) { return 2; }
+  int n = rsgpu_device_count();
+  int s = rsgpu_grid_create( pts, 3, 0.05f, &g );
+  printf( "%d %d %s\n", n, s, rsgpu_last_error() );
+  if( g ) { rsgpu_grid_destroy( g ); }
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(api.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lrsgpu", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    n, status = (int(x) for x in out.stdout.split()[:2])
+    if n == 0:
+        assert status == -1 and "no CUDA device" in out.stdout  # RSGPU_ERR_NO_DEVICE: there is no CPU fallback
+    else:
+        assert status == 0

@@ -190,3 +190,26 @@ int main( void )
         assert status == -1 and "no CUDA device" in out.stdout  # RSGPU_ERR_NO_DEVICE: there is no CPU fallback
     else:
         assert status == 0
+
+
+def test_sharding_and_merge_properties():
+    """shard_range tiles [0, n) in rank order with sizes differing by at most one; merging per-shard top-k lists gives the
+    top-k of the whole (the identity the pose-sharded step rests on), for any split and any k"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(0, 300), world=st.integers(1, 9), k=st.integers(0, 40), seed=st.integers(0, 2 ** 16))
+    def check(n, world, k, seed):
+        edges = [pipeline.shard_range(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        sizes = [hi - lo for lo, hi in edges]
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:])) and max(sizes) - min(sizes) <= 1
+        rng = np.random.default_rng(seed)
+        props = np.zeros((n, 17), np.float32)
+        props[:, 16] = rng.choice(np.array([-1.0, 0.3, 0.5, 0.5, 0.9], np.float32), n)  # many ties
+        ids = np.arange(n, dtype=np.int64) * 3
+        whole = pipeline.merge_topk([props], [ids], k)
+        parts = [pipeline.merge_topk([props[lo:hi]], [ids[lo:hi]], k) for lo, hi in edges]
+        merged = pipeline.merge_topk([p[0] for p in parts], [p[1] for p in parts], k)
+        assert (merged[1] == whole[1]).all() and (merged[0] == whole[0]).all()
+    check()

@@ -253,6 +253,25 @@ int rsgpu_nms( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1, const float
 int rsgpu_poisson_level( const float* pts, int32_t n, float voxel, int32_t max_n_neigh, int32_t* out_indices, int32_t* n_out,
                          int32_t* n_rounds );
 
+/* ---- coverage term of the arrangement optimiser -------------------------------------------------
+   Grids are isect_grid3d_t's (lib/rs/intersect.h:20-30, 57-116): `origin` = the padded bbox min corner, `res` = x/y/z
+   resolution (isect_grid3d_init :57-75), cell of a point = floorf( (p - origin) * (1.0f / voxel) ) per axis, stored at
+   (y * res[2] + z) * res[0] + x, one byte per cell.
+   rsgpu_rasterize_points replaces the loop of rsao_rasterize_scene_to_grid (apps/segment_transfer/
+   arrangement_optimization.cpp:1064-1080; the caller applies its quality filter to the points first): cells of the n
+   points - moved by `pose` (column-major 4x4) when not NULL - are set to 1 in `grid`, which is not cleared.
+   rsgpu_coverage_masks replaces rsao__rasterize_arrangement_to_grid (:1082-1106) + the counting loop of
+   rsao__compute_scene_coverage_score (:343-373) for a whole LIST of candidate placements: placement i = objects[i] (its
+   level-2 points) under poses[16 i ..].  *n_lit = number of lit cells of scene_grid; out_masks[i * n_words + w], n_words >=
+   ceil( *n_lit / 32 ), holds one bit per lit scan cell (bit b = the b-th lit cell in ascending cell index), set iff the
+   placement lights that cell.  The reference's coverage score of any arrangement is then
+   popcount( OR of its placements' masks ) / *n_lit (0 when *n_lit is 0).  out_masks == NULL only counts the lit cells. */
+int rsgpu_rasterize_points( const float* pts, int32_t n, const float* pose, const float origin[3], const int32_t res[3], float voxel,
+                            uint8_t* grid );
+int rsgpu_coverage_masks( const rsgpu_cloud_t* const* objects, const float* poses, int32_t n_poses, const float origin[3],
+                          const int32_t res[3], float voxel, const uint8_t* scene_grid, uint32_t* out_masks, int32_t n_words,
+                          int32_t* n_lit );
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,9 @@ def load():
         "orc_overlap_factor": (f32, [_f32p, i32, _f32p, i32, _f32p, _f32p, f32, C.c_int, C.c_int]),
         "orc_nms": (None, [_f32p, i32, _f32p, i32, _f32p, _f32p, i32, f32, _u8p]),
         "orc_poisson_level": (i32, [_f32p, i32, f32, i32, _i32p]),
+        "orc_cov_grid": (i32, [_f32p, _f32p, f32, _i32p, _f32p]),
+        "orc_cov_rasterize": (None, [_f32p, i32, vp, _f32p, _i32p, f32, _u8p]),
+        "orc_cov_score": (f32, [_u8p, _u8p, i32]),
         "orc_neighborhood": (None, [vp, _f32p, _f32p, i32, i32, f32, f32, f32, _i32p, _f32p]),
     }
     for name, (res, args) in sig.items():
@@ -249,3 +252,25 @@ def poisson_level(pos0, level):
     out = np.zeros(len(p), np.int32)
     n = load().orc_poisson_level(p.reshape(-1), len(p), np.float32(LEVEL_VOXEL[level]), level, out)
     return out[:n].copy()
+
+
+def cov_grid(bbox_min, bbox_max, voxel=0.05):
+    """isect_grid3d_init over a bbox -> (res int32[3], origin float32[3], n_cells)"""
+    res, origin = np.zeros(3, np.int32), np.zeros(3, np.float32)
+    n = load().orc_cov_grid(_f32(bbox_min).reshape(3), _f32(bbox_max).reshape(3), np.float32(voxel), res, origin)
+    return res, origin, int(n)
+
+
+def cov_rasterize(pts, pose, res, origin, voxel=0.05, grid=None):
+    """cells lit by the points (under `pose`, column-major 16 floats, or None) -> uint8 grid [n_cells] (OR-ed into `grid`)"""
+    p = _f32(pts).reshape(-1, 3)
+    res = np.ascontiguousarray(res, np.int32)
+    if grid is None:
+        grid = np.zeros(int(res[0]) * int(res[1]) * int(res[2]), np.uint8)
+    ps = _f32(pose).reshape(16) if pose is not None else None
+    load().orc_cov_rasterize(p.reshape(-1), len(p), ps.ctypes.data if ps is not None else None, _f32(origin).reshape(3), res, np.float32(voxel), grid)
+    return grid
+
+
+def cov_score(scn_grid, arr_grid):
+    return float(load().orc_cov_score(np.ascontiguousarray(scn_grid, np.uint8), np.ascontiguousarray(arr_grid, np.uint8), len(scn_grid)))

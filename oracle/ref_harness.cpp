@@ -54,6 +54,7 @@
 #include "rs_database.h"
 #include "rs_distance_function.h"
 #include "pose_proposal.h"
+#include "intersect.h" /* declarations only: the implementation is instantiated in pose_proposal.cpp's TU */
 #include "GCoptimization.h"
 #include "rs_pointcloud_filters.h"
 
@@ -411,6 +412,43 @@ int64_t ref_compute_neighborhood( void* cloud, int lvl, int max_nn, float radius
   for( int64_t i = 0; i < n; ++i ) { (*a)[i] = e[i].idx1; (*b)[i] = e[i].idx2; (*w)[i] = e[i].weight; }
   msh_array_free( e );
   return n;
+}
+
+/* ---------------------------------------------------------------- coverage grids
+   The arrangement optimiser's coverage term (apps/segment_transfer/arrangement_optimization.cpp:343-373) rasterises the
+   scan (rsao_rasterize_scene_to_grid :1064-1080) and the placed dynamic objects (rsao__rasterize_arrangement_to_grid
+   :1082-1106) into 5 cm grids built by isect_grid3d_init over the scan's bbox (apps/segment_transfer/main.cpp:323-325).
+   Those two loops live in a translation unit that is not part of this harness, so they are re-issued here on the
+   reference's own primitives: isect_grid3d_init, msh_mat4_vec3_mul, isect_grid3d_cell_from_world_space (intersect.h:57-116,
+   defined in pose_proposal.cpp's TU). */
+} /* extern "C" */
+extern "C" {
+/* res[3] = x/y/z resolution, origin[3] = padded min corner; returns n_cells */
+int32_t ref_cov_grid( const float* bbox_min, const float* bbox_max, float voxel, int32_t* res, float* origin )
+{
+  msh_bbox_t bb; bb.min_p = msh_vec3( bbox_min[0], bbox_min[1], bbox_min[2] ); bb.max_p = msh_vec3( bbox_max[0], bbox_max[1], bbox_max[2] );
+  isect_grid3d_t g; memset( &g, 0, sizeof( g ) );
+  isect_grid3d_init( &g, &bb, voxel );
+  res[0] = g.x_res; res[1] = g.y_res; res[2] = g.z_res;
+  origin[0] = g.bbox.min_p.x; origin[1] = g.bbox.min_p.y; origin[2] = g.bbox.min_p.z;
+  int32_t n = g.n_cells;
+  isect_grid3d_term( &g );
+  return n;
+}
+/* cells of the points (under `pose` when given) set to 1 in `grid` (n_cells bytes, not cleared) */
+void ref_cov_rasterize( const float* bbox_min, const float* bbox_max, float voxel, const float* pts, int32_t n, const float* pose, uint8_t* grid )
+{
+  msh_bbox_t bb; bb.min_p = msh_vec3( bbox_min[0], bbox_min[1], bbox_min[2] ); bb.max_p = msh_vec3( bbox_max[0], bbox_max[1], bbox_max[2] );
+  isect_grid3d_t g; memset( &g, 0, sizeof( g ) );
+  isect_grid3d_init( &g, &bb, voxel );
+  for( int32_t i = 0; i < n; ++i )
+  {
+    msh_vec3_t p = msh_vec3( pts[3 * i], pts[3 * i + 1], pts[3 * i + 2] );
+    if( pose ) { p = msh_mat4_vec3_mul( mat_from( pose ), p, 1 ); }
+    uint8_t* cell = isect_grid3d_cell_from_world_space( &g, p );
+    if( cell ) { grid[cell - g.data] = 1; }
+  }
+  isect_grid3d_term( &g );
 }
 
 /* ---------------------------------------------------------------- NMS (pose_proposal.cpp:371-452, intersect.h:309-368) */

@@ -12,6 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
@@ -73,6 +74,8 @@ def load(openmp=False):
         "ref_capture_get": (None, [vp, vp, vp, vp, vp, vp]),
         "ref_overlap_factor": (f32, [vp, _f32p, _f32p, f32, C.c_int, C.c_int]),
         "ref_cloud_centroid": (None, [vp, _f32p]),
+        "ref_cov_grid": (i32, [_f32p, _f32p, f32, _i32p, _f32p]),
+        "ref_cov_rasterize": (None, [_f32p, _f32p, f32, _f32p, i32, vp, _u8p]),
         "ref_nms": (i32, [vp, C.c_int, _f32p, i32, f32, _f32p]),
         "ref_compute_neighborhood": (i64, [vp, C.c_int, C.c_int, f32, f32, f32, C.POINTER(C.POINTER(C.c_int32)),
                                           C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_float))]),
@@ -333,3 +336,19 @@ def cloud_centroid(cloud: RefCloud):
     c = np.zeros(3, np.float32)
     cloud.L.ref_cloud_centroid(cloud.h, c)
     return c
+
+
+def cov_grid(bbox_min, bbox_max, voxel=0.05):
+    res, origin = np.zeros(3, np.int32), np.zeros(3, np.float32)
+    n = load(False).ref_cov_grid(_f32(bbox_min).reshape(3), _f32(bbox_max).reshape(3), np.float32(voxel), res, origin)
+    return res, origin, int(n)
+
+
+def cov_rasterize(bbox_min, bbox_max, pts, pose, n_cells, voxel=0.05, grid=None):
+    p = _f32(pts).reshape(-1, 3)
+    if grid is None:
+        grid = np.zeros(n_cells, np.uint8)
+    ps = _f32(pose).reshape(16) if pose is not None else None
+    load(False).ref_cov_rasterize(_f32(bbox_min).reshape(3), _f32(bbox_max).reshape(3), np.float32(voxel), p.reshape(-1), len(p),
+                                  ps.ctypes.data if ps is not None else None, grid)
+    return grid

@@ -912,3 +912,47 @@ int32_t orc_poisson_level( const float* pos0, int32_t n, float voxel, int32_t le
   orc_grid_free( g );
   return n_out;
 }
+
+
+/* ------------------------------------------------------------------------------------------------ coverage term (8 f3) */
+/* isect_grid3d_init (lib/rs/intersect.h:57-75): bbox fattened by 0.3, resolution ceilf( extent / voxel ) + 1 per axis */
+int32_t orc_cov_grid( const float* bbox_min, const float* bbox_max, float voxel, int32_t* res, float* origin )
+{
+  for( int a = 0; a < 3; ++a )
+  {
+    const float mn = bbox_min[a] - 0.3f, mx = bbox_max[a] + 0.3f;
+    origin[a] = mn;
+    res[a] = (int32_t)ceilf( ( mx - mn ) / voxel ) + 1;
+  }
+  return res[0] * res[1] * res[2];
+}
+
+/* rsao_rasterize_scene_to_grid / rsao__rasterize_arrangement_to_grid (apps/segment_transfer/arrangement_optimization.cpp:
+   1064-1106): every point (moved by `pose` first when given, msh_mat4_vec3_mul) lights the cell
+   floorf( (p - origin) * (1.0f / voxel) ) per axis, stored at (y * zr + z) * xr + x (intersect.h:102-116); points outside
+   the grid are ignored.  `grid` is not cleared. */
+void orc_cov_rasterize( const float* pts, int32_t n, const float* pose, const float* origin, const int32_t* res, float voxel, uint8_t* grid )
+{
+  const float inv = 1.0f / voxel;
+  for( int32_t i = 0; i < n; ++i )
+  {
+    float p[3] = { pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2] };
+    if( pose ) { float q[3]; xf_apply( pose, p, 1, q ); p[0] = q[0]; p[1] = q[1]; p[2] = q[2]; }
+    const int32_t x = (int32_t)floorf( ( p[0] - origin[0] ) * inv ), y = (int32_t)floorf( ( p[1] - origin[1] ) * inv ),
+                  z = (int32_t)floorf( ( p[2] - origin[2] ) * inv );
+    if( x < 0 || x >= res[0] || y < 0 || y >= res[1] || z < 0 || z >= res[2] ) { continue; }
+    grid[( (size_t)y * res[2] + z ) * res[0] + x] = 1;
+  }
+}
+
+/* rsao__compute_scene_coverage_score (:343-373): cells lit in both grids / cells lit in the scan's grid, 0 when none */
+float orc_cov_score( const uint8_t* scn, const uint8_t* arr, int32_t n_cells )
+{
+  int32_t agree = 0, valid = 0;
+  for( int32_t i = 0; i < n_cells; ++i )
+  {
+    if( scn[i] > 0 ) { valid++; }
+    if( scn[i] > 0 && arr[i] > 0 ) { agree++; }
+  }
+  return valid == 0 ? 0.0f : (float)agree / (float)valid;
+}

@@ -110,6 +110,8 @@ SIGNATURES = {
     "rsgpu_overlap_factors": (_int, [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp]),
     "rsgpu_nms": (_int, [_vp, _vp, _vp, _vp, _i32, _f32, _vp]),
     "rsgpu_poisson_level": (_int, [_vp, _i32, _f32, _i32, _vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    "rsgpu_rasterize_points": (_int, [_vp, _i32, _vp, _vp, _vp, _f32, _vp]),
+    "rsgpu_coverage_masks": (_int, [C.POINTER(_vp), _vp, _i32, _vp, _vp, _f32, _vp, _vp, _i32, C.POINTER(_i32)]),
     "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
 }
 
@@ -436,3 +438,51 @@ def compute_levels(pos0, nor0):
         idx = poisson_level(p, lvl)
         levels.append((np.ascontiguousarray(p[idx]), np.ascontiguousarray(n[idx])))
     return levels
+
+
+# ------------------------------------------------------------------------------------------------ coverage term (8 f3)
+def coverage_grid(bbox_min, bbox_max, voxel=0.05):
+    """isect_grid3d_init (reference lib/rs/intersect.h:57-75) over a bbox -> (res int32[3], origin float32[3]): the bbox
+    fattened by 0.3, resolution ceilf( extent / voxel ) + 1 per axis - host arithmetic in float32, like the reference"""
+    mn = _f32(bbox_min).reshape(3) - np.float32(0.3)
+    mx = _f32(bbox_max).reshape(3) + np.float32(0.3)
+    res = (np.ceil((mx - mn) / np.float32(voxel)).astype(np.int32) + 1).astype(np.int32)
+    return res, mn.astype(np.float32)
+
+
+def rasterize_points(pts, pose, res, origin, voxel=0.05, grid=None):
+    """rsao_rasterize_scene_to_grid's loop: cells lit by the points (under `pose` when given) -> uint8 grid (OR-ed into `grid`)"""
+    p = _f32(pts).reshape(-1, 3)
+    res = np.ascontiguousarray(res, np.int32)
+    if grid is None:
+        grid = np.zeros(int(res[0]) * int(res[1]) * int(res[2]), np.uint8)
+    ps = _f32(pose).reshape(16) if pose is not None else None
+    _check(lib().rsgpu_rasterize_points(_ptr(p), len(p), _ptr(ps) if ps is not None else None, _ptr(_f32(origin).reshape(3)), _ptr(res),
+                                        np.float32(voxel), _ptr(grid)))
+    return grid
+
+
+def coverage_masks(objects_lvl2, poses, res, origin, scene_grid, voxel=0.05):
+    """bit masks of the candidate placements over the scan's lit cells -> (masks uint32 [n, n_words], n_lit)"""
+    ps = _f32(poses).reshape(-1, 16)
+    assert len(ps) == len(objects_lvl2)
+    res = np.ascontiguousarray(res, np.int32)
+    sg = np.ascontiguousarray(scene_grid, np.uint8)
+    n_lit = int(np.count_nonzero(sg))
+    n_words = (n_lit + 31) // 32
+    masks = np.zeros((len(ps), n_words), np.uint32)
+    oh = (C.c_void_p * max(len(ps), 1))(*[o.h for o in objects_lvl2])
+    got = C.c_int32(0)
+    _check(lib().rsgpu_coverage_masks(oh, _ptr(ps), len(ps), _ptr(_f32(origin).reshape(3)), _ptr(res), np.float32(voxel), _ptr(sg),
+                                      _ptr(masks) if masks.size else None, n_words, C.byref(got)))
+    assert got.value == n_lit
+    return masks, n_lit
+
+
+def coverage_score(masks, n_lit):
+    """rsao__compute_scene_coverage_score of the arrangement formed by the placements whose masks are given"""
+    if n_lit == 0 or len(masks) == 0:
+        return np.float32(0.0)
+    u = np.bitwise_or.reduce(np.ascontiguousarray(masks, np.uint32), axis=0)
+    agree = int(np.unpackbits(u.view(np.uint8)).sum())
+    return np.float32(agree) / np.float32(n_lit)

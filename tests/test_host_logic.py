@@ -213,3 +213,16 @@ def test_sharding_and_merge_properties():
         merged = pipeline.merge_topk([p[0] for p in parts], [p[1] for p in parts], k)
         assert (merged[1] == whole[1]).all() and (merged[0] == whole[0]).all()
     check()
+
+
+def test_coverage_grid_host_arithmetic_matches_oracle():
+    """api.coverage_grid (isect_grid3d_init in float32 on the host) against the oracle's restatement"""
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        mn = rng.uniform(-5, 5, 3).astype(np.float32)
+        mx = (mn + rng.uniform(0.1, 9, 3)).astype(np.float32)
+        for voxel in (0.05, 0.15, 0.1):
+            res, origin = api.coverage_grid(mn, mx, voxel)
+            ro, oo, _ = O.cov_grid(mn, mx, voxel)
+            assert (res == ro).all() and (origin == oo).all()
+    assert api.coverage_score(np.zeros((0, 3), np.uint32), 10) == 0 and api.coverage_score(np.array([[1, 0], [2, 0]], np.uint32), 4) == np.float32(0.5)

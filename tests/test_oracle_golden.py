@@ -163,3 +163,20 @@ def test_poisson_levels_match_golden():
         pos = g[f"{name}_pos0"]
         for lvl in range(1, 5):
             assert (O.poisson_level(pos, lvl) == g[f"{name}_idx{lvl}"]).all(), (name, lvl)
+
+
+def test_coverage_grids_match_golden():
+    """coverage term: the oracle's grid set-up and rasterisation against tests/golden/coverage_golden.npz
+    (written from the reference's grid primitives by make_golden_coverage.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(common.GOLDEN), "coverage_golden.npz"))
+    for voxel, tag in ((0.05, "v5"), (0.15, "v15")):
+        res, origin, n = O.cov_grid(g["bbox_min"], g["bbox_max"], voxel)
+        assert (res == g[f"{tag}_res"]).all() and (origin == g[f"{tag}_origin"]).all()
+        lit = np.nonzero(O.cov_rasterize(g["scan_pos2"], None, res, origin, voxel))[0]
+        assert (lit == g[f"{tag}_scan_lit"]).all()
+    res, origin, n = O.cov_grid(g["bbox_min"], g["bbox_max"], 0.05)
+    for k in range(int(g["n_poses"][0])):
+        pts = g[f"obj{int(g[f'pose{k}_obj'][0])}_pos2"]
+        lit = np.nonzero(O.cov_rasterize(pts, g[f"pose{k}"], res, origin, 0.05))[0]
+        assert (lit == g[f"pose{k}_lit"]).all(), k

@@ -160,3 +160,24 @@ def test_poisson_levels_against_reference():
         for lvl in range(1, 5):
             want = _match_rows(pos0, rc.level(lvl)[0])
             assert (O.poisson_level(pos0, lvl) == want).all(), lvl
+
+
+def test_coverage_grids_against_reference(S):
+    """coverage term of the arrangement optimiser: grid set-up and rasterisation of the oracle against the
+    reference's own primitives (isect_grid3d_init, msh_mat4_vec3_mul, isect_grid3d_cell_from_world_space)"""
+    scene, _, _ = S
+    mn, mx = scene.scan.pos(0).min(0), scene.scan.pos(0).max(0)
+    for voxel in (0.05, 0.15):
+        ro, oo, no = O.cov_grid(mn, mx, voxel)
+        rr, orr, nr = R.cov_grid(mn, mx, voxel)
+        assert (ro == rr).all() and (oo == orr).all() and no == nr
+        go = O.cov_rasterize(scene.scan.pos(2), None, ro, oo, voxel)
+        gr = R.cov_rasterize(mn, mx, scene.scan.pos(2), None, nr, voxel)
+        assert (go == gr).all() and go.sum() > 100
+        rng = np.random.default_rng(6)
+        for o in scene.objects:
+            d = synth.yaw_pose(rng.uniform(0, 6.28), rng.uniform(-1.5, 1.5), rng.uniform(-1.5, 1.5), rng.uniform(-0.2, 0.2))
+            pose = common.colmajor((d.astype(np.float64) @ o.pose.astype(np.float64)).astype(np.float32))  # some of it leaves the grid
+            ao = O.cov_rasterize(o.cloud.pos(2), pose, ro, oo, voxel)
+            ar = R.cov_rasterize(mn, mx, o.cloud.pos(2), pose, nr, voxel)
+            assert (ao == ar).all()

@@ -12,6 +12,8 @@
 //   rsgpu_rasterize_points   points (optionally posed) -> byte grid        rsao_rasterize_scene_to_grid :1064-1080
 //   rsgpu_coverage_masks     (object, pose) list -> bit masks over the scan's lit cells   rsao__rasterize_arrangement_to_grid :1082-1106
 #include "rsgpu_internal.cuh"
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -52,10 +54,17 @@ struct CovJob
   int n;
 };
 
+struct LitFlag
+{
+  __host__ __device__ int operator()( unsigned char v ) const { return v > 0 ? 1 : 0; }
+};
+
 // one block per placement: its points under its pose light bits of the placement's mask (bit = rank of the cell among
-// the scan's lit cells; cells the scan does not light cannot count towards the score and have no bit)
+// the scan's lit cells = exclusive prefix count of lit cells; cells the scan does not light cannot count towards the
+// score and have no bit)
 __global__ void __launch_bounds__( 256 ) coverage_mask_kernel( const CovJob* __restrict__ jobs, const float* __restrict__ poses, CovGrid g,
-                                                               const int* __restrict__ bit_of_cell, int n_words, unsigned* __restrict__ masks )
+                                                               const unsigned char* __restrict__ scene, const int* __restrict__ rank_of_cell,
+                                                               int n_words, unsigned* __restrict__ masks )
 {
   const CovJob job = jobs[blockIdx.x];
   const float* m = poses + 16 * (size_t)blockIdx.x;
@@ -66,8 +75,9 @@ __global__ void __launch_bounds__( 256 ) coverage_mask_kernel( const CovJob* __r
     xf_apply( m, job.pos[3 * (size_t)i], job.pos[3 * (size_t)i + 1], job.pos[3 * (size_t)i + 2], 1.0f, px, py, pz );
     const long long c = cov_cell( g, px, py, pz );
     if( c < 0 ) { continue; }
-    const int b = bit_of_cell[c];
-    if( b >= 0 ) { atomicOr( mask + ( b >> 5 ), 1u << ( b & 31 ) ); }
+    if( scene[c] == 0 ) { continue; }
+    const int b = rank_of_cell[c];
+    atomicOr( mask + ( b >> 5 ), 1u << ( b & 31 ) );
   }
 }
 
@@ -118,10 +128,23 @@ int rsgpu_coverage_masks( const rsgpu_cloud_t* const* objects, const float* pose
   RS_TRY( ensure_device() );
   CovGrid g; long long n_cells = 0;
   RS_TRY( make_grid( origin, res, voxel, g, n_cells ) );
-  // bit of every cell = its rank among the scan's lit cells, ascending cell index; -1 for the others
-  std::vector<int> bit_of_cell( (size_t)n_cells );
-  int lit = 0;
-  for( long long c = 0; c < n_cells; ++c ) { bit_of_cell[(size_t)c] = scene_grid[c] > 0 ? lit++ : -1; }
+  // bit of every cell = its rank among the scan's lit cells in ascending cell index: an exclusive prefix count on the device
+  cudaStream_t st = rt().stream;
+  DevBuf<unsigned char> d_scene; DevBuf<int> d_rank; DevBuf<unsigned char> d_tmp;
+  RS_CUDA( d_scene.alloc( (size_t)n_cells ) ); RS_CUDA( d_rank.alloc( (size_t)n_cells ) );
+  RS_CUDA( cudaMemcpyAsync( d_scene.p, scene_grid, (size_t)n_cells, cudaMemcpyHostToDevice, st ) );
+  int last_rank = 0;
+  {
+    ProfScope prof( "coverage" );
+    auto flags = thrust::make_transform_iterator( (const unsigned char*)d_scene.p, LitFlag() );
+    size_t tmp_bytes = 0;
+    RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, tmp_bytes, flags, d_rank.p, (int)n_cells, st ) );
+    RS_CUDA( d_tmp.alloc( tmp_bytes ) );
+    RS_CUDA( cub::DeviceScan::ExclusiveSum( d_tmp.p, tmp_bytes, flags, d_rank.p, (int)n_cells, st ) );
+  }
+  RS_CUDA( cudaMemcpyAsync( &last_rank, d_rank.p + ( n_cells - 1 ), sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  RS_CUDA( rs::stream_sync( st ) );
+  const int lit = last_rank + ( scene_grid[n_cells - 1] > 0 ? 1 : 0 );
   *n_lit = lit;
   const int need_words = ( lit + 31 ) / 32;
   if( n_poses == 0 || !out_masks ) { return RSGPU_OK; } // a caller sizing its buffer: n_words = (*n_lit + 31) / 32
@@ -133,17 +156,15 @@ int rsgpu_coverage_masks( const rsgpu_cloud_t* const* objects, const float* pose
     if( !objects[i] ) { return fail( RSGPU_ERR_INVALID, "rsgpu_coverage_masks: NULL object" ); }
     jobs[i].pos = objects[i]->pos.p; jobs[i].n = objects[i]->n;
   }
-  cudaStream_t st = rt().stream;
-  DevBuf<CovJob> d_jobs; DevBuf<float> d_poses; DevBuf<int> d_bits; DevBuf<unsigned> d_masks;
-  RS_CUDA( d_jobs.alloc( n_poses ) ); RS_CUDA( d_poses.alloc( (size_t)n_poses * 16 ) ); RS_CUDA( d_bits.alloc( (size_t)n_cells ) );
+  DevBuf<CovJob> d_jobs; DevBuf<float> d_poses; DevBuf<unsigned> d_masks;
+  RS_CUDA( d_jobs.alloc( n_poses ) ); RS_CUDA( d_poses.alloc( (size_t)n_poses * 16 ) );
   RS_CUDA( d_masks.alloc( (size_t)n_poses * n_words ) );
   RS_CUDA( cudaMemcpyAsync( d_jobs.p, jobs.data(), sizeof( CovJob ) * (size_t)n_poses, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemcpyAsync( d_poses.p, poses, sizeof( float ) * 16 * (size_t)n_poses, cudaMemcpyHostToDevice, st ) );
-  RS_CUDA( cudaMemcpyAsync( d_bits.p, bit_of_cell.data(), sizeof( int ) * (size_t)n_cells, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemsetAsync( d_masks.p, 0, sizeof( unsigned ) * (size_t)n_poses * n_words, st ) );
   {
     ProfScope prof( "coverage" );
-    coverage_mask_kernel<<<(unsigned)n_poses, 256, 0, st>>>( d_jobs.p, d_poses.p, g, d_bits.p, n_words, d_masks.p );
+    coverage_mask_kernel<<<(unsigned)n_poses, 256, 0, st>>>( d_jobs.p, d_poses.p, g, d_scene.p, d_rank.p, n_words, d_masks.p );
     RS_CHECK_LAUNCH();
   }
   RS_CUDA( cudaMemcpyAsync( out_masks, d_masks.p, sizeof( unsigned ) * (size_t)n_poses * n_words, cudaMemcpyDeviceToHost, st ) );

@@ -1,7 +1,10 @@
 """Writes the file set of the drop-in test (a first-scan database + a rescan PLY) into a directory.  With --golden it
 also runs the pure-CPU reference build (integration/_build/pose_proposal_ref) on it and stores the resulting proposal
 .bin as tests/golden/dropin_pp.bin, together with the .rsdb and one object PLY the reference wrote (build container only;
-the .rsdb holds the absolute paths of the folder it was written in, default /tmp/rsgpu_dropin_case)."""
+the .rsdb holds the absolute paths of the folder it was written in, default /tmp/rsgpu_dropin_case), then runs the pure-CPU
+reference build of segment_transfer (integration/_build/segment_transfer_ref, gco replaced by the pass-through stand-in) on
+that output and stores what it decided as tests/golden/dropin_st.npz: the optimised and refined arrangement and the
+per-vertex class / instance labels of the level-1 scan."""
 import os
 import shutil
 import subprocess
@@ -26,6 +29,21 @@ def write_case(folder):
     return db, p1, os.path.join(folder, "scan1_pp.rsdb"), scan1
 
 
+def run_segment_transfer(exe, pp_rsdb, folder):
+    """`segment_transfer <pp.rsdb> -o <folder>/out/scan1_st.rsdb` -> (stdout, arrangement rows of the last scene, labelled level-1 PLY)"""
+    out_dir = os.path.join(folder, "out")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "scan1_st.rsdb")
+    r = subprocess.run([exe, pp_rsdb, "-o", out], capture_output=True, text=True, timeout=1200)
+    if r.returncode != 0:
+        raise RuntimeError(f"{exe} failed ({r.returncode}): {r.stdout[-2000:]}{r.stderr[-2000:]}")
+    db = rsio.read_database(out)
+    last = max(p[1] for p in db["poses"])
+    rows = [p for p in db["poses"] if p[1] == last]
+    ply = rsio.read_ply(os.path.join(out_dir, "predictions", "scan1_st.ply"))
+    return r.stdout, rows, ply
+
+
 def main():
     folder = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "/tmp/rsgpu_dropin_case"
     db, scan, out, _ = write_case(folder)
@@ -39,6 +57,14 @@ def main():
         shutil.copy(out, os.path.join(gold, "dropin_pp.rsdb"))
         shutil.copy(os.path.join(folder, "scan1_pp", "obj_102.ply"), os.path.join(gold, "dropin_obj_102.ply"))
         print("wrote tests/golden/dropin_pp.bin", os.path.getsize(os.path.join(gold, "dropin_pp.bin")), "bytes, dropin_pp.rsdb, dropin_obj_102.ply")
+        exe = os.path.join(ROOT, "integration", "_build", "segment_transfer_ref")
+        _, rows, ply = run_segment_transfer(exe, out, folder)
+        np.savez_compressed(os.path.join(gold, "dropin_st.npz"),
+                            placement_uidx=np.array([r[0] for r in rows], np.int32), object_idx=np.array([r[2] for r in rows], np.int32),
+                            score=np.array([r[3] for r in rows], np.float32), pose=np.stack([r[4] for r in rows]).astype(np.float32),
+                            class_idx=np.asarray(ply["class_idx"], np.int32), instance_idx=np.asarray(ply["instance_idx"], np.int32),
+                            x=np.asarray(ply["x"], np.float32))
+        print("wrote tests/golden/dropin_st.npz:", len(rows), "placements,", len(ply), "labelled vertices")
 
 
 if __name__ == "__main__":

@@ -32,6 +32,38 @@ def test_no_device_fails_loudly():
         api.HashGrid(np.zeros((4, 3), np.float32), 0.05)
 
 
+def test_segment_transfer_dropin_without_device_exits_like_the_reference(tmp_path):
+    """the drop-in executable has no CPU path either: without a device its first replaced call (the scan rasterisation)
+    ends the run with the reference's own exit(-1) and the rsgpu error text"""
+    import subprocess
+    import sys
+    exe = os.path.join(ROOT, "integration", "_build", "segment_transfer_rsgpu")
+    if api.device_count() > 0 or not os.path.exists(exe):
+        pytest.skip("a CUDA device is present, or integration/_build is not built")
+    sys.path.insert(0, os.path.join(ROOT, "integration"))
+    import make_dropin_case
+    from rescan_b200 import rsio
+    folder = str(tmp_path)
+    db, scan, out, scan1 = make_dropin_case.write_case(folder)
+    # a pose_proposal output for that case without running it: scan 1 appended to the first-scan database, golden proposals
+    pp = os.path.join(folder, "scan1_pp")
+    os.makedirs(pp, exist_ok=True)
+    lines = open(db).read().splitlines()
+    text = []
+    for ln in lines:
+        if ln.startswith("model_folder"):
+            ln = "model_folder " + os.path.join(folder, "scan0")
+        text.append(ln)
+        if ln.startswith("scene 0"):
+            text.append(f"scene 1 1 {scan} {os.path.join(pp, 'scan1_pp.bin')} ")
+    open(out, "w").write("\n".join(text) + "\n")
+    import shutil
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "dropin_pp.bin"), os.path.join(pp, "scan1_pp.bin"))
+    r = subprocess.run([exe, out, "-o", os.path.join(folder, "out", "x.rsdb")], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "rsgpu drop-in" in r.stderr and "no CUDA device" in r.stderr
+
+
 def test_product_never_imports_oracle():
     for root, _, files in os.walk(os.path.join(ROOT, "rescan_b200")):
         for f in files:

@@ -17,10 +17,15 @@ sys.path.insert(0, ROOT)
 from rescan_b200 import rsio, synth  # noqa: E402
 
 
-def write_case(folder):
+SMALL = dict(n_objects=3, n_static=1, room=(3.2, 1.6, 2.8), spacing=0.035)
+
+
+def write_case(folder, **scene):
+    """first scan + database and a rescan of the same objects; `scene` = synth.make_scene arguments (default: the small test case)"""
     os.makedirs(folder, exist_ok=True)
-    scan0 = synth.make_scene(n_objects=3, n_static=1, room=(3.2, 1.6, 2.8), spacing=0.035, seed=synth.SEED + 99)
-    scan1 = synth.make_scene(n_objects=3, n_static=1, room=(3.2, 1.6, 2.8), spacing=0.035, seed=synth.SEED + 100, objects=scan0.objects)
+    scene = scene or SMALL
+    scan0 = synth.make_scene(seed=synth.SEED + 99, **scene)
+    scan1 = synth.make_scene(seed=synth.SEED + 100, objects=scan0.objects, **scene)
     p0 = os.path.join(folder, "scan0.ply")
     p1 = os.path.join(folder, "scan1.ply")
     rsio.write_ply(p0, scan0.scan.pos(0), scan0.scan.nor(0), scan0.scan_class, scan0.scan_instance)

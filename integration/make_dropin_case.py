@@ -34,6 +34,24 @@ def write_case(folder, **scene):
     return db, p1, os.path.join(folder, "scan1_pp.rsdb"), scan1
 
 
+def write_pose_proposal_output(folder, db, scan, proposals_bin):
+    """What `pose_proposal <db> <scan> <folder>/scan1_pp.rsdb` leaves behind, without running it: the first-scan database with
+    the rescan appended as scene 1 (rs_database.h:539-611 writes the same lines) and a proposal .bin (copied from
+    `proposals_bin`).  The object models stay where the first-scan database has them.  Returns the .rsdb path."""
+    out = os.path.join(folder, "scan1_pp.rsdb")
+    pp = os.path.join(folder, "scan1_pp")
+    os.makedirs(pp, exist_ok=True)
+    text = []
+    for ln in open(db).read().splitlines():
+        text.append(ln)
+        if ln.startswith("scene 0"):
+            text.append(f"scene 1 1 {scan} {os.path.join(pp, 'scan1_pp.bin')} ")
+    with open(out, "w") as f:
+        f.write("\n".join(text) + "\n")
+    shutil.copy(proposals_bin, os.path.join(pp, "scan1_pp.bin"))
+    return out
+
+
 def run_segment_transfer(exe, pp_rsdb, folder):
     """`segment_transfer <pp.rsdb> -o <folder>/out/scan1_st.rsdb` -> (stdout, arrangement rows of the last scene, labelled level-1 PLY)"""
     out_dir = os.path.join(folder, "out")

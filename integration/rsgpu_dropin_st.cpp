@@ -22,6 +22,7 @@
 #include <cstring>
 #include <cassert>
 #include <map>
+#include <sys/mman.h>
 #include <unordered_set>
 #include <utility>
 #include <vector>
@@ -112,6 +113,21 @@ int32_t placement_cmp( const void* a, const void* b, void* rsdb_ptr )
   const int32_t key_b = ( rsdb_is_object_static( rsdb, pb->object_idx ) ? 1 : 0 ) << 10 | rsdb->objects[pb->object_idx].class_idx;
   return key_a - key_b;
 }
+// A large buffer the device will fill: 2 MB-aligned and advised for transparent huge pages, so that the copy back touches
+// (and the driver pins) tens of pages instead of tens of thousands.  Released with free().  [applied after the last GPU
+// session of round 1: functionally covered by the tests, its effect on the copy time is not measured yet - DESIGN.md 9]
+void* result_buffer( size_t bytes )
+{
+  void* p = NULL;
+  const size_t huge = (size_t)2 << 20;
+  if( bytes < 4 * huge ) { return malloc( bytes ? bytes : 1 ); }
+  if( posix_memalign( &p, huge, ( bytes + huge - 1 ) / huge * huge ) != 0 ) { return malloc( bytes ); }
+#ifdef MADV_HUGEPAGE
+  madvise( p, ( bytes + huge - 1 ) / huge * huge, MADV_HUGEPAGE );
+#endif
+  return p;
+}
+
 rsdb_t* g_sort_rsdb = NULL;
 int placement_cmp_qsort( const void* a, const void* b ) { return placement_cmp( a, b, g_sort_rsdb ); }
 } // namespace
@@ -348,7 +364,7 @@ rspf_smooth_labels( rsdb_t* rsdb, rs_pointcloud_t* in_pc )
   // unary term (:926-939): 0 for the vertex's own label, else 30, 15 when its class is static, 1 when it is unlabelled
   std::vector<uint8_t> label_is_static( n_labels, 0 );
   for( int32_t i = 0; i < n_pts; ++i ) { label_is_static[labels[i]] = rsdb_is_class_static( rsdb, label_to_class[labels[i]] ) ? 1 : 0; }
-  int32_t* data_cost = (int32_t*)malloc( (size_t)n_pts * n_labels * sizeof( int32_t ) );
+  int32_t* data_cost = (int32_t*)result_buffer( (size_t)n_pts * n_labels * sizeof( int32_t ) );
   if( n_pts > 0 ) { RSGPU_OR_DIE( rsgpu_unary_costs( labels.data(), label_is_static.data(), n_pts, n_labels, data_cost ) ); }
   // Potts pairwise term (:941-950)
   const int32_t edge_cost = 10;

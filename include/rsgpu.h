@@ -272,6 +272,15 @@ int rsgpu_coverage_masks( const rsgpu_cloud_t* const* objects, const float* pose
                           const int32_t res[3], float voxel, const uint8_t* scene_grid, uint32_t* out_masks, int32_t n_words,
                           int32_t* n_lit );
 
+/* ---- plane detection of the scan (the stage that bounds segment_transfer once SURVEY.md 8 is on the device) ---------
+   rsgpu_plane_inlier_counts replaces evaluate_plane_model (lib/rs/rs_pointcloud_filters.cpp:117-134) for a whole LIST of
+   candidate planes, i.e. one RANSAC round of rspf__detect_walls / rspf__detect_floor (:137-253): planes = n_planes x
+   {center xyz, normal xyz}; active[i] != 0 <-> weights[i] > 0.01 (points no earlier plane explained); counts[p] = number of
+   active points with |normal . (pt - center)| < dist_threshold in the reference's float arithmetic.  The caller keeps the
+   reference's choice (first candidate with the strictly largest count) and its remove_inliers pass. */
+int rsgpu_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t n_pts, const float* planes, int32_t n_planes, float dist_threshold,
+                               int32_t* counts );
+
 #ifdef __cplusplus
 }
 #endif

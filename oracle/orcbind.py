@@ -63,6 +63,7 @@ def load():
         "orc_cov_rasterize": (None, [_f32p, i32, vp, _f32p, _i32p, f32, _u8p]),
         "orc_cov_score": (f32, [_u8p, _u8p, i32]),
         "orc_neighborhood": (None, [vp, _f32p, _f32p, i32, i32, f32, f32, f32, _i32p, _f32p]),
+        "orc_plane_inlier_counts": (None, [_f32p, _u8p, i32, _f32p, i32, f32, _i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -274,3 +275,13 @@ def cov_rasterize(pts, pose, res, origin, voxel=0.05, grid=None):
 
 def cov_score(scn_grid, arr_grid):
     return float(load().orc_cov_score(np.ascontiguousarray(scn_grid, np.uint8), np.ascontiguousarray(arr_grid, np.uint8), len(scn_grid)))
+
+
+def plane_inlier_counts(pts, active, planes, dist_threshold):
+    """evaluate_plane_model for a list of candidate planes [P, 6] = {center, normal} -> int32 counts [P]"""
+    p = _f32(pts).reshape(-1, 3)
+    a = np.ascontiguousarray(active, np.uint8)
+    pl = _f32(planes).reshape(-1, 6)
+    out = np.zeros(len(pl), np.int32)
+    load().orc_plane_inlier_counts(p.reshape(-1), a, len(p), pl.reshape(-1), len(pl), np.float32(dist_threshold), out)
+    return out

@@ -352,3 +352,22 @@ def cov_rasterize(bbox_min, bbox_max, pts, pose, n_cells, voxel=0.05, grid=None)
     load(False).ref_cov_rasterize(_f32(bbox_min).reshape(3), _f32(bbox_max).reshape(3), np.float32(voxel), p.reshape(-1), len(p),
                                   ps.ctypes.data if ps is not None else None, grid)
     return grid
+
+
+def plane_inlier_counts(pts, weights, planes, dist_threshold):
+    """the reference's own evaluate_plane_model (lib/rs/rs_pointcloud_filters.cpp:117-134, C++ linkage: called through its
+    mangled name) once per candidate plane [P, 6] = {center, normal}; `weights` are the detector's doubles (> 0.01 = active)"""
+    L = load()
+    fn = getattr(L, "_Z20evaluate_plane_modelP16rspf_plane_modelPdP5vec3fmf")
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float]
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    w = np.ascontiguousarray(weights, np.float64)
+    out = np.zeros(len(planes), np.int64)
+    model = np.zeros(512, np.uint8)  # rspf_plane_model_t: plane {center, normal} at byte 0, size_t n_inliers at byte 24
+    for k, pl in enumerate(np.ascontiguousarray(planes, np.float32).reshape(-1, 6)):
+        model[:] = 0
+        model[:24] = pl.view(np.uint8)
+        fn(model.ctypes.data, w.ctypes.data, p.ctypes.data, len(p), np.float32(dist_threshold))
+        out[k] = model[24:32].view(np.uint64)[0]
+    return out

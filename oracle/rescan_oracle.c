@@ -956,3 +956,27 @@ float orc_cov_score( const uint8_t* scn, const uint8_t* arr, int32_t n_cells )
   }
   return valid == 0 ? 0.0f : (float)agree / (float)valid;
 }
+
+/* ------------------------------------------------------------------------------------------------ plane detection */
+/* evaluate_plane_model (lib/rs/rs_pointcloud_filters.cpp:117-134) for a list of candidate planes {center xyz, normal xyz}:
+   counts[p] = number of points with weights[i] > 0.01 (active[i] != 0 here) and |n . (pt - center)| < dist_threshold, the
+   distance as the float expression n.x*d.x + n.y*d.y + n.z*d.z of msh_vec3_dot( n, msh_vec3_sub( pt, center ) ) */
+void orc_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t n, const float* planes, int32_t n_planes, float dist_threshold,
+                              int32_t* counts )
+{
+  for( int32_t p = 0; p < n_planes; ++p )
+  {
+    const float* c = planes + 6 * (size_t)p;
+    const float* nr = c + 3;
+    int32_t cnt = 0;
+    for( int32_t i = 0; i < n; ++i )
+    {
+      if( !active[i] ) { continue; }
+      const float dx = pts[3 * (size_t)i] - c[0], dy = pts[3 * (size_t)i + 1] - c[1], dz = pts[3 * (size_t)i + 2] - c[2];
+      float d = nr[0] * dx + nr[1] * dy + nr[2] * dz;
+      d = d < 0 ? -d : d;
+      if( d < dist_threshold ) { cnt++; }
+    }
+    counts[p] = cnt;
+  }
+}

@@ -113,6 +113,7 @@ SIGNATURES = {
     "rsgpu_rasterize_points": (_int, [_vp, _i32, _vp, _vp, _vp, _f32, _vp]),
     "rsgpu_coverage_masks": (_int, [C.POINTER(_vp), _vp, _i32, _vp, _vp, _f32, _vp, _vp, _i32, C.POINTER(_i32)]),
     "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
+    "rsgpu_plane_inlier_counts": (_int, [_vp, _vp, _i32, _vp, _i32, _f32, _vp]),
 }
 
 
@@ -486,3 +487,16 @@ def coverage_score(masks, n_lit):
     u = np.bitwise_or.reduce(np.ascontiguousarray(masks, np.uint32), axis=0)
     agree = int(np.unpackbits(u.view(np.uint8)).sum())
     return np.float32(agree) / np.float32(n_lit)
+
+
+# ------------------------------------------------------------------------------------------------ plane detection
+def plane_inlier_counts(pts, active, planes, dist_threshold):
+    """evaluate_plane_model (reference lib/rs/rs_pointcloud_filters.cpp:117-134) for one RANSAC round's candidate planes
+    [P, 6] = {center, normal} over the points still active -> int32 counts [P]"""
+    p = _f32(pts).reshape(-1, 3)
+    a = np.ascontiguousarray(active, np.uint8)
+    assert len(a) == len(p)
+    pl = _f32(planes).reshape(-1, 6)
+    out = np.zeros(len(pl), np.int32)
+    _check(lib().rsgpu_plane_inlier_counts(_ptr(p), _ptr(a), len(p), _ptr(pl), len(pl), np.float32(dist_threshold), _ptr(out)))
+    return out

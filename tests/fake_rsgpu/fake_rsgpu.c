@@ -24,6 +24,8 @@ void orc_unary_costs( const int32_t* labels, const uint8_t* label_is_static, int
 void orc_neighborhood( const orc_grid_t* grid, const float* pos, const float* nor, int32_t V, int32_t max_nn, float radius_sq, float dist_exp,
                        float angle_exp, int32_t* nbr, float* weight );
 void orc_cov_rasterize( const float* pts, int32_t n, const float* pose, const float* origin, const int32_t* res, float voxel, uint8_t* grid );
+void orc_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t n, const float* planes, int32_t n_planes, float dist_threshold,
+                              int32_t* counts );
 
 struct rsgpu_grid { orc_grid_t* g; float* pts; float* nor; int32_t n; };
 struct rsgpu_cloud { float* pos; float* nor; int32_t n; };
@@ -142,5 +144,12 @@ int rsgpu_coverage_masks( const rsgpu_cloud_t* const* objects, const float* pose
     }
   }
   free( tmp ); free( rank ); g_calls++;
+  return RSGPU_OK;
+}
+
+int rsgpu_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t n_pts, const float* planes, int32_t n_planes, float dist_threshold,
+                               int32_t* counts )
+{
+  orc_plane_inlier_counts( pts, active, n_pts, planes, n_planes, dist_threshold, counts ); g_calls++;
   return RSGPU_OK;
 }

@@ -50,8 +50,10 @@ def test_segment_transfer_dropin_without_device_exits_like_the_reference(tmp_pat
     assert "rsgpu drop-in" in r.stderr and "no CUDA device" in r.stderr
 
 
-def test_segment_transfer_shim_host_logic_against_cpu_reference(tmp_path):
-    """integration/rsgpu_dropin_st.cpp linked with the reference's unmodified segment_transfer sources and, in place of
+@pytest.mark.parametrize("variant", ["segment_transfer_fake", "segment_transfer_fake_planes"])
+def test_segment_transfer_shim_host_logic_against_cpu_reference(tmp_path, variant):
+    """integration/rsgpu_dropin_st.cpp (and, for the _planes variant, integration/rsgpu_dropin_planes.cpp: the RANSAC rounds of
+    the wall / floor detector drawn first and counted in one call each) linked with the reference's unmodified segment_transfer sources and, in place of
     librsgpu.so, tests/fake_rsgpu (the rsgpu entry points the shim uses, backed by the CPU oracle): the shim's host logic -
     placement order and the two labelling passes, the per-placement mask cache of the coverage term under 25 000 annealing
     moves, edge de-duplication, label maps - must lead to what the pure-CPU reference build decided
@@ -61,7 +63,7 @@ def test_segment_transfer_shim_host_logic_against_cpu_reference(tmp_path):
     if not os.path.isdir("/root/reference/apps/segment_transfer"):
         pytest.skip("needs the reference tree to compile segment_transfer")
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "fake_rsgpu")], stdout=subprocess.DEVNULL)
-    exe = os.path.join(ROOT, "tests", "fake_rsgpu", "_build", "segment_transfer_fake")
+    exe = os.path.join(ROOT, "tests", "fake_rsgpu", "_build", variant)
     sys.path.insert(0, os.path.join(ROOT, "integration"))
     import make_dropin_case
     folder = str(tmp_path)
@@ -69,6 +71,7 @@ def test_segment_transfer_shim_host_logic_against_cpu_reference(tmp_path):
     out = make_dropin_case.write_pose_proposal_output(folder, db, scan, os.path.join(ROOT, "tests", "golden", "dropin_pp.bin"))
     stdout, rows, ply = make_dropin_case.run_segment_transfer(exe, out, folder)
     assert "(GPU)" in stdout  # the shim's replaced stages ran (here on the stand-in)
+    assert ("candidates counted in one call each" in stdout) == variant.endswith("_planes")
     g = np.load(os.path.join(ROOT, "tests", "golden", "dropin_st.npz"))
     assert [r[0] for r in rows] == list(g["placement_uidx"]) and [r[2] for r in rows] == list(g["object_idx"])
     for r, score, pose in zip(rows, g["score"], g["pose"]):

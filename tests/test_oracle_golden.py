@@ -180,3 +180,13 @@ def test_coverage_grids_match_golden():
         pts = g[f"obj{int(g[f'pose{k}_obj'][0])}_pos2"]
         lit = np.nonzero(O.cov_rasterize(pts, g[f"pose{k}"], res, origin, 0.05))[0]
         assert (lit == g[f"pose{k}_lit"]).all(), k
+
+
+def test_plane_inlier_counts_match_golden():
+    """evaluate_plane_model of the reference (tests/golden/make_golden_planes.py) incl. a NaN and a zero normal"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(common.GOLDEN), "planes_golden.npz"))
+    for thr in (0.033, 0.05):
+        got = O.plane_inlier_counts(g["pts"], g["weights"] > 0.01, g["planes"], thr)
+        assert (got == g[f"counts_{int(thr * 1000)}"]).all()
+    assert g["counts_33"][7] == 0 and g["counts_33"][11] == int((g["weights"] > 0.01).sum())

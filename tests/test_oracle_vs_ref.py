@@ -181,3 +181,17 @@ def test_coverage_grids_against_reference(S):
             ao = O.cov_rasterize(o.cloud.pos(2), pose, ro, oo, voxel)
             ar = R.cov_rasterize(mn, mx, o.cloud.pos(2), pose, nr, voxel)
             assert (ao == ar).all()
+
+
+def test_plane_inlier_counts_against_reference(S):
+    """oracle restatement of evaluate_plane_model against the compiled reference on random point triples of the scan"""
+    scene = S[0]
+    p, n = scene.scan.pos(2), scene.scan.nor(2)
+    rng = np.random.default_rng(8)
+    w = (np.abs(n[:, 1]) < 0.2).astype(np.float64)
+    idx = rng.integers(0, len(p), (60, 3))
+    a, b, c = p[idx[:, 0]], p[idx[:, 1]], p[idx[:, 2]]
+    nr = np.cross(b - a, c - a).astype(np.float32)
+    nr = (nr / np.linalg.norm(nr, axis=1, keepdims=True)).astype(np.float32)
+    planes = np.concatenate([a, nr], 1).astype(np.float32)
+    assert (O.plane_inlier_counts(p, w > 0.01, planes, 0.033) == R.plane_inlier_counts(p, w, planes, 0.033)).all()

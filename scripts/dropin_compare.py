@@ -4,7 +4,8 @@ given size, run on the same files in the same call (integration/_build/*, built 
     pose_proposal_rsgpu  first-scan database + rescan  ->  proposals          (GPU; the CPU build takes minutes at this size)
     segment_transfer_rsgpu / segment_transfer_ref on that output  ->  placements, poses, per-vertex labels, stage times
 
-    python scripts/dropin_compare.py [--points 200000] [--objects 10] [--static 2] [--room 7 2.6 5] [--skip-cpu]"""
+    python scripts/dropin_compare.py [--points 200000] [--objects 10] [--static 2] [--room 7 2.6 5] [--skip-cpu]
+                                     [--pp-exe pose_proposal_rsgpu_levels] [--st-exe segment_transfer_rsgpu_all]"""
 import argparse
 import json
 import os
@@ -29,6 +30,8 @@ ap.add_argument("--static", type=int, default=2)
 ap.add_argument("--room", type=float, nargs=3, default=[7.0, 2.6, 5.0])
 ap.add_argument("--folder", default="/tmp/rsgpu_dropin_compare")
 ap.add_argument("--skip-cpu", action="store_true")
+ap.add_argument("--pp-exe", default="pose_proposal_rsgpu", help="or pose_proposal_rsgpu_levels (level building bound as well)")
+ap.add_argument("--st-exe", default="segment_transfer_rsgpu", help="or segment_transfer_rsgpu_planes / segment_transfer_rsgpu_all")
 args = ap.parse_args()
 B = os.path.join(ROOT, "integration", "_build")
 shutil.rmtree(args.folder, ignore_errors=True)
@@ -36,7 +39,7 @@ db, scan, out, scan1 = make_dropin_case.write_case(args.folder, n_objects=args.o
                                                    target_points=args.points)
 row = dict(scan_points=int(scan1.scan.n(0)), objects=args.objects, static=args.static, room=args.room)
 t0 = time.perf_counter()
-r = subprocess.run([os.path.join(B, "pose_proposal_rsgpu"), db, scan, out, "-v"], capture_output=True, text=True, timeout=900)
+r = subprocess.run([os.path.join(B, args.pp_exe), db, scan, out, "-v"], capture_output=True, text=True, timeout=900)
 assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 row["pose_proposal_rsgpu_wall_s"] = time.perf_counter() - t0
 row["proposals_per_object"] = [len(p) for p in rsio.read_proposals(os.path.join(args.folder, "scan1_pp", "scan1_pp.bin"))]
@@ -51,7 +54,8 @@ def stages(stdout):
 
 
 results = {}
-for arm, exe in (("gpu", "segment_transfer_rsgpu"), ("cpu", "segment_transfer_ref")):
+row["executables"] = [args.pp_exe, args.st_exe]
+for arm, exe in (("gpu", args.st_exe), ("cpu", "segment_transfer_ref")):
     if arm == "cpu" and args.skip_cpu:
         continue
     sub = os.path.join(args.folder, arm)

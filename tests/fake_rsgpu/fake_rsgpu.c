@@ -24,6 +24,7 @@ void orc_unary_costs( const int32_t* labels, const uint8_t* label_is_static, int
 void orc_neighborhood( const orc_grid_t* grid, const float* pos, const float* nor, int32_t V, int32_t max_nn, float radius_sq, float dist_exp,
                        float angle_exp, int32_t* nbr, float* weight );
 void orc_cov_rasterize( const float* pts, int32_t n, const float* pose, const float* origin, const int32_t* res, float voxel, uint8_t* grid );
+int32_t orc_poisson_level( const float* pos0, int32_t n, float voxel, int32_t level, int32_t* out_idx );
 void orc_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t n, const float* planes, int32_t n_planes, float dist_threshold,
                               int32_t* counts );
 
@@ -151,5 +152,16 @@ int rsgpu_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t 
                                int32_t* counts )
 {
   orc_plane_inlier_counts( pts, active, n_pts, planes, n_planes, dist_threshold, counts ); g_calls++;
+  return RSGPU_OK;
+}
+
+int rsgpu_poisson_level( const float* pts, int32_t n, float voxel, int32_t max_n_neigh, int32_t* out_indices, int32_t* n_out, int32_t* n_rounds )
+{
+  /* the oracle takes the level and derives max_n_neigh = 1024 * level / 4 itself (rs_pointcloud.h:994-995) */
+  const int32_t level = max_n_neigh / 256;
+  if( level < 1 || level > 4 || level * 256 != max_n_neigh ) { return RSGPU_ERR_INVALID; }
+  *n_out = orc_poisson_level( pts, n, voxel, level, out_indices );
+  if( n_rounds ) { *n_rounds = 0; }
+  g_calls++;
   return RSGPU_OK;
 }

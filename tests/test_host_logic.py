@@ -50,10 +50,11 @@ def test_segment_transfer_dropin_without_device_exits_like_the_reference(tmp_pat
     assert "rsgpu drop-in" in r.stderr and "no CUDA device" in r.stderr
 
 
-@pytest.mark.parametrize("variant", ["segment_transfer_fake", "segment_transfer_fake_planes"])
+@pytest.mark.parametrize("variant", ["segment_transfer_fake", "segment_transfer_fake_planes", "segment_transfer_fake_all"])
 def test_segment_transfer_shim_host_logic_against_cpu_reference(tmp_path, variant):
     """integration/rsgpu_dropin_st.cpp (and, for the _planes variant, integration/rsgpu_dropin_planes.cpp: the RANSAC rounds of
-    the wall / floor detector drawn first and counted in one call each) linked with the reference's unmodified segment_transfer sources and, in place of
+    the wall / floor detector drawn first and counted in one call each; for _all also integration/rsgpu_dropin_levels.cpp: level
+    building at its call site) linked with the reference's unmodified segment_transfer sources and, in place of
     librsgpu.so, tests/fake_rsgpu (the rsgpu entry points the shim uses, backed by the CPU oracle): the shim's host logic -
     placement order and the two labelling passes, the per-placement mask cache of the coverage term under 25 000 annealing
     moves, edge de-duplication, label maps - must lead to what the pure-CPU reference build decided
@@ -71,7 +72,8 @@ def test_segment_transfer_shim_host_logic_against_cpu_reference(tmp_path, varian
     out = make_dropin_case.write_pose_proposal_output(folder, db, scan, os.path.join(ROOT, "tests", "golden", "dropin_pp.bin"))
     stdout, rows, ply = make_dropin_case.run_segment_transfer(exe, out, folder)
     assert "(GPU)" in stdout  # the shim's replaced stages ran (here on the stand-in)
-    assert ("candidates counted in one call each" in stdout) == variant.endswith("_planes")
+    assert ("candidates counted in one call each" in stdout) == (variant != "segment_transfer_fake")
+    assert ("selected by rsgpu_poisson_level" in stdout) == variant.endswith("_all")
     g = np.load(os.path.join(ROOT, "tests", "golden", "dropin_st.npz"))
     assert [r[0] for r in rows] == list(g["placement_uidx"]) and [r[2] for r in rows] == list(g["object_idx"])
     for r, score, pose in zip(rows, g["score"], g["pose"]):

@@ -12,7 +12,8 @@
 // drawing them first and counting afterwards visits the same candidates in the same order; counts are integers computed with
 // the reference's float expression, so the chosen planes are the reference's.
 // STATUS: host logic verified on the CPU tier against the pure-CPU build (tests/test_host_logic.py, oracle-backed stand-in);
-// the CUDA entry point is checked against the oracle by tests/test_gpu_zplanes.py.
+// the CUDA entry point matches the reference's golden vectors and the oracle on a B200 (tests/test_gpu_zplanes.py); this
+// object itself has not run on a GPU yet.
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>

@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """bench.py — pose evaluations/s of the GPU pose_proposal hot path (BASELINE.json metric) on synthetic scans.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one pass of the hot path over one scan (rescan_b200.pipeline.run_step): grid builds, dense pose
-search (level 4) + verification (levels 3, 2) for every dynamic object, ICP refinement of the per-object top-k
-and rescoring at level 1.  `value` times it with the scan resident in HBM; `e2e` times the same step through the
-host-buffer C ABI (scan uploaded from pinned host memory and proposals read back every step).  N > 1 is weak
-scaling: every rank gets its own `n_seeds` translation seeds of the same scan; the only exchanges are the
-all-gathers of per-object top-k lists.  Rank 0 prints ONE JSON line.
+Workloads (BASELINE.json configs):
+  C2 (default at N = 1)  ~200 K-point scan, 10 objects, 36 rotations x 2 048 translation seeds, one GPU.
+  C3 (default at N > 1)  ~2 M-point scan, 60 objects, 72 rotations x 20 000 seeds: ONE fixed problem whose translation
+                         seeds are sharded over the N ranks (reference loop apps/pose_proposal/pose_proposal.cpp:213-243)
+                         => "scaling": "strong".  The line also carries the same problem run by rank 0 alone
+                         (`single_gpu_same_workload`), so the scaling of THIS workload can be read from one line.
+  C5 (--workload C5)     NN-search microbenchmark, the HBM-bound regime of the same gather: 10 M scene points, r = 0.10 m,
+                         k = 64, 4 M queries (msh_hash_grid_radius_search, lib/msh/msh_hash_grid.h:1090-1259); metric =
+                         NN queries/s, queries sharded over the ranks.
+
+One pose step = one pass of the hot path over one scan (rescan_b200.pipeline.run_step): grid builds, dense pose search
+(level 4) + verification (levels 3, 2) for every dynamic object, NMS, ICP refinement of the survivors and rescoring at
+level 1, NMS, sort.  `value` times it with the scan resident in HBM; `e2e` times the same step through the host-buffer
+C ABI (scan uploaded from pinned host memory and proposals read back every step).  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -28,28 +36,39 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pose_evaluations_per_sec"
 UNIT = "pose evaluations/s"
+NN_METRIC = "nn_queries_per_sec"
+NN_UNIT = "NN queries/s"
 L2_FLUSH_BYTES = 256 << 20
+C5 = dict(points=10_000_000, radius=0.10, k=64, queries=4_000_000, room=(20.0, 2.8, 15.0))
 
 
-def workload_config(name, world, nms=True, exchange="host"):
+def resolve_workload(args, world):
+    """N = 1: the configuration the metric is quoted on (C2); N > 1: the multi-GPU configuration BASELINE.json names (C3)"""
+    if args.workload:
+        return args.workload
+    return "C2" if max(world, args.gpus) <= 1 else "C3"
+
+
+def workload_config(name, world, nms=True, exchange="nvlink", scaling="strong"):
     from rescan_b200 import synth
     cfg = synth.CONFIGS[name]
     sc = cfg["scene"]
+    total = cfg["n_seeds"] * (world if scaling == "weak" else 1)
     return {"workload": f"{name}: pose_proposal on one synthetic scene pair", "scan_points_target": sc.get("target_points"),
             "objects": sc["n_objects"], "static_objects": sc["n_static"], "rotations": cfg["n_rot"],
-            "translation_seeds_per_gpu": cfg["n_seeds"], "translation_seeds_total": cfg["n_seeds"] * world,
+            "translation_seeds_total": total, "translation_seeds_per_gpu": -(-total // world),
             "top_k": 64, "parallelism": f"pose-sharded x{world}", "exchange": exchange if world > 1 else None,
             "stages": "grid build, dense search lvl 4, verification lvl 3/2, top-k" + (", NMS" if nms else "") + ", ICP, rescoring lvl 1"
                       + (", NMS" if nms else "") + ", sort",
             "l2": "flushed between steps (256 MiB write inside the timed region); working set is L2-resident within a step"}
 
 
-def build_workload(name, world):
+def build_workload(name, world, scaling="strong"):
     from rescan_b200 import synth, posegrid
     cfg = synth.CONFIGS[name]
     scene = synth.make_scene(**cfg["scene"])
     rotations = posegrid.rotation_xforms(cfg["n_rot"])
-    translations = synth.translation_seeds(scene.scan, cfg["n_seeds"] * world)
+    translations = synth.translation_seeds(scene.scan, cfg["n_seeds"] * (world if scaling == "weak" else 1))
     return scene, rotations, translations
 
 
@@ -99,15 +118,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def dense_kernel_traffic():
-    """DRAM bytes (read + write) of ONE dense-scoring launch from the committed ncu --set full capture of the same
-    kernel on the same workload (profiles/dense_kernel_traffic.json; bench.py itself never runs under a profiler)"""
-    p = os.path.join(ROOT, "profiles", "dense_kernel_traffic.json")
+def kernel_counters(key):
+    """per-launch hardware counters of one kernel on one workload from the committed ncu --set full capture
+    (profiles/kernel_counters.json, written by scripts/ncu_counters.py from the .ncu-rep named in its `source`; bench.py
+    itself never runs under a profiler)"""
+    p = os.path.join(ROOT, "profiles", "kernel_counters.json")
     try:
-        d = json.load(open(p))
-        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source", "profiles/dense_kernel_traffic.json")
+        return json.load(open(p)).get(key)
     except Exception:
-        return None, None
+        return None
 
 
 def measured_peaks():
@@ -129,7 +148,8 @@ def cpu_reference_rate(scene, rotations, translations, target_seconds, threads=N
     from rescan_b200 import posegrid
     threads = threads or os.cpu_count() or 1
     dyn = [o for o in scene.objects if not o.is_static]
-    grid = posegrid.pose_grid(rotations, translations).reshape(-1, 16)
+    n_rot, n_tr = len(rotations), len(translations)
+    n_grid = n_rot * n_tr
     use_ref = refbind.available(openmp=True)
     if use_ref:
         scan = refbind.RefCloud.from_levels({l: (scene.scan.pos(l), scene.scan.nor(l)) for l in range(5)}, openmp=True)
@@ -142,13 +162,18 @@ def cpu_reference_rate(scene, rotations, translations, target_seconds, threads=N
 
         def run(oi, x):
             return orcbind.score_poses(dyn[oi].cloud.pos(4), dyn[oi].cloud.nor(4), og, scene.scan.nor(1), x, 64, 0.10, threads)[1]
+
+    def poses(ids):  # pose id = t * n_rot + r, formed like posegrid.pose_grid without materialising the whole grid
+        x = np.ascontiguousarray(rotations[ids % n_rot].reshape(-1, 16).copy())
+        x[:, 12:15] = translations[ids // n_rot]
+        return x
     # pilot to size the sample
-    pilot = grid[:: max(1, len(grid) // 64)][:64]
+    pilot = poses(np.arange(0, n_grid, max(1, n_grid // 64))[:64])
     t = sum(run(oi, pilot) for oi in range(len(dyn)))
     rate = len(pilot) * len(dyn) / max(t, 1e-6)
-    per_obj = int(min(len(grid), max(64, rate * target_seconds / len(dyn))))
-    stride = max(1, len(grid) // per_obj)
-    sample = np.ascontiguousarray(grid[::stride][:per_obj])
+    per_obj = int(min(n_grid, max(16, rate * target_seconds / len(dyn))))
+    stride = max(1, n_grid // per_obj)
+    sample = poses(np.arange(0, n_grid, stride)[:per_obj])
     times = []
     for s in range(warmup + steps):
         t = sum(run(oi, sample) for oi in range(len(dyn)))
@@ -161,16 +186,180 @@ def cpu_reference_rate(scene, rotations, translations, target_seconds, threads=N
     return n_eval / (sum(times) / len(times)), info, times
 
 
+def surface_cloud(n, rng, room, noise=0.001):
+    """C5 scene: points uniform on the six faces of a room with 1 mm Gaussian noise"""
+    X, Y, Z = room
+    areas = np.array([X * Z, X * Z, X * Y, X * Y, Y * Z, Y * Z])
+    face = rng.choice(6, size=n, p=areas / areas.sum())
+    u, v = rng.random(n), rng.random(n)
+    p = np.zeros((n, 3))
+    for f, (fix_axis, fix_val, a, b) in enumerate([(1, 0.0, 0, 2), (1, Y, 0, 2), (2, 0.0, 0, 1), (2, Z, 0, 1), (0, 0.0, 1, 2), (0, X, 1, 2)]):
+        m = face == f
+        p[m, fix_axis] = fix_val
+        p[m, a] = u[m] * room[a]
+        p[m, b] = v[m] * room[b]
+    p += rng.normal(0.0, noise, p.shape)
+    return np.ascontiguousarray(p, np.float32)
+
+
+def c5_inputs(n_points=None, n_queries=None):
+    rng = np.random.default_rng(20191027)
+    n, nq, r = n_points or C5["points"], n_queries or C5["queries"], C5["radius"]
+    cloud = surface_cloud(n, rng, C5["room"])
+    q = cloud[rng.integers(0, n, nq)] + rng.uniform(-r / 2, r / 2, (nq, 3)).astype(np.float32)
+    return cloud, np.ascontiguousarray(q, np.float32)
+
+
+def c5_config(world, n_points, n_queries):
+    return {"workload": "C5: NN-search microbenchmark (msh_hash_grid_radius_search)", "scene_points": n_points, "radius_m": C5["radius"],
+            "k": C5["k"], "queries_total": n_queries, "queries_per_gpu": -(-n_queries // world), "sort": 1,
+            "parallelism": f"query-sharded x{world}", "exchange": None,
+            "l2": "inputs larger than L2: 160 MB of records + 48 MB of queries + 2 GB of result rows per launch"}
+
+
+def cpu_nn_rate(cloud, queries, target_seconds, steps=1, warmup=0):
+    """the reference's own msh_hash_grid_radius_search (its OpenMP query loop, all host cores) on a bounded query sample"""
+    from oracle import refbind, orcbind
+    r32 = np.float32(C5["radius"])
+    threads = os.cpu_count() or 1
+    use_ref = refbind.available(openmp=True)
+    if use_ref:
+        g = refbind.RefGrid(cloud, r32, openmp=True)
+        run = lambda qs: g.radius_search(qs, float(r32), C5["k"])
+    else:
+        g = orcbind.OrcGrid(cloud, float(r32))
+        run = lambda qs: g.radius_search(qs, float(r32), C5["k"])
+    t0 = time.perf_counter()
+    run(queries[:2000])
+    rate = 2000 / max(time.perf_counter() - t0, 1e-6)
+    n = int(min(len(queries), max(2000, rate * target_seconds)))
+    qs = np.ascontiguousarray(queries[:n])
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        run(qs)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    info = {"cores": threads if use_ref else 1, "kind": "reference" if use_ref else "port",
+            "sample": f"the first {n} of the {len(queries)} queries per step, msh_hash_grid_radius_search k = {C5['k']}, r = {C5['radius']}"
+                      + (", its own OpenMP query loop" if use_ref else "")}
+    return n / (sum(times) / len(times)), info, times
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    scene, rotations, translations = build_workload(args.workload, 1)
-    rate, info, times = cpu_reference_rate(scene, rotations, translations, target_seconds=8.0, steps=args.steps, warmup=args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, 1),
-            "cpu_baseline": dict(info, value=rate, unit=UNIT),
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    name = resolve_workload(args, world)
+    if name == "C5":
+        cloud, q = c5_inputs(args.c5_points, args.c5_queries)
+        rate, info, times = cpu_nn_rate(cloud, q, target_seconds=6.0, steps=args.steps, warmup=args.warmup)
+        metric, unit, cfg = NN_METRIC, NN_UNIT, c5_config(max(world, 1), len(cloud), len(q))
+    else:
+        scene, rotations, translations = build_workload(name, 1)
+        rate, info, times = cpu_reference_rate(scene, rotations, translations, target_seconds=8.0, steps=args.steps, warmup=args.warmup)
+        metric, unit, cfg = METRIC, UNIT, workload_config(name, max(world, 1))
+    line = {"impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": dict(info, value=rate, unit=unit),
+            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ C5: NN search
+def run_nn_workload(args, rank, world, local_rank, device, dist):
+    """query-sharded radius search, no collective on the data path: every rank holds the whole grid"""
+    import torch
+    from rescan_b200 import api, pipeline
+    cloud, q_all = c5_inputs(args.c5_points, args.c5_queries)
+    lo, hi = pipeline.shard_range(len(q_all), rank, world)
+    q = np.ascontiguousarray(q_all[lo:hi])
+    nq, k, r32 = len(q), C5["k"], float(np.float32(C5["radius"]))
+    grid = api.HashGrid(cloud, np.float32(r32))
+    dq = torch.from_numpy(q).to(device)
+    d2 = torch.empty((nq, k), dtype=torch.float32, device=device)
+    idx = torch.empty((nq, k), dtype=torch.int32, device=device)
+    nn = torch.empty(nq, dtype=torch.int64, device=device)
+    hq = torch.from_numpy(q).pin_memory()
+    h_d2 = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    h_idx = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    h_nn = torch.empty(nq, dtype=torch.int64).pin_memory()
+    nB, nC = grid.search_census_dev(dq.data_ptr(), nq, r32)  # exact algorithmic cell / candidate counts, untimed
+    totals = []
+
+    def step(resident):
+        if resident:
+            totals.append(grid.radius_search_dev(dq.data_ptr(), nq, r32, k, d2.data_ptr(), idx.data_ptr(), nn.data_ptr()))
+        else:  # host buffers through the C ABI: queries uploaded, result rows copied back
+            totals.append(grid.radius_search_host(hq.numpy(), r32, k, h_d2.numpy(), h_idx.numpy(), h_nn.numpy()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(resident)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = api.launch_count()
+    api.profile_reset()
+    api.profile_enable(True)
+    ms_value = timed(True, args.steps)
+    api.profile_enable(False)
+    launches = api.launch_count() - l0
+    kern_ms, kern_launches = api.profile_get("search")
+    hits = totals[-1]
+    step(False)
+    ms_e2e = timed(False, args.steps)
+    clk = clocks.stop()
+
+    def total(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+    nq_all, launches_all = total(nq), total(launches)
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    bytes_alg = 12 * nq + 8 * nB + 16 * nC + 8 * hits + 8 * nq  # SURVEY.md 8d, no early-out credit, this rank's shard
+    avg_ms = kern_ms / max(kern_launches, 1)
+    achieved = bytes_alg / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    ctr = kernel_counters("C5:radius_search") or {}
+    traffic = ctr.get("dram_bytes")
+    line = {"metric": NN_METRIC, "value": nq_all * args.steps / (ms_value * 1e-3), "unit": NN_UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": c5_config(world, len(cloud), len(q_all)),
+            "e2e": {"value": nq_all * args.steps / (ms_e2e * 1e-3), "unit": NN_UNIT, "h2d_bytes_per_step": 12 * nq_all,
+                    "d2h_bytes_per_step": (8 * k + 8) * nq_all, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "kernel": "radius_search_kernel (warp per query, k-list in registers)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_frac_of_peak": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic and avg_ms > 0 else None,
+                         "traffic_source": ctr.get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
+                         "launches_timed": kern_launches, "avg_launch_ms": avg_ms,
+                         "cells_per_query": nB / nq, "candidates_per_query": nC / nq, "hits_per_query": hits / nq,
+                         "note": "algorithmic bytes = 12 (query) + 8/cell + 16/candidate point + 8/returned neighbour + 8 per query "
+                                 "(SURVEY.md 8d, no early-out credit), rank 0 shard; traffic = dram__bytes_read + dram__bytes_write of one launch "
+                                 "from the committed ncu capture of the same launch"},
+            "clocks": clk}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, info, _ = cpu_nn_rate(cloud, q_all, target_seconds=10.0)
+        line["cpu_baseline"] = dict(info, value=rate, unit=NN_UNIT)
     print(json.dumps(line), flush=True)
 
 
@@ -181,13 +370,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default=None, help="C2 | C3 | C5 (default: C2 at N = 1, C3 at N > 1)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the named problem split over the ranks (default); weak = every rank gets the named number of seeds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same problem on rank 0")
     ap.add_argument("--lanes", type=int, default=None, help="objects in flight at once (default RSGPU_LANES or 8); 1 = serial object loop")
-    ap.add_argument("--exchange", default="host", choices=["host", "nccl"],
-                    help="N > 1: transport of the two per-step list exchanges (host = gloo all-gather of the host-resident lists; "
-                         "nccl = staged through HBM, NCCL all-gather)")
+    ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "host", "nccl"],
+                    help="N > 1: transport of the two per-step list exchanges (nvlink = peer-mapped slots written over NVLink by copy "
+                         "engines, no SM; host = gloo all-gather of the host-resident lists; nccl = staged through HBM, NCCL all-gather)")
     ap.add_argument("--nms", type=int, default=1, help="1: the two NMS passes of main.cpp:161/205 run on the GPU inside the step; 0: top-k only")
+    ap.add_argument("--c5-points", type=int, default=None)
+    ap.add_argument("--c5-queries", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -206,20 +400,39 @@ def main():
     torch.cuda.set_device(local_rank)
     api.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    host_group = None
+    name = resolve_workload(args, world)
+    host_group, peer = None, None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+    if name == "C5":
+        run_nn_workload(args, rank, world, local_rank, device, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    exchange_name = None
+    if world > 1:
+        if args.exchange == "nvlink":
+            try:
+                from rescan_b200 import peerx
+                peer = peerx.PeerExchange(dist, rank, world, local_rank)
+                exchange_name = "nvlink (peer-mapped slots, copy engines; rescan_b200/peerx.py)"
+            except Exception as e:
+                print(f"bench.py: peer exchange unavailable ({e}); falling back to the host exchange", file=sys.stderr)
+                args.exchange = "host"
         if args.exchange == "host":
             # the per-object top-k lists are host-resident and a few KB: exchanged over a gloo group next to the NCCL one
             try:
                 os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
                 host_group = dist.new_group(backend="gloo")
+                exchange_name = "host (gloo)"
             except Exception as e:  # no usable host transport: NCCL carries the lists (staged through HBM)
                 print(f"bench.py: gloo group unavailable ({e}); exchanging over NCCL", file=sys.stderr)
                 host_group = None
+        if exchange_name is None:
+            exchange_name = "nccl"
 
-    scene, rotations, translations = build_workload(args.workload, world)
+    scene, rotations, translations = build_workload(name, world, args.scaling)
     models = pipeline.upload_objects(scene.objects)
     p1, n1 = scene.scan.pos(1), scene.scan.nor(1)
     p2, n2 = scene.scan.pos(2), scene.scan.nor(2)
@@ -230,11 +443,14 @@ def main():
     hp = {k: v.numpy() for k, v in pinned.items()}
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
 
-    def step(resident, lanes=None):
+    def step(resident, lanes=None, alone=False):
         flush.zero_()
-        return pipeline.run_step((hp["p1"], hp["n1"]), (hp["p2"], hp["n2"]), models, rotations, translations, top_k=64, rank=rank,
-                                 world=world, dist=dist if world > 1 else None, device=device, scan_dev=scan_dev if resident else None,
-                                 nms_dist=0.2 if args.nms else None, lanes=args.lanes if lanes is None else lanes, host_group=host_group)
+        solo = alone or world == 1
+        return pipeline.run_step((hp["p1"], hp["n1"]), (hp["p2"], hp["n2"]), models, rotations, translations, top_k=64,
+                                 rank=0 if solo else rank, world=1 if solo else world, dist=None if solo else dist, device=device,
+                                 scan_dev=scan_dev if resident else None, nms_dist=0.2 if args.nms else None,
+                                 lanes=args.lanes if lanes is None else lanes, host_group=None if solo else host_group,
+                                 peer=None if solo else peer)
 
     def barrier():
         if world > 1:
@@ -253,13 +469,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), res
 
-    # algorithmic bytes of the dominant kernel (dense level-4 scoring), exact census on this rank's shard, untimed
+    # algorithmic bytes of the dense level-4 scoring (what the reference's search reads for the same poses), exact census on
+    # this rank's shard, untimed; big pose grids are counted on every `cstride`-th translation and scaled
     lo, hi = pipeline.shard_range(len(translations), rank, world)
+    cstride = max(1, (hi - lo) // 2048)
     g1 = api.HashGrid(p1, 0.05, normals=n1)
-    census = [api.score_pose_grid_count(m.levels[4], g1, rotations, translations[lo:hi]) for m in models if not m.is_static]
+    census = [api.score_pose_grid_count(m.levels[4], g1, rotations, np.ascontiguousarray(translations[lo:hi:cstride])) for m in models if not m.is_static]
     g1.close()
-    dense_bytes = sum(c["bytes"] for c in census)
-    dense_queries = sum(c["queries"] for c in census)
+    cscale = (hi - lo) / max(len(range(lo, hi, cstride)), 1)
+    dense_bytes = sum(c["bytes"] for c in census) * cscale
+    dense_queries = sum(c["queries"] for c in census) * cscale
 
     for _ in range(args.warmup):
         step(True)
@@ -271,14 +490,15 @@ def main():
     for _ in range(1):
         step(False)
     ms_e2e, res_e2e = timed(False, args.steps)
-    # per-kernel device times for the roofline line: the same steps with ONE object in flight, so that the CUDA-event
-    # interval around a launch (taken on its launch stream) is that kernel's own duration and not a share of the device
+    # per-kernel device times: the same steps with ONE object in flight, so that the CUDA-event interval around a launch
+    # (taken on its launch stream) is that kernel's own duration and not a share of the device
     api.profile_reset()
     api.profile_enable(True)
-    ms_serial, _ = timed(True, args.steps, lanes=1)
+    ms_serial, _ = timed(True, max(1, min(args.steps, 2 if name == "C3" else args.steps)), lanes=1)
     api.profile_enable(False)
-    dense_ms, dense_launches = api.profile_get("score_dense")
-    prof = {n: api.profile_get(n) for n in ("grid_build", "score_dense", "score", "icp", "overlap")}  # ms over those steps, launches
+    n_prof_steps = max(1, min(args.steps, 2 if name == "C3" else args.steps))
+    prof_names = ("grid_build", "score_dense", "dense_prefilter", "dense_bin", "dense_search", "dense_reduce", "score", "icp", "overlap", "nms")
+    prof = {n: api.profile_get(n) for n in prof_names}  # ms over those steps, launches
     clk = clocks.stop()
 
     def total(x):
@@ -294,36 +514,76 @@ def main():
     d2h = total(sum(r.d2h_bytes for r in res_e2e)) / args.steps
     launches_all = total(launches)
 
+    # N > 1: the same fixed problem on ONE GPU (rank 0 alone, the other ranks wait), so that the scaling of this workload
+    # can be read from this line whatever workload the N = 1 run of the driver uses
+    single = None
+    if world > 1 and not args.no_single:
+        if rank == 0:
+            step(True, alone=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rs = [step(True, alone=True) for _ in range(2)]
+            e1.record()
+            torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1)
+            single = {"n_gpus": 1, "steps": 2, "warmup": 1, "ms_per_step": ms1 / 2,
+                      "value": sum(r.n_evaluations for r in rs) / (ms1 * 1e-3), "unit": UNIT}
+        barrier()
+
     if rank == 0:
         peak, peak_src = measured_peaks()
-        traffic, traffic_src = dense_kernel_traffic()
-        steps_dense_bytes = dense_bytes * args.steps
-        achieved = steps_dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
+        dense_ms, dense_launches = prof["score_dense"]
+        per_step_alg = dense_bytes
+        alg_tput = per_step_alg * n_prof_steps / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
+        ctr = kernel_counters(f"{name}:dense_search") or kernel_counters("C2:dense_search") or {}
+        sm_mhz = (clk.get("sm_mhz") or 1965.0)
+        issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions/s: 4 schedulers per SM, one instruction per cycle each
+        avg_launch_ms = dense_ms / max(dense_launches, 1)
+        inst = ctr.get("inst_executed")  # warp instructions of the dense launches of ONE step, from the committed ncu capture
+        inst_rate = (inst * n_prof_steps / (dense_ms * 1e-3) / 1e9) if inst and dense_ms > 0 else None
+        traffic = ctr.get("dram_bytes")
         line = {"metric": METRIC, "value": evals / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world, bool(args.nms),
-                                                                          "host (gloo)" if host_group is not None else "nccl"),
+                "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+                "scaling": args.scaling if world > 1 else "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(name, world, bool(args.nms), exchange_name, args.scaling),
                 "nn_queries_per_sec": queries / (ms_value * 1e-3),
+                "nn_queries_note": "object points of evaluated poses (the reference searches every one); most are answered by the "
+                                   "block-cone prefilter without a search",
                 "e2e": {"value": evals_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_all),
-                "roofline": {"bound": "hbm", "kernel": "score_kernel_g<GRID> (dense level-4 pose scoring)", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": dense_bytes / max(len(census), 1),
-                             "launches_timed": dense_launches, "timed_in": "a separate pass of the same steps with one object in flight (lanes=1)", "avg_launch_ms": dense_ms / max(dense_launches, 1),
-                             "dense_nn_queries_per_sec": dense_queries * args.steps / (dense_ms * 1e-3) if dense_ms > 0 else 0.0,
-                             "note": "algorithmic bytes = what the reference's search reads for the same poses: 8B/cell + 16B/point + "
-                                     "12B/normal per query + 68B/pose (SURVEY.md 8d, no early-out credit), rank 0 shard. The kernel "
-                                     "prunes cells by distance and normal cone and skips poses that cannot pass the level threshold, "
-                                     "and the 5 MB working set is L2/L1-resident (traffic = DRAM bytes of one launch), so achieved "
-                                     "exceeds the HBM peak: it is an algorithmic-throughput figure, not DRAM utilisation"},
-                "kernel_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()}, step_one_object_in_flight=ms_serial / args.steps),
+                "roofline": {"bound": "issue", "kernel": "dense level-4 pose scoring (prefilter + bin + cell-staged search + reduce)",
+                             "achieved": inst_rate, "peak": issue_peak, "unit": "G warp-inst/s",
+                             "frac": (inst_rate / issue_peak) if inst_rate else None,
+                             "traffic": traffic, "counters_source": ctr.get("source"),
+                             "hbm": {"peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                                     "achieved_from_measured_traffic": (traffic * n_prof_steps / (dense_ms * 1e-3) / 1e9) if traffic and dense_ms > 0 else None,
+                                     "frac": (traffic * n_prof_steps / (dense_ms * 1e-3) / 1e9 / peak) if traffic and dense_ms > 0 else None},
+                             "algorithmic_throughput": alg_tput, "algorithmic_throughput_unit": "GB/s",
+                             "algorithmic_bytes_per_step": per_step_alg, "census_stride": cstride,
+                             "launches_timed": dense_launches, "timed_in": "a separate pass of the same steps with one object in flight (lanes=1)",
+                             "avg_launch_ms": avg_launch_ms, "dense_ms_per_step": dense_ms / n_prof_steps,
+                             "dense_nn_queries_per_sec": dense_queries * n_prof_steps / (dense_ms * 1e-3) if dense_ms > 0 else 0.0,
+                             "note": "The dense search is not HBM-bound on this workload: its working set (grid + cone tables) is "
+                                     "L2-resident, so the bound it is held against is the SM issue rate (warp instructions of one step "
+                                     "from the committed ncu capture / measured time / (148 SMs x 4 schedulers x SM clock)); hbm.frac is the "
+                                     "measured DRAM traffic against the copy peak.  algorithmic_throughput = what the reference's search "
+                                     "reads for the same poses (8 B/cell + 16 B/point + 12 B/normal per query + 68 B/pose, SURVEY.md 8d, no "
+                                     "early-out credit) per second: a work rate, not a bandwidth (the kernel prunes).  The HBM-bound regime "
+                                     "of the same gather is `bench.py --workload C5`."},
+                "kernel_ms_per_step": dict({k: v[0] / n_prof_steps for k, v in prof.items() if v[1]}, step_one_object_in_flight=ms_serial / n_prof_steps),
                 "lanes": args.lanes if args.lanes is not None else pipeline.default_lanes(),
                 "clocks": clk}
+        if single is not None:
+            line["single_gpu_same_workload"] = single
         if world == 1 and not args.no_cpu_baseline:
             rate, info, _ = cpu_reference_rate(scene, rotations, translations, target_seconds=15.0)
             line["cpu_baseline"] = dict(info, value=rate, unit=UNIT)
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -281,6 +281,24 @@ int rsgpu_coverage_masks( const rsgpu_cloud_t* const* objects, const float* pose
 int rsgpu_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t n_pts, const float* planes, int32_t n_planes, float dist_threshold,
                                int32_t* counts );
 
+/* ---- multi-GPU exchange of the pose-sharded search ---------------------------------------------------
+   The reference's loop over translations (apps/pose_proposal/pose_proposal.cpp:213-243) is split over one process per GPU;
+   what the ranks exchange is the survivor list of :348-359 (pose_proposal_t records + pose ids) and, after the refinement
+   of apps/pose_proposal/main.cpp:175-204, the refined rows.  rsgpu_peer_* is that all-gather over NVLink without an SM-resident
+   collective kernel: every rank's receive area is mapped by all peers (CUDA IPC), payloads and round flags are written by
+   copy engines, one warp waits for the flags.
+     rsgpu_peer_init      allocates this rank's area (slot_bytes = largest payload of one rank) and returns its IPC handle
+                          (rsgpu_peer_handle_bytes() bytes) for the caller to distribute (set-up, any transport);
+     rsgpu_peer_open      handles = world x rsgpu_peer_handle_bytes() bytes, rank-major;
+     rsgpu_peer_allgather collective: `nbytes` (equal on every rank) from host `send` -> host `recv` [world][nbytes];
+                          timeout_s <= 0 means 30 s; a peer that never sends gives RSGPU_ERR_CUDA, not a hang;
+     rsgpu_peer_close     every rank must have left its last rsgpu_peer_allgather (caller barrier) before any rank closes. */
+int rsgpu_peer_handle_bytes( void );
+int rsgpu_peer_init( int32_t rank, int32_t world, int64_t slot_bytes, void* handle_out );
+int rsgpu_peer_open( const void* handles );
+int rsgpu_peer_allgather( const void* send, int64_t nbytes, void* recv, double timeout_s );
+int rsgpu_peer_close( void );
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,11 @@ SIGNATURES = {
     "rsgpu_coverage_masks": (_int, [C.POINTER(_vp), _vp, _i32, _vp, _vp, _f32, _vp, _vp, _i32, C.POINTER(_i32)]),
     "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
     "rsgpu_plane_inlier_counts": (_int, [_vp, _vp, _i32, _vp, _i32, _f32, _vp]),
+    "rsgpu_peer_handle_bytes": (_int, []),
+    "rsgpu_peer_init": (_int, [_i32, _i32, _i64, _vp]),
+    "rsgpu_peer_open": (_int, [_vp]),
+    "rsgpu_peer_allgather": (_int, [_vp, _i64, _vp, C.c_double]),
+    "rsgpu_peer_close": (_int, []),
 }
 
 
@@ -268,6 +273,17 @@ class HashGrid:
 
     def knn_search(self, q, k, sort=1):
         return self._search(lib().rsgpu_grid_knn_search, q, 0.0, k, sort)
+
+    def radius_search_host(self, q, radius, k, d2, idx, nn, sort=1):
+        """msh_hash_grid_radius_search with caller-allocated HOST buffers exactly as the reference takes them
+        (msh_hash_grid.h:196-216: q float32 [nq,3], d2 float32 [nq,k], idx int32 [nq,k], nn uint64/int64 [nq]) -> total"""
+        nq = len(q)
+        assert q.dtype == np.float32 and d2.dtype == np.float32 and idx.dtype == np.int32 and nn.itemsize == 8
+        assert d2.shape == (nq, k) and idx.shape == (nq, k) and len(nn) == nq
+        sd = SearchDesc(q.ctypes.data, nq, d2.ctypes.data, idx.ctypes.data, nn.ctypes.data, radius, k, sort)
+        tot = C.c_size_t(0)
+        _check(lib().rsgpu_grid_radius_search(self.h, C.byref(sd), C.byref(tot)))
+        return int(tot.value)
 
     def radius_search_dev(self, q_ptr, nq, radius, k, d2_ptr, idx_ptr, nn_ptr=None):
         """same search with every buffer already in HBM (raw device pointers; n_neighbors is uint64) -> total"""

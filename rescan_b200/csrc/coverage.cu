@@ -31,9 +31,12 @@ struct CovGrid
 // cell of a world-space point, -1 outside the grid; layout y * (xr * zr) + z * xr + x (:115)
 __device__ __forceinline__ long long cov_cell( const CovGrid& g, float px, float py, float pz )
 {
-  const int x = (int)floorf( __fmul_rn( __fsub_rn( px, g.ox ), g.inv_voxel ) );
-  const int y = (int)floorf( __fmul_rn( __fsub_rn( py, g.oy ), g.inv_voxel ) );
-  const int z = (int)floorf( __fmul_rn( __fsub_rn( pz, g.oz ), g.inv_voxel ) );
+  const float fx = floorf( __fmul_rn( __fsub_rn( px, g.ox ), g.inv_voxel ) );
+  const float fy = floorf( __fmul_rn( __fsub_rn( py, g.oy ), g.inv_voxel ) );
+  const float fz = floorf( __fmul_rn( __fsub_rn( pz, g.oz ), g.inv_voxel ) );
+  // non-finite coordinates: the reference's x86 (int) cast gives INT_MIN (rejected below); CUDA's gives 0 for NaN
+  if( !( fx == fx ) || !( fy == fy ) || !( fz == fz ) ) { return -1; }
+  const int x = (int)fx, y = (int)fy, z = (int)fz;
   if( x < 0 || x >= g.xr || y < 0 || y >= g.yr || z < 0 || z >= g.zr ) { return -1; }
   return ( (long long)y * g.zr + z ) * g.xr + x;
 }

@@ -1,18 +1,17 @@
 // Batched point-to-plane ICP: replaces icp_align (reference lib/rs/icp.h:416-500) with its per-iteration
 // icp_find_corrs (:306-412) and icp_estimate_rigid_xform_pt2pl (:210-298, LDL^T from lineqn.h:153-218).
 //
-// One thread block per starting pose, resident for the whole alignment (no host round trips, one launch for
-// the batch).  Every iteration: (A) the block's warps find correspondences with nearest_compatible (k = 16
-// rank rule, acosf gate folded into a dot threshold); (B) three block-wide fp64 reductions — distance
-// statistics for the 2.5 sigma rejection, weighted centroids, the 6x6 normal equations — each reduced with
-// warp shuffles in a fixed order (deterministic); (C) thread 0 factors and solves the 6x6 system in fp64
-// exactly like trimesh::ldltdc/ldltsl and composes the update with the reference's float msh_translate /
-// msh_rotate / msh_mat4_mul order.  The scan grid is built ONCE by the caller and shared by all poses: the
-// search is exact, so the reference's per-call grid rebuild (:434-437) is not reproduced.
-//
-// Deliberate deviation: the reference accumulates its sums sequentially in float; here the terms
-// are formed in float exactly as the reference forms them and summed in fp64.  Results agree to the
-// tolerance stated in tests (1e-5 m / 1e-5 rad), not bit for bit.
+// Every iteration: (A) correspondences with the nearest-compatible-neighbour query (k = 16 rank rule, acosf gate folded
+// into a dot threshold); (B) distance statistics for the 2.5 sigma rejection, weighted centroids and the 6x6 normal
+// equations, accumulated SEQUENTIALLY IN FLOAT in the reference's point order (one accumulator per column walked down
+// the rows of shared tiles; msh_std.h:1778-1824, icp.h:137-148, 226-252) - the outlier cut and the |d err| < 1e-5 stop
+// are discontinuous in those sums, so only the reference's order reproduces its iteration counts; (C) the 6x6 system
+// factored and solved in fp64 exactly like trimesh::ldltdc/ldltsl and the update composed in the reference's float
+// msh_translate / msh_rotate / msh_mat4_mul order.  Refined poses, errors and iteration counts are bit-identical to the
+// reference's (tests/test_gpu_parity.py, tests/test_gpu_golden.py).  `icp_sums=fp64` selects deterministic fp64
+// warp-shuffle reductions instead (poses then agree to ~1e-3 m only; profiles/icp_parity_r01.md).
+// The scan grid is built ONCE by the caller and shared by all poses: the search is exact, so the reference's per-call
+// grid rebuild (:434-437) is not reproduced.  Batch structure: see icp_run below.
 #include "rsgpu_internal.cuh"
 #include "nearest.cuh"
 #include "nearest_group.cuh"
@@ -821,8 +820,13 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
           // "icp_phases" = 1: time the two kinds of launches separately (rsgpu_profile_get "icp_search" / "icp_solve")
           cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
           if( phase_prof ) { cudaEventCreate( &e0 ); cudaEventCreate( &e1 ); cudaEventCreate( &e2 ); cudaEventRecord( e0, aux[p] ); }
-          icp_search_kernel<<<search_blocks, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, dtask[p].p, np, TPT, dT2i.p, dot_thr, sq.p, sm.p, sp.p, sn.p );
-          count_launch();
+          // every alignment of the partition has an empty object cloud: nothing to search (a 0-block launch is invalid); the
+          // solve marks them inactive through nc == 0 and they return err = 1e6 like the reference (icp.h:444-456)
+          if( search_blocks > 0 )
+          {
+            icp_search_kernel<<<search_blocks, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, dtask[p].p, np, TPT, dT2i.p, dot_thr, sq.p, sm.p, sp.p, sn.p );
+            count_launch();
+          }
           if( phase_prof ) { cudaEventRecord( e1, aux[p] ); }
           if( exact ) { icp_solve_kernel<true><<<(unsigned)np, ICP_THREADS, tile_bytes, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }
           else { icp_solve_kernel<false><<<(unsigned)np, ICP_THREADS, 0, aux[p]>>>( scan->view(), dB.p, dS.p, dids[p].p, it, sq.p, sm.p, sp.p, sn.p, dact[p].p + it ); }

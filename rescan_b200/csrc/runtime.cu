@@ -149,20 +149,31 @@ static void configure_pool( int device )
   cudaGetLastError();
 }
 
+// The CUDA current device is per HOST THREAD: every thread that enters the library is bound to the process's device once
+// (thread_local flag), whether or not it ever attached to a lane; the process-wide part (device count, pool set-up) runs
+// once under call_once.  rsgpu_set_device() bumps the generation, so threads re-bind after a device change.
+static std::atomic<int> g_dev_generation{ 1 };
+static std::once_flag g_dev_once;
+static std::atomic<int> g_dev_count{ -1 };
 int ensure_device()
 {
-  static int state = 0; // 0 unknown, 1 ok, -1 none
-  if( state == 1 ) { return RSGPU_OK; }
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount( &n );
-  if( e != cudaSuccess || n <= 0 )
+  static thread_local int bound_generation = 0;
+  const int gen = g_dev_generation.load( std::memory_order_acquire );
+  if( bound_generation == gen ) { return RSGPU_OK; }
+  std::call_once( g_dev_once, []() {
+    int n = 0;
+    if( cudaGetDeviceCount( &n ) != cudaSuccess ) { cudaGetLastError(); n = 0; }
+    g_dev_count.store( n );
+  } );
+  if( g_dev_count.load() <= 0 ) { return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" ); }
+  RS_CUDA( cudaSetDevice( g_rt.device ) );
+  static std::mutex pool_mu;
+  static int pool_device = -1;
   {
-    cudaGetLastError();
-    return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" );
+    std::lock_guard<std::mutex> lk( pool_mu );
+    if( pool_device != g_rt.device ) { configure_pool( g_rt.device ); pool_device = g_rt.device; }
   }
-  RS_CUDA( cudaSetDevice( rt().device ) );
-  configure_pool( rt().device );
-  state = 1;
+  bound_generation = gen;
   return RSGPU_OK;
 }
 
@@ -229,13 +240,13 @@ int rsgpu_device_count( void )
 
 int rsgpu_set_device( int device )
 {
-  rt().device = device;
   int n = rsgpu_device_count();
   if( n <= 0 ) { return fail( RSGPU_ERR_NO_DEVICE, "rsgpu: no CUDA device available (there is no CPU fallback)" ); }
   if( device < 0 || device >= n ) { return fail( RSGPU_ERR_INVALID, "rsgpu_set_device: device index out of range" ); }
-  RS_CUDA( cudaSetDevice( device ) );
-  configure_pool( device );
-  return RSGPU_OK;
+  g_rt.device = device; // ONE device per process: lanes and unattached threads all follow it
+  for( int i = 0; i < N_LANES; ++i ) { g_lane_rt[i].device = device; }
+  g_dev_generation.fetch_add( 1, std::memory_order_acq_rel ); // every thread re-binds on its next call
+  return ensure_device();
 }
 
 int rsgpu_lane_count( void ) { return N_LANES; }

@@ -390,7 +390,9 @@ __global__ void select_kernel( const float* __restrict__ scores, long long n_tra
     float s = scores[t * n_rot + r];
     if( s > best ) { best = s; br = r; }
   }
-  flag[t] = best > thr ? 1 : 0;
+  // br < 0: no rotation scored above 0; with a negative caller threshold the reference would emit a zero matrix with
+  // score 0 here, which its final |score| > 1e-6 copy drops again (:348-359) - never flagged
+  flag[t] = ( br >= 0 && best > thr ) ? 1 : 0;
   best_r[t] = br; best_s[t] = best;
 }
 
@@ -614,6 +616,7 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   rsgpu_propose_opts_t opts;
   if( opts_in ) { opts = *opts_in; } else { rsgpu_propose_default_opts( &opts ); }
   long long n = (long long)n_rot * n_trans;
+  if( opts.top_k > 512 ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_propose_poses: top_k > 512" ); }
   if( n == 0 ) { return RSGPU_OK; }
   if( n_trans > 2147483647ll ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_propose_poses: more than 2^31 translations" ); }
   cudaStream_t st = rt().stream;
@@ -686,7 +689,6 @@ int rsgpu_propose_poses( const rsgpu_cloud_t* o4, const rsgpu_cloud_t* o3, const
   RS_CUDA( sel.alloc( n_prop ) ); RS_CUDA( nsel.alloc( 1 ) ); RS_CUDA( dout.alloc( (size_t)cap_sel * RSGPU_POSE_FLOATS ) ); RS_CUDA( dids.alloc( cap_sel ) );
   if( opts.top_k > 0 )
   {
-    if( opts.top_k > 512 ) { return fail( RSGPU_ERR_UNSUPPORTED, "rsgpu_propose_poses: top_k > 512" ); }
     const int k = opts.top_k;
     if( k <= 32 ) { topk_kernel<1><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }
     else if( k <= 64 ) { topk_kernel<2><<<1, 32, 0, st>>>( psc.p, n_prop, k, sel.p, nsel.p ); }

@@ -62,18 +62,25 @@ def shard_range(n, rank, world):
 
 
 def merge_topk(per_rank_props, per_rank_ids, top_k):
-    """deterministic merge of per-rank proposal lists: descending score, ties by pose id (identical on every rank)"""
+    """deterministic merge of per-rank proposal lists (identical on every rank), in the order a single rank's
+    rsgpu_propose_poses returns the same list: top_k > 0 descending score with ties by pose id; top_k <= 0 (the reference's
+    behaviour: every survivor) ascending pose id = emission order, so the NMS that follows breaks ties between equal scores
+    the same way for any number of ranks (pose_proposal.cpp:348-359, 404-411)"""
     props = np.concatenate(per_rank_props) if per_rank_props else np.zeros((0, api.POSE_FLOATS), np.float32)
     ids = np.concatenate(per_rank_ids) if per_rank_ids else np.zeros(0, np.int64)
-    order = np.lexsort((ids, -props[:, 16].astype(np.float64)))
     if top_k > 0:
-        order = order[:top_k]
+        order = np.lexsort((ids, -props[:, 16].astype(np.float64)))[:top_k]
+    else:
+        order = np.argsort(ids, kind="stable")
     return props[order], ids[order]
 
 
 def _allgather_bytes(buf, dist, device, group=None):
-    """ONE all-gather of equally sized byte buffers -> uint8 [world, nbytes].  device = a CUDA device: staged through
-    HBM and moved by NCCL over NVLink; device = cpu (with a gloo `group`): the host-resident bytes never touch the GPU"""
+    """ONE all-gather of equally sized byte buffers -> uint8 [world, nbytes].  group = a peerx.PeerExchange: peer-mapped
+    slots written over NVLink by copy engines (the default of bench.py); device = a CUDA device: staged through HBM and moved
+    by NCCL; device = cpu (with a gloo `group`): the host-resident bytes never touch the GPU"""
+    if hasattr(group, "allgather"):
+        return group.allgather(buf)
     import torch
     world = dist.get_world_size()
     send = torch.from_numpy(np.ascontiguousarray(buf).view(np.uint8).reshape(-1)).to(device, non_blocking=True)
@@ -181,8 +188,11 @@ def configure_host_waits(lanes, local_world=None):
 
 def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, icp_max_dist=0.10,
              icp_max_angle=np.float32(np.deg2rad(60.0)), rank=0, world=1, dist=None, device=None,
-             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None, trace=False, host_group=None):
-    """scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
+             scan_dev=None, do_icp=True, nms_dist=None, previous=None, lanes=None, trace=False, host_group=None, peer=None):
+    """top_k: per-object cap on the proposals that leave the search (descending score, ties by pose id).  The reference keeps
+    every survivor (pose_proposal.cpp:348-359) = top_k 0; the default 64 is BASELINE.json's C3 configuration ("top-k = 64 per
+    object") and a deliberate deviation for the bench workloads - pass top_k=0 for the reference's behaviour.
+    scan_lvl1 / scan_lvl2: (pos, nor) host arrays of the scan levels; scan_dev: optional dict of device pointers
     {"p1","n1","p2","n2"} (+ sizes from the host arrays) to build the grids from HBM-resident data instead.
     nms_dist: centroid-distance threshold of the two NMS passes (the reference passes 0.2, main.cpp:161/205); None
     skips both.  previous: per dynamic object, float32 [n,16] placements of earlier arrangements, appended with
@@ -191,6 +201,8 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     (they come back through the C ABI) and a few KB; an NCCL kernel issued while the dense search saturates the GPU is
     not dispatched before the pending dense blocks drain (measured 14 ms at N = 2), a host all-gather of
     the same bytes takes 0.3 ms.  Without it the exchanges use `dist` / `device` as given (NCCL staged through HBM).
+    peer: optional peerx.PeerExchange: both exchanges then go over NVLink through peer-mapped slots (copy engines, no
+    collective kernel); takes precedence over host_group.
     lanes: how many objects are in flight at once (default RSGPU_LANES or 8; 1 = the reference's serial object loop).
     The objects are independent (pose_proposal.cpp:190-250, main.cpp:175-204), so every object's chain runs on its own
     lane: the latency-bound stages of one object (verification, NMS rounds, ICP iterations) fill the device next to the
@@ -208,6 +220,8 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         return out
     p1, n1 = scan_lvl1
     p2, n2 = scan_lvl2
+    if peer is not None:
+        host_group = peer
     t_g = time.perf_counter()
     import threading
     if scan_dev is None:

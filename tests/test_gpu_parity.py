@@ -185,11 +185,14 @@ def _pose_delta(a16, b16):
 
 
 def test_icp_align_matches_oracle(scene):
+    """icp_align at the pose_proposal call site (main.cpp:195: level 2, 0.10 m, 60 degrees) for perturbed starts of every object:
+    the default path accumulates in the reference's float order, so pose, error and iteration count are BIT-identical to the
+    oracle's (itself pinned bit-equal to the compiled reference); 1e-5 m / 1e-5 rad is north_star's tolerance, kept as a second
+    assertion so that a failure says how far off it is"""
     p2, n2 = scene.scan.pos(2), scene.scan.nor(2)
     grid = api.HashGrid(p2, 0.05, normals=n2)
     rng = np.random.default_rng(31)
-    worst = (0.0, 0.0)
-    n_close = n_total = 0
+    n_iterated = 0
     for o in scene.objects:
         starts = [common.colmajor(m) for _, m in common.perturbed_poses(rng, type("S", (), {"objects": [o]})(), 4, 0.03, 0.08)]
         cloud = api.PointCloud(o.cloud.pos(2), o.cloud.nor(2))
@@ -197,13 +200,10 @@ def test_icp_align_matches_oracle(scene):
         for b, s in enumerate(starts):
             To, eo, ito = O.icp_align(o.cloud.pos(2), o.cloud.nor(2), p2, n2, s, 0.10, np.float32(np.deg2rad(60.0)))
             dt, da = _pose_delta(T[b], To)
-            n_total += 1
-            if dt < 1e-5 and da < 1e-5:
-                n_close += 1
-            worst = (max(worst[0], dt), max(worst[1], da))
-            assert abs(err[b] - eo) < 1e-4
-    # float-sequential sums of the reference vs fp64 reductions here: rare bifurcations are tolerated, not the rule
-    assert n_close >= 0.9 * n_total, f"only {n_close}/{n_total} ICP runs within 1e-5 m / 1e-5 rad (worst {worst})"
+            assert dt < 1e-5 and da < 1e-5, (dt, da)
+            assert (T[b] == To).all() and err[b] == np.float32(eo) and it[b] == ito
+            n_iterated += int(ito > 0)
+    assert n_iterated >= 2 * len(scene.objects)
 
 
 @pytest.mark.parametrize("lvl,max_dist,max_angle_deg,T2_shift", [
@@ -281,5 +281,13 @@ def test_neighborhood_edges(scan1):
     same = gn == on
     assert same.mean() > 0.999  # rows differ only by tie order
     assert np.allclose(gw[same], ow[same], rtol=2e-6, atol=1e-9)
+    # a row that differs holds the same neighbours in another order (exact distance ties), or - when the tie straddles the
+    # k-th place - differs in tied entries only: compare the distances of the entries that are not shared
+    pf = p.astype(np.float32)
     for r in np.unique(np.nonzero(~same)[0])[:200]:
-        assert sorted(gn[r]) == sorted(on[r]) or True
+        a, b = set(gn[r].tolist()), set(on[r].tolist())
+        if a == b:
+            continue
+        da = sorted(float(((pf[i] - pf[r]) ** 2).sum()) for i in a - b if i >= 0)
+        db = sorted(float(((pf[i] - pf[r]) ** 2).sum()) for i in b - a if i >= 0)
+        assert len(da) == len(db) and np.allclose(da, db, rtol=0, atol=1e-12), (r, da, db)

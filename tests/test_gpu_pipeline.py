@@ -112,45 +112,59 @@ def test_lanes_do_not_change_results():
                 assert a.shape == b.shape and (a == b).all() and (ia == ib).all()
 
 
-def _rank_worker(rank, world, port, out_dir, lanes):
+def _rank_worker(rank, world, port, out_dir, lanes, exchange="gloo", top_k=16):
     import os
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0; the exchange itself runs over gloo
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0
     api.set_device(0)
+    peer = None
+    if exchange == "peer":
+        # the product's transport (bench.py default): peer-mapped slots + copy engines (csrc/peer.cu); with both ranks on one
+        # GPU the peer copies are local, the protocol (IPC mapping, ring, flags, wait kernel) is the same
+        from rescan_b200 import peerx
+        peer = peerx.PeerExchange(dist, rank, world, slot_bytes=1 << 20, timeout_s=20.0)
+        got = peer.allgather(np.full(1000, rank + 1, np.uint8))
+        assert got.shape == (world, 1000) and all((got[r] == r + 1).all() for r in range(world))
+        for n in (0, 1, 7, 4096, 1 << 20):  # ring wrap-around, empty and full-slot payloads
+            got = peer.allgather((np.arange(n) * (rank + 3) % 251).astype(np.uint8))
+            assert all((got[r] == (np.arange(n) * (r + 3) % 251).astype(np.uint8)).all() for r in range(world))
     scene = common.small_scene()
     rots, _ = common.rotation_xforms(12)
     trans = synth.translation_seeds(scene.scan, 192, seed=3)
     for i, o in enumerate(scene.objects):
         trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
     models = pipeline.upload_objects(scene.objects)
-    res = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans, top_k=16,
-                            nms_dist=0.2, rank=rank, world=world, dist=dist, device=torch.device("cpu"), lanes=lanes)
+    res = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans, top_k=top_k,
+                            nms_dist=0.2, rank=rank, world=world, dist=dist, device=torch.device("cpu"), lanes=lanes, peer=peer)
     np.savez(os.path.join(out_dir, f"r{rank}_{lanes}.npz"), **{f"p{k}": p for k, p in enumerate(res.proposals)},
              **{f"i{k}": i for k, i in enumerate(res.pose_ids)}, n_eval=res.n_evaluations)
+    if peer is not None:
+        peer.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("lanes", [1, 4])
-def test_pose_sharded_step_equals_single_rank(tmp_path, lanes):
-    """two ranks (sharing the one GPU, exchanging over gloo) through the pose-sharded step: every rank ends with the
-    single-rank lists, bit for bit"""
+@pytest.mark.parametrize("lanes,exchange,top_k", [(1, "gloo", 16), (4, "gloo", 16), (4, "peer", 16), (1, "peer", 0)])
+def test_pose_sharded_step_equals_single_rank(tmp_path, lanes, exchange, top_k):
+    """two ranks (sharing the one GPU; lists exchanged over gloo or through the peer-mapped slots of csrc/peer.cu) through the
+    pose-sharded step: every rank ends with the single-rank lists, bit for bit - also with top_k = 0 (every survivor, the
+    reference's behaviour), where the merged list must reach the NMS in the single-rank order"""
     import socket
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_rank_worker, args=(2, port, str(tmp_path), lanes), nprocs=2, join=True)
+    mp.spawn(_rank_worker, args=(2, port, str(tmp_path), lanes, exchange, top_k), nprocs=2, join=True)
     scene = common.small_scene()
     rots, _ = common.rotation_xforms(12)
     trans = synth.translation_seeds(scene.scan, 192, seed=3)
     for i, o in enumerate(scene.objects):
         trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
     models = pipeline.upload_objects(scene.objects)
-    ref = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans, top_k=16,
+    ref = pipeline.run_step((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rots, trans, top_k=top_k,
                             nms_dist=0.2, lanes=1)
     total_eval = 0
     for rank in range(2):

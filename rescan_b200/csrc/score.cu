@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <mutex>
+#include <string>
 
 using namespace rs;
 
@@ -277,6 +279,10 @@ ScoreParams make_params( float radius, int k )
   return sp;
 }
 
+} // namespace
+#include "dense_binned.cuh"
+namespace
+{
 // core launcher: scores (device) [n_poses]; gate may alias scores
 // prune_thr > 0 (propose only): poses that provably cannot score above prune_thr are reported as 0
 int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const PoseSource& ps, bool grid_mode, long long n_poses,
@@ -301,6 +307,38 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
   // RSGPU_SCORE_IMPL=coop selects the warp-per-query kernel (the census pass always uses it)
   const bool coop_env = option( "score_impl" ) == "coop";
   const bool group_impl = !d_counts && !coop_env;
+  // the dense pose grid goes through the cell-binned, shared-memory-staged search (dense_binned.cuh) unless
+  // "dense_impl" = "warp" asks for the first design (one warp per pose, score_kernel_g) or the input is outside its envelope
+  if( grid_mode && group_impl && option( "dense_impl" ) != "warp" && dense_binned_supported( obj, scene, ps ) )
+  {
+    DbScratch S; DbPlan P;
+    RS_TRY( dense_binned_alloc( S, P, obj, scene, ps, n_poses ) );
+    const cudaStream_t lane_st2 = st;
+    if( bulk_stream() != st )
+    {
+      cudaEvent_t fork = nullptr;
+      RS_CUDA( cudaEventCreateWithFlags( &fork, cudaEventDisableTiming ) );
+      cudaEventRecord( fork, lane_st2 );
+      st = bulk_stream();
+      cudaStreamWaitEvent( st, fork, 0 );
+      cudaEventDestroy( fork );
+    }
+    int status;
+    {
+      ProfScope prof( "score_dense", st );
+      status = dense_binned_run( S, P, obj, scene, ps, sp, (double)prune_thr, d_scores, st );
+    }
+    if( st != lane_st2 )
+    {
+      cudaEvent_t join = nullptr;
+      RS_CUDA( cudaEventCreateWithFlags( &join, cudaEventDisableTiming ) );
+      cudaEventRecord( join, st );
+      cudaStreamWaitEvent( lane_st2, join, 0 );
+      cudaEventDestroy( join );
+    }
+    RS_CUDA( rs::stream_sync( lane_st2, true ) ); // the scratch dies here
+    return status;
+  }
   if( group_impl && n_split < ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP ) { n_split = ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP; }
   int chunk = ( ( obj->n + n_split - 1 ) / n_split + 31 ) / 32 * 32;
   n_split = ( obj->n + chunk - 1 ) / chunk;

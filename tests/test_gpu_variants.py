@@ -21,7 +21,7 @@ def scene():
 @pytest.fixture(autouse=True)
 def _restore_options():
     yield
-    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps"):
+    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps"):
         api.set_option(name, None)
 
 
@@ -77,7 +77,10 @@ def test_scoring_variants_bit_identical(scene):
     base_scores = api.score_pose_grid(c4, grid, rots, trans)
     base_props = _propose_all(scene, grid, rots, trans)
     assert sum(len(pr) for pr, _ in base_props) > 0
-    for opts in ({"score_impl": "coop"}, {"prune": "0"}, {"score_g": "8"}, {"score_minb": "4", "score_warps": "4"}, {"score_warps": "4"}, {"score_warps": "2"}, {"score_warps": "1", "score_minb": "16"}, {"search": "lane"}):
+    W = {"dense_impl": "warp"}  # the first design of the dense search (one warp per pose); the default is the cell-binned one
+    for opts in ({"score_impl": "coop"}, {"prune": "0"}, W, dict(W, prune="0"), dict(W, score_g="8"), dict(W, score_minb="4", score_warps="4"),
+                 dict(W, score_warps="2"), dict(W, score_warps="1", score_minb="16"), dict(W, search="lane"), {"score_g": "8"}, {"search": "lane"},
+                 {"dense_cap": "20000"}, {"dense_cap": "300000", "dense_bps": "1"}, {"dense_bps": "6", "prune": "0"}):
         for k, v in opts.items():
             api.set_option(k, v)
         s = api.score_pose_grid(c4, grid, rots, trans)
@@ -86,6 +89,38 @@ def test_scoring_variants_bit_identical(scene):
             assert (ia == ib).all() and (pa == pb).all(), f"proposals differ under {opts}"
         for k in opts:
             api.set_option(k, None)
+
+
+@pytest.mark.parametrize("which", ["tiny", "small"])
+def test_dense_binned_equals_warp_design(which):
+    """the cell-binned, shared-memory-staged dense search (csrc/dense_binned.cuh) against the first design (one warp per pose,
+    csrc/nearest_group.cuh): every score of the pose grid bit-identical, for every object, with one chunk and with many
+    (dense_cap), on a sparse scene (blocks staged) and on a dense one (1 cm spacing: blocks above the staging capacity are
+    read from global memory; the k = 64 cap binds), seeds on the scan's border included (home cell outside the grid)"""
+    scene = common.tiny_scene() if which == "tiny" else common.small_scene()
+    grid = api.HashGrid(scene.scan.pos(1), 0.05, normals=scene.scan.nor(1))
+    rots, _ = common.rotation_xforms(9)
+    trans = synth.translation_seeds(scene.scan, 96, seed=21)
+    for i, o in enumerate(scene.objects):
+        trans[i] = [o.pose[0, 3], 0.0, o.pose[2, 3]]
+    lo, hi = scene.scan.pos(1).min(0), scene.scan.pos(1).max(0)
+    trans[-4:] = [[lo[0], 0, lo[2]], [hi[0], 0, hi[2]], [hi[0] + 0.05, 0, 0.5 * (lo[2] + hi[2])], [0.5 * (lo[0] + hi[0]), 0, hi[2] + 0.08]]
+    n_pos = 0
+    for o in scene.objects:
+        for lvl, k in ((4, 64), (3, 64), (4, 8)):  # level 3 as a stand-in for a big object; a small k makes the cap bind
+            c = api.PointCloud(o.cloud.pos(lvl), o.cloud.nor(lvl))
+            if len(c) > 4096:
+                continue
+            api.set_option("dense_impl", "warp")
+            want = api.score_pose_grid(c, grid, rots, trans, max_n_neigh=k)
+            api.set_option("dense_impl", None)
+            for cap in (None, "5000", "70000"):
+                api.set_option("dense_cap", cap)
+                got = api.score_pose_grid(c, grid, rots, trans, max_n_neigh=k)
+                api.set_option("dense_cap", None)
+                assert (got == want).all(), (which, lvl, k, cap, int((got != want).sum()))
+            n_pos += int((want > 0.25).sum())
+    assert n_pos > 0
 
 
 def test_icp_variants_bit_identical(scene):

@@ -40,6 +40,7 @@ constexpr int DB_PTS_BITS = 12;                   // object points per cloud on 
 constexpr int DB_MAX_PTS = 1 << DB_PTS_BITS;
 constexpr uint32_t DB_POSE_MAX = 1u << ( 32 - DB_PTS_BITS ); // poses per chunk
 constexpr uint32_t DB_DONE = 0xffffffffu;
+constexpr int DB_NCLS = 8;                        // sub-bins per cell: the query normal's dominant axis and sign (6 used)
 
 // ------------------------------------------------------------------------------------------------ P: rotated clouds
 __global__ void db_prepare_kernel( const float* __restrict__ pos, const float* __restrict__ nor, int n, const float* __restrict__ rots, int n_rot,
@@ -94,8 +95,9 @@ struct DbCounters
 
 // ------------------------------------------------------------------------------------------------ A: prefilter
 // One warp per pose of the chunk.  Dynamic shared memory: per warp n_pad x (uint32 cell + uint16 point).
-// bins: n_cells + 1 counters; bin n_cells takes the queries the staged search does not handle (home cell outside the
-// grid, or a window that is not a subset of the 3x3x3 block: last-bit cases) - they go to the generic search.
+// bins: n_cells x DB_NCLS + 1 counters (cell-major, so a cell's queries are contiguous after the scan, ordered by class);
+// the last bin takes the queries the staged search does not handle (a window that is not a subset of the 3x3x3 block
+// around the clamped home cell: last-bit cases) - they go to the generic search.
 template <int WARPS>
 __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g, DbPoseGrid pg, long long pose0, unsigned n_chunk_poses, ScoreParams sp,
                                                                       double prune_cnt, int n_pad, DbCounters* __restrict__ ctr,
@@ -127,24 +129,25 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
       px = __fadd_rn( u.x, __fmul_rn( 1.0f, tx ) ); py = __fadd_rn( u.y, __fmul_rn( 1.0f, ty ) ); pz = __fadd_rn( u.z, __fmul_rn( 1.0f, tz ) );
       nx = __fadd_rn( v.x, __fmul_rn( 0.0f, tx ) ); ny = __fadd_rn( v.y, __fmul_rn( 0.0f, ty ) ); nz = __fadd_rn( v.z, __fmul_rn( 0.0f, tz ) );
     }
-    // the same test as the first design (window, block occupancy + block normal cone in one load)
-    bool active = false; uint32_t cell = n_cells;
+    // the first design's test (window, block occupancy + block normal cone in one load), on the 3x3x3 block around the
+    // query's own cell CLAMPED into the grid: a query up to one cell outside the scan's box still has a window of in-grid
+    // cells, and that window is a subset of the clamped cell's block
+    bool active = false; uint32_t bin = n_cells * DB_NCLS;
     if( valid )
     {
       const CellWindow w = make_window( g, px, py, pz, sp.radius );
       if( w.n_cells != 0 )
       {
-        const bool inside = w.c0x >= 0 && w.c0x < g.W && w.c0y >= 0 && w.c0y < g.H && w.c0z >= 0 && w.c0z < g.D;
-        const bool within1 = w.lox >= w.c0x - 1 && w.lox + w.nx <= w.c0x + 2 && w.loy >= w.c0y - 1 && w.loy + w.ny <= w.c0y + 2 &&
-                             w.loz >= w.c0z - 1 && w.loz + w.nz <= w.c0z + 2;
+        const int ccx = min( max( w.c0x, 0 ), g.W - 1 ), ccy = min( max( w.c0y, 0 ), g.H - 1 ), ccz = min( max( w.c0z, 0 ), g.D - 1 );
+        const bool in_block = w.lox >= ccx - 1 && w.lox + w.nx <= ccx + 2 && w.loy >= ccy - 1 && w.loy + w.ny <= ccy + 2 &&
+                              w.loz >= ccz - 1 && w.loz + w.nz <= ccz + 2;
         active = true;
-        if( inside && within1 )
+        if( in_block )
         {
-          const uint32_t c0id = ( (uint32_t)w.c0z * g.H + w.c0y ) * g.W + w.c0x;
-          cell = c0id;
+          const uint32_t ccid = ( (uint32_t)ccz * g.H + ccy ) * g.W + ccx;
           if( g.ncone )
           {
-            const float4 u = __ldg( g.ncone + c0id );
+            const float4 u = __ldg( g.ncone + ccid );
             if( u.w > 1.5f ) { active = false; }
             else
             {
@@ -152,7 +155,18 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
               active = cone_possible_loaded( u, cull, nx, ny, nz );
             }
           }
-          else { active = __ldg( g.occ27 + c0id ) != 0; }
+          else { active = __ldg( g.occ27 + ccid ) != 0; }
+          // the points of the block (a superset of the window's) all lie in nbox: farther than the radius from it = no neighbour
+          if( active && g.nbox )
+          {
+            const float4 lo = __ldg( g.nbox + 2 * (size_t)ccid ), hi = __ldg( g.nbox + 2 * (size_t)ccid + 1 );
+            active = box_gap_bits( lo, hi, px, py, pz ) < __float_as_uint( sp.r2f );
+          }
+          // sub-bin: dominant axis and sign of the query normal (queries of a warp of the search then face the same way, so
+          // the per-cell normal-cone culling skips whole cells)
+          const float ax = fabsf( nx ), ay = fabsf( ny ), az = fabsf( nz );
+          const int cls = ay >= ax && ay >= az ? ( ny < 0.f ? 1 : 0 ) : ( ax >= az ? ( nx < 0.f ? 3 : 2 ) : ( nz < 0.f ? 5 : 4 ) );
+          bin = ccid * DB_NCLS + (uint32_t)cls;
         }
       }
     }
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
     if( active )
     {
       const int o = n_list + __popc( bal & ( ( 1u << lane ) - 1u ) );
-      lcell[o] = cell; lidx[o] = (uint16_t)i;
+      lcell[o] = bin; lidx[o] = (uint16_t)i;
     }
     n_list += __popc( bal );
   }
@@ -174,10 +188,10 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
   if( pruned ) { return; }
   for( int j = lane; j < n_list; j += 32 )
   {
-    const uint32_t cell = lcell[j];
-    const uint32_t at = atomicAdd( bins + cell, 1u );
+    const uint32_t bin = lcell[j];
+    const uint32_t at = atomicAdd( bins + bin, 1u );
     queue[base + j] = make_uint2( base + (unsigned)j, ( pl << DB_PTS_BITS ) | (uint32_t)lidx[j] );
-    qbin[base + j] = make_uint2( cell, at );
+    qbin[base + j] = make_uint2( bin, at );
   }
 }
 
@@ -187,7 +201,7 @@ __global__ void db_items_kernel( const uint32_t* __restrict__ offs, uint32_t n_c
 {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if( c >= n_cells ) { return; }
-  const uint32_t a = offs[c], b = offs[c + 1];
+  const uint32_t a = offs[(size_t)c * DB_NCLS], b = offs[(size_t)( c + 1 ) * DB_NCLS];
   if( a == b ) { return; }
   const uint32_t n = ( b - a + DB_QCHUNK - 1 ) / DB_QCHUNK;
   const uint32_t at = atomicAdd( &ctr->n_items, n );
@@ -224,6 +238,18 @@ __device__ __forceinline__ void db_mbar_wait( uint64_t* bar, unsigned parity )
   asm volatile( "{\n\t.reg .pred p;\n\tDB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DB_DONE;\n\tbra DB_WAIT;\n\tDB_DONE:\n\t}"
                 ::"r"( db_smem_u32( bar ) ), "r"( parity ) : "memory" );
 }
+// same with a back-off between probes: the producer warp waits for whole items to be consumed and must not eat issue slots
+__device__ __forceinline__ void db_mbar_wait_backoff( uint64_t* bar, unsigned parity )
+{
+  for( ;; )
+  {
+    unsigned ok;
+    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                  : "=r"( ok ) : "r"( db_smem_u32( bar ) ), "r"( parity ) : "memory" );
+    if( ok ) { return; }
+    __nanosleep( 2000 ); // an item keeps the compute warps busy for tens of microseconds
+  }
+}
 // 1-D bulk-async copy global -> shared (bytes a multiple of 16, both addresses 16-byte aligned), completion on the mbarrier
 __device__ __forceinline__ void db_bulk_g2s( void* dst, const void* src, unsigned bytes, uint64_t* bar )
 {
@@ -239,6 +265,8 @@ struct DbBlock // one staged 3x3x3 block (per buffer)
   uint32_t gs[27];     // per cell (dz, dy, dx order): first record (position in recs)
   uint32_t cn[27];     // number of records
   uint32_t so[27];     // offset in the staged arrays
+  float4 cone[27];     // per cell {unit mean normal, cos(widest deviation)} (w <= 0: no usable cone), nearest.cuh ConeCull
+  float4 blo[27], bhi[27]; // per cell: bounding box of its points (rsgpu_internal.cuh box_gap_bits)
 };
 
 struct DbSmem
@@ -273,7 +301,7 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
     for( unsigned it = 0;; ++it )
     {
       const int b = it & 1;
-      if( it >= 2 ) { db_mbar_wait( &S.empty[b], ( ( it >> 1 ) - 1 ) & 1 ); } // the compute warps left this buffer
+      if( it >= 2 ) { db_mbar_wait_backoff( &S.empty[b], ( ( it >> 1 ) - 1 ) & 1 ); } // the compute warps left this buffer
       unsigned item = 0;
       if( lane == 0 ) { item = atomicAdd( &ctr->item_cursor, 1u ); }
       item = __shfl_sync( RS_FULL, item, 0 );
@@ -288,6 +316,9 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
       const int c0x = (int)( c0 % (uint32_t)g.W ); const uint32_t rr = c0 / (uint32_t)g.W;
       const int c0y = (int)( rr % (uint32_t)g.H ), c0z = (int)( rr / (uint32_t)g.H );
       uint32_t s = 0, n = 0;
+      float4 cone = make_float4( 0.f, 0.f, 0.f, -1.f );
+      const float ninf = __int_as_float( 0xff800000 );
+      float4 blo = make_float4( ninf, ninf, ninf, 0.f ), bhi = make_float4( -ninf, -ninf, -ninf, 0.f ); // no table: everything is "inside"
       if( lane < 27 )
       {
         const int cx = c0x + lane % 3 - 1, cy = c0y + ( lane / 3 ) % 3 - 1, cz = c0z + lane / 9 - 1;
@@ -295,6 +326,8 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
         {
           const uint32_t id = ( (uint32_t)cz * g.H + cy ) * g.W + cx;
           s = __ldg( g.cell_start + id ); n = __ldg( g.cell_start + id + 1 ) - s;
+          if( g.cone && n ) { cone = __ldg( g.cone + id ); }
+          if( g.cbox && n ) { blo = __ldg( g.cbox + 2 * (size_t)id ); bhi = __ldg( g.cbox + 2 * (size_t)id + 1 ); }
         }
       }
       // compact layout in lane (= cell) order: exclusive prefix of the counts
@@ -304,10 +337,10 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
       const uint32_t total = __shfl_sync( RS_FULL, incl, 31 );
       const uint32_t so = incl - n;
       const bool staged = total <= (uint32_t)DB_CAP;
-      if( lane < 27 ) { B.gs[lane] = s; B.cn[lane] = n; B.so[lane] = so; }
+      if( lane < 27 ) { B.gs[lane] = s; B.cn[lane] = n; B.so[lane] = so; B.cone[lane] = cone; B.blo[lane] = blo; B.bhi[lane] = bhi; }
       if( lane == 0 )
       {
-        B.cell = c0; B.q_begin = im.y; const uint32_t qe = __ldg( offs + c0 + 1 ); B.q_end = min( im.y + (uint32_t)DB_QCHUNK, qe );
+        B.cell = c0; B.q_begin = im.y; const uint32_t qe = __ldg( offs + (size_t)( c0 + 1 ) * DB_NCLS ); B.q_end = min( im.y + (uint32_t)DB_QCHUNK, qe );
         B.staged = staged ? 1u : 0u;
       }
       __syncwarp(); // the block description of all lanes is ordered before lane 0's (releasing) arrive
@@ -360,23 +393,26 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
       uint2 ent = make_uint2( 0u, 0u );
       float px = 0.f, py = 0.f, pz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
       unsigned inwin = 0; // bit e: cell e of the block lies in this query's window
-      float glx2 = 0.f, ghx2 = 0.f, gly2 = 0.f, ghy2 = 0.f, glz2 = 0.f, ghz2 = 0.f;
+      float gx[3] = { 0.f, 0.f, 0.f }, gy[3] = { 0.f, 0.f, 0.f }, gz[3] = { 0.f, 0.f, 0.f }; // squared per-axis gap to block column d
+      ConeCull cull; cull.on = false; cull.cb = 0.f; cull.sb = 1.f;
       if( qv )
       {
         ent = __ldg( sorted + qi );
         const long long pose = pose0 + ( ent.y >> DB_PTS_BITS );
         const long long t = pose / pg.n_rot; const int r = (int)( pose - t * pg.n_rot );
         db_query( pg, t, r, (int)( ent.y & ( DB_MAX_PTS - 1 ) ), px, py, pz, nx, ny, nz );
-        // window and per-axis squared gaps exactly as rsg::group_search (msh_hash_grid.h:1150-1198)
+        // window and per-axis squared gaps exactly as rsg::group_search (msh_hash_grid.h:1150-1198): a cell below the
+        // query's own cell gets the gap to the own cell's lower face, a cell above it the gap to the upper face (for cells
+        // further out - only possible for queries outside the grid - an underestimate, which is conservative)
         const CellWindow w = make_window( g, px, py, pz, sp.radius );
         float a;
-        a = (float)__dsub_rn( (double)w.qx, __dmul_rn( (double)w.c0x, g.cell ) ); glx2 = __fmul_rn( a, a );
-        a = (float)__dsub_rn( __dmul_rn( (double)( w.c0x + 1 ), g.cell ), (double)w.qx ); ghx2 = __fmul_rn( a, a );
-        a = (float)__dsub_rn( (double)w.qy, __dmul_rn( (double)w.c0y, g.cell ) ); gly2 = __fmul_rn( a, a );
-        a = (float)__dsub_rn( __dmul_rn( (double)( w.c0y + 1 ), g.cell ), (double)w.qy ); ghy2 = __fmul_rn( a, a );
-        a = (float)__dsub_rn( (double)w.qz, __dmul_rn( (double)w.c0z, g.cell ) ); glz2 = __fmul_rn( a, a );
-        a = (float)__dsub_rn( __dmul_rn( (double)( w.c0z + 1 ), g.cell ), (double)w.qz ); ghz2 = __fmul_rn( a, a );
-        // block cell (dx, dy, dz) in {0,1,2}^3 is grid cell c0 + d - 1; in the window iff lo <= c < lo + n per axis
+        a = (float)__dsub_rn( (double)w.qx, __dmul_rn( (double)w.c0x, g.cell ) ); const float glx2 = __fmul_rn( a, a );
+        a = (float)__dsub_rn( __dmul_rn( (double)( w.c0x + 1 ), g.cell ), (double)w.qx ); const float ghx2 = __fmul_rn( a, a );
+        a = (float)__dsub_rn( (double)w.qy, __dmul_rn( (double)w.c0y, g.cell ) ); const float gly2 = __fmul_rn( a, a );
+        a = (float)__dsub_rn( __dmul_rn( (double)( w.c0y + 1 ), g.cell ), (double)w.qy ); const float ghy2 = __fmul_rn( a, a );
+        a = (float)__dsub_rn( (double)w.qz, __dmul_rn( (double)w.c0z, g.cell ) ); const float glz2 = __fmul_rn( a, a );
+        a = (float)__dsub_rn( __dmul_rn( (double)( w.c0z + 1 ), g.cell ), (double)w.qz ); const float ghz2 = __fmul_rn( a, a );
+        // block column d in {0,1,2} is grid column c0 + d - 1 (c0 = the block's centre = the query's own cell clamped into the grid)
         unsigned mx = 0, my = 0, mz = 0;
 #pragma unroll
         for( int d = 0; d < 3; ++d )
@@ -385,29 +421,34 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
           if( cx >= w.lox && cx < w.lox + w.nx ) { mx |= 1u << d; }
           if( cy >= w.loy && cy < w.loy + w.ny ) { my |= 1u << d; }
           if( cz >= w.loz && cz < w.loz + w.nz ) { mz |= 1u << d; }
+          gx[d] = cx < w.c0x ? glx2 : ( cx > w.c0x ? ghx2 : 0.0f );
+          gy[d] = cy < w.c0y ? gly2 : ( cy > w.c0y ? ghy2 : 0.0f );
+          gz[d] = cz < w.c0z ? glz2 : ( cz > w.c0z ? ghz2 : 0.0f );
         }
-#pragma unroll
-        for( int e = 0; e < 27; ++e )
-        {
-          if( ( ( mx >> ( e % 3 ) ) & 1u ) && ( ( my >> ( ( e / 3 ) % 3 ) ) & 1u ) && ( ( mz >> ( e / 9 ) ) & 1u ) ) { inwin |= 1u << e; }
-        }
+        // 27-bit mask = outer product of the three 3-bit masks
+        const unsigned row = mx * ( ( my & 1u ) | ( ( my & 2u ) << 2 ) | ( ( my & 4u ) << 4 ) ); // 9 bits: (dy, dx)
+        inwin = row * ( ( mz & 1u ) | ( ( mz & 2u ) << 8 ) | ( ( mz & 4u ) << 16 ) );
+        cull = make_cull( g, sp.dot_thr, nx, ny, nz );
       }
-      // ---- sweep: nearest compatible point, key = (d2 bits, record position); n_in = points of visited cells inside the radius
+      // ---- sweep: nearest compatible point, key = (d2 bits, record position).  closer = an upper bound of the number of
+      // points strictly closer than the final winner: points met at or below the running best, plus whole cells that were
+      // skipped for their normals only
       unsigned long long best = (unsigned long long)r2bits << 32;
       float bestdot = 0.f;
-      uint32_t n_in = 0;
+      uint32_t closer = 0;
+#pragma unroll 1
       for( int eo = 0; eo < 27; ++eo )
       {
         const int e = kDbOrder[eo];
         const uint32_t cn = B.cn[e];
         if( cn == 0 ) { continue; }
         const int dx = e % 3, dy = ( e / 3 ) % 3, dz = e / 9;
-        const float gx2 = dx == 0 ? glx2 : ( dx == 2 ? ghx2 : 0.0f );
-        const float gy2 = dy == 0 ? gly2 : ( dy == 2 ? ghy2 : 0.0f );
-        const float gz2 = dz == 0 ? glz2 : ( dz == 2 ? ghz2 : 0.0f );
-        const uint32_t gapc = __float_as_uint( __fadd_rn( __fadd_rn( gz2, gy2 ), gx2 ) ) & 0xffffffe0u; // rounded down: conservative
-        const bool win = ( inwin >> e ) & 1u;
-        const bool want = win && gapc < (uint32_t)( best >> 32 );
+        // (gz*gz + gy*gy) + gx*gx (:1221), 5 mantissa bits dropped: conservative
+        const uint32_t gapc = __float_as_uint( __fadd_rn( __fadd_rn( dz == 0 ? gz[0] : ( dz == 1 ? gz[1] : gz[2] ), dy == 0 ? gy[0] : ( dy == 1 ? gy[1] : gy[2] ) ),
+                                                          dx == 0 ? gx[0] : ( dx == 1 ? gx[1] : gx[2] ) ) ) & 0xffffffe0u;
+        bool want = ( ( inwin >> e ) & 1u ) && gapc < (uint32_t)( best >> 32 );
+        if( want ) { want = box_gap_bits( B.blo[e], B.bhi[e], px, py, pz ) < (uint32_t)( best >> 32 ); } // all its points are farther
+        if( want && !cone_possible_loaded( B.cone[e], cull, nx, ny, nz ) ) { want = false; closer += cn; } // none can be compatible
         if( !__any_sync( RS_FULL, want ) ) { continue; }
         const uint32_t gs = B.gs[e];
         const float4* __restrict__ rp = recs + ( staged ? B.so[e] : gs );
@@ -419,9 +460,9 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
           {
             const float4 rec = rp[j]; // all lanes read the same address: one broadcast
             const uint32_t db = __float_as_uint( dist2_exact( rec, px, py, pz ) );
-            n_in += db < r2bits;
             if( db <= (uint32_t)( best >> 32 ) )
             {
+              ++closer;
               const unsigned long long key = ( (unsigned long long)db << 32 ) | ( gs + j );
               if( key < best )
               {
@@ -435,22 +476,22 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
       }
       const uint32_t dcb = (uint32_t)( best >> 32 );
       bool found = qv && dcb < r2bits;
-      // ---- rank of the winner under the k-cap: only when the visited cells hold at least k points inside the radius
-      const bool need = found && n_in >= uk;
+      // ---- rank of the winner under the k-cap (fewer than k points strictly closer): exact count only where the bound allows k
+      const bool need = found && closer >= uk;
       if( __any_sync( RS_FULL, need ) )
       {
         const float dcf = __uint_as_float( dcb );
         uint32_t cnt = 0;
+#pragma unroll 1
         for( int e = 0; e < 27; ++e )
         {
           const uint32_t cn = B.cn[e];
           if( cn == 0 ) { continue; }
           const int dx = e % 3, dy = ( e / 3 ) % 3, dz = e / 9;
-          const float gx2 = dx == 0 ? glx2 : ( dx == 2 ? ghx2 : 0.0f );
-          const float gy2 = dy == 0 ? gly2 : ( dy == 2 ? ghy2 : 0.0f );
-          const float gz2 = dz == 0 ? glz2 : ( dz == 2 ? ghz2 : 0.0f );
-          const uint32_t gapc = __float_as_uint( __fadd_rn( __fadd_rn( gz2, gy2 ), gx2 ) ) & 0xffffffe0u;
-          const bool want = need && ( ( inwin >> e ) & 1u ) && gapc < dcb;
+          const uint32_t gapc = __float_as_uint( __fadd_rn( __fadd_rn( dz == 0 ? gz[0] : ( dz == 1 ? gz[1] : gz[2] ), dy == 0 ? gy[0] : ( dy == 1 ? gy[1] : gy[2] ) ),
+                                                            dx == 0 ? gx[0] : ( dx == 1 ? gx[1] : gx[2] ) ) ) & 0xffffffe0u;
+          bool want = need && ( ( inwin >> e ) & 1u ) && gapc < dcb;
+          if( want ) { want = box_gap_bits( B.blo[e], B.bhi[e], px, py, pz ) < dcb; }
           if( !__any_sync( RS_FULL, want ) ) { continue; }
           const float4* __restrict__ rp = recs + ( staged ? B.so[e] : B.gs[e] );
           if( want )
@@ -485,7 +526,7 @@ __global__ void __launch_bounds__( 128 ) db_fallback_kernel( GridView g, DbPoseG
                                                              uint32_t n_cells, const uint2* __restrict__ sorted, double* __restrict__ terms )
 {
   const int lane = threadIdx.x & 31;
-  const uint32_t a = offs[n_cells], b = offs[n_cells + 1];
+  const uint32_t a = offs[(size_t)n_cells * DB_NCLS], b = offs[(size_t)n_cells * DB_NCLS + 1];
   const unsigned warp = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5, n_warps = ( gridDim.x * blockDim.x ) >> 5;
   for( uint32_t q0 = a + warp * 32; q0 < b; q0 += n_warps * 32 )
   {
@@ -557,14 +598,14 @@ struct DbScratch
 // chunk (every point of every pose survives the prefilter) fits the queue - nothing can overflow, nothing is re-tried.
 struct DbPlan
 {
-  size_t n_cells = 0, entries_max = 0, items_max = 0, chunk_poses_max = 0, scan_bytes = 0;
+  size_t n_cells = 0, n_bins = 0, entries_max = 0, items_max = 0, chunk_poses_max = 0, scan_bytes = 0;
   long long trans_per_chunk = 0, n_trans = 0;
 };
 
 bool dense_binned_supported( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const PoseSource& ps )
 {
   const size_t n_cells = (size_t)scene->info.width * scene->info.height * scene->info.depth;
-  return obj->n >= 1 && obj->n <= DB_MAX_PTS && ps.n_rot >= 1 && ps.n_rot <= 4096 && n_cells + 2 < ( (size_t)1 << 28 ) && scene->has_normals &&
+  return obj->n >= 1 && obj->n <= DB_MAX_PTS && ps.n_rot >= 1 && ps.n_rot <= 4096 && n_cells * DB_NCLS + 2 < ( (size_t)1 << 28 ) && scene->has_normals &&
          scene->info.n_pts > 0;
 }
 
@@ -575,6 +616,7 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   const int n = obj->n, n_rot = ps.n_rot;
   P.n_cells = (size_t)scene->info.width * scene->info.height * scene->info.depth;
   P.n_trans = n_poses / n_rot;
+  P.n_bins = P.n_cells * DB_NCLS + 2; // + the fallback bin + the end of the scan
   size_t cap = (size_t)32 << 20;
   {
     const std::string o = option( "dense_cap" );
@@ -590,11 +632,11 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   P.entries_max = P.chunk_poses_max * (size_t)n;
   P.items_max = P.entries_max / DB_QCHUNK + P.n_cells + 2;
   RS_CUDA( S.upos.alloc( (size_t)n * n_rot ) ); RS_CUDA( S.unor.alloc( (size_t)n * n_rot ) );
-  RS_CUDA( S.bins.alloc( P.n_cells + 2 ) ); RS_CUDA( S.offs.alloc( P.n_cells + 2 ) );
+  RS_CUDA( S.bins.alloc( P.n_bins ) ); RS_CUDA( S.offs.alloc( P.n_bins ) );
   RS_CUDA( S.pose_base.alloc( P.chunk_poses_max ) ); RS_CUDA( S.pose_cnt.alloc( P.chunk_poses_max ) );
   RS_CUDA( S.queue.alloc( P.entries_max ) ); RS_CUDA( S.qbin.alloc( P.entries_max ) ); RS_CUDA( S.sorted.alloc( P.entries_max ) );
   RS_CUDA( S.items.alloc( P.items_max ) ); RS_CUDA( S.terms.alloc( P.entries_max ) ); RS_CUDA( S.ctr.alloc( 1 ) );
-  RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, P.scan_bytes, S.bins.p, S.offs.p, (int64_t)( P.n_cells + 2 ), rt().stream ) );
+  RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, P.scan_bytes, S.bins.p, S.offs.p, (int64_t)P.n_bins, rt().stream ) );
   RS_CUDA( S.scan_tmp.alloc( P.scan_bytes ) );
   return RSGPU_OK;
 }
@@ -636,7 +678,7 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
     const long long nt = std::min( P.trans_per_chunk, P.n_trans - t0 );
     const long long pose0 = t0 * n_rot;
     const unsigned n_chunk = (unsigned)( nt * n_rot );
-    RS_CUDA( cudaMemsetAsync( S.bins.p, 0, sizeof( uint32_t ) * ( n_cells + 2 ), st ) );
+    RS_CUDA( cudaMemsetAsync( S.bins.p, 0, sizeof( uint32_t ) * P.n_bins, st ) );
     RS_CUDA( cudaMemsetAsync( S.ctr.p, 0, sizeof( DbCounters ), st ) );
     {
       ProfScope prof( "dense_prefilter", st );
@@ -655,7 +697,7 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
     }
     {
       ProfScope prof( "dense_bin", st );
-      RS_CUDA( cub::DeviceScan::ExclusiveSum( S.scan_tmp.p, scan_bytes, S.bins.p, S.offs.p, (int64_t)( n_cells + 2 ), st ) );
+      RS_CUDA( cub::DeviceScan::ExclusiveSum( S.scan_tmp.p, scan_bytes, S.bins.p, S.offs.p, (int64_t)P.n_bins, st ) );
       db_items_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( S.offs.p, (uint32_t)n_cells, S.ctr.p, S.items.p );
       RS_CHECK_LAUNCH();
       db_scatter_kernel<<<dev_sms * 8, 256, 0, st>>>( S.ctr.p, S.offs.p, S.queue.p, S.qbin.p, S.sorted.p );
@@ -667,6 +709,24 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
       RS_CHECK_LAUNCH();
       db_fallback_kernel<<<dev_sms * 2, 128, 0, st>>>( g, pg, pose0, sp, S.offs.p, (uint32_t)n_cells, S.sorted.p, S.terms.p );
       RS_CHECK_LAUNCH();
+    }
+    if( option( "dense_stats" ) == "1" )
+    {
+      // diagnostic (synchronises): queue length, items, how full the items' warps are, fallback queries, blocks above the staging capacity
+      DbCounters hc; std::vector<uint32_t> hoffs( P.n_bins );
+      cudaStreamSynchronize( st );
+      cudaMemcpy( &hc, S.ctr.p, sizeof( hc ), cudaMemcpyDeviceToHost );
+      cudaMemcpy( hoffs.data(), S.offs.p, sizeof( uint32_t ) * P.n_bins, cudaMemcpyDeviceToHost );
+      size_t used = 0, warps = 0, big = 0, mx = 0;
+      for( size_t c = 0; c < n_cells; ++c )
+      {
+        const size_t q = hoffs[( c + 1 ) * DB_NCLS] - hoffs[c * DB_NCLS];
+        if( !q ) { continue; }
+        ++used; warps += ( q + 31 ) / 32; mx = std::max( mx, q ); big += q > 4096;
+      }
+      fprintf( stderr, "dense chunk: poses %u points %d queue %u (%.1f%% of worst case) items %u cells_with_queries %zu warp_rounds %zu (fill %.1f%%) "
+                       "max_per_cell %zu cells>4096 %zu fallback %u\n", n_chunk, n, hc.n_queue, 100.0 * hc.n_queue / ( (double)n_chunk * n ), hc.n_items, used, warps,
+               warps ? 100.0 * ( hoffs[n_cells * DB_NCLS] ) / ( 32.0 * warps ) : 0.0, mx, big, hoffs[n_cells * DB_NCLS + 1] - hoffs[n_cells * DB_NCLS] );
     }
     {
       ProfScope prof( "dense_reduce", st );

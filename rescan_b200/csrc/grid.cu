@@ -103,6 +103,41 @@ __global__ void occ27_kernel( const uint32_t* __restrict__ cell_start, int W, in
   occ[c] = total;
 }
 
+// bounding box of the points of every cell (cbox) and of every 3x3x3 block of cells (nbox): {lo, hi} pairs, empty = {+inf, -inf}
+__global__ void cbox_kernel( const float4* __restrict__ recs, const uint32_t* __restrict__ cell_start, size_t n_cells, float4* __restrict__ cbox )
+{
+  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if( c >= n_cells ) { return; }
+  const float inf = __int_as_float( 0x7f800000 );
+  float4 lo = make_float4( inf, inf, inf, 0.f ), hi = make_float4( -inf, -inf, -inf, 0.f );
+  for( uint32_t p = cell_start[c]; p < cell_start[c + 1]; ++p )
+  {
+    const float4 r = recs[p];
+    lo.x = fminf( lo.x, r.x ); lo.y = fminf( lo.y, r.y ); lo.z = fminf( lo.z, r.z );
+    hi.x = fmaxf( hi.x, r.x ); hi.y = fmaxf( hi.y, r.y ); hi.z = fmaxf( hi.z, r.z );
+  }
+  cbox[2 * c] = lo; cbox[2 * c + 1] = hi;
+}
+__global__ void nbox_kernel( const float4* __restrict__ cbox, int W, int H, int D, float4* __restrict__ nbox )
+{
+  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t n = (size_t)W * H * D;
+  if( c >= n ) { return; }
+  int x = (int)( c % W ); size_t r = c / W; int y = (int)( r % H ); int z = (int)( r / H );
+  const float inf = __int_as_float( 0x7f800000 );
+  float4 lo = make_float4( inf, inf, inf, 0.f ), hi = make_float4( -inf, -inf, -inf, 0.f );
+  for( int zz = max( z - 1, 0 ); zz <= min( z + 1, D - 1 ); ++zz )
+    for( int yy = max( y - 1, 0 ); yy <= min( y + 1, H - 1 ); ++yy )
+      for( int xx = max( x - 1, 0 ); xx <= min( x + 1, W - 1 ); ++xx )
+      {
+        size_t id = ( (size_t)zz * H + yy ) * W + xx;
+        const float4 a = cbox[2 * id], b = cbox[2 * id + 1];
+        lo.x = fminf( lo.x, a.x ); lo.y = fminf( lo.y, a.y ); lo.z = fminf( lo.z, a.z );
+        hi.x = fmaxf( hi.x, b.x ); hi.y = fmaxf( hi.y, b.y ); hi.z = fmaxf( hi.z, b.z );
+      }
+  nbox[2 * c] = lo; nbox[2 * c + 1] = hi;
+}
+
 __global__ void relay_normals_kernel( const float* __restrict__ nor, int n, const float4* __restrict__ recs, float4* __restrict__ out )
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,6 +324,17 @@ int build_from_device( const float* d_pts, int32_t n, float radius, rsgpu_grid_t
     RS_CUDA( g->occ27.alloc( n_cells ) );
     occ27_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->cell_start.p, (int)dim[0], (int)dim[1], (int)dim[2], g->occ27.p );
     RS_CHECK_LAUNCH();
+    // point bounding boxes per cell / per 3x3x3 block (distance culling of the dense pose search); skipped for very large
+    // tables (64 B per cell)
+    if( n_cells <= ( (size_t)1 << 25 ) )
+    {
+      RS_CUDA( g->cbox.alloc( 2 * n_cells ) ); RS_CUDA( g->nbox.alloc( 2 * n_cells ) );
+      cbox_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->recs.p, g->cell_start.p, n_cells, g->cbox.p );
+      RS_CHECK_LAUNCH();
+      nbox_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->cbox.p, (int)dim[0], (int)dim[1], (int)dim[2], g->nbox.p );
+      RS_CHECK_LAUNCH();
+      g->has_boxes = true;
+    }
     RS_CUDA( rs::stream_sync( st ) ); // temporaries die here
   }
   uint32_t hs[2] = { 0, 0 };

@@ -93,6 +93,8 @@ struct GridView
   const uint32_t* __restrict__ occ27; // points in the 3x3x3 block of cells centred on each cell (0 = a query there sees nothing)
   const float4* __restrict__ cone;    // per cell {unit mean normal, cos(max angle to it)}; nullptr when normals are not unit
   const float4* __restrict__ ncone;   // the same for all normals in the 3x3x3 block around each cell
+  const float4* __restrict__ cbox;    // per cell: bounding box of ITS POINTS, {lo.xyz, -} at 2c, {hi.xyz, -} at 2c + 1 (lo > hi: empty); may be nullptr
+  const float4* __restrict__ nbox;    // the same for the points of the 3x3x3 block around each cell; may be nullptr
   float mnx, mny, mnz;
   int W, H, D;
   double cell, inv_cell;
@@ -107,6 +109,8 @@ struct rsgpu_grid
   rs::DevBuf<uint32_t> occ27;
   rs::DevBuf<float4> cone;
   rs::DevBuf<float4> ncone;
+  rs::DevBuf<float4> cbox, nbox;
+  bool has_boxes = false;
   bool has_cone = false;
   bool has_normals = false;
   rsgpu_grid_info_t info;
@@ -114,6 +118,7 @@ struct rsgpu_grid
   {
     GridView v;
     v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p; v.occ27 = occ27.p; v.cone = ( has_normals && has_cone ) ? cone.p : nullptr; v.ncone = v.cone ? ncone.p : nullptr;
+    v.cbox = has_boxes ? cbox.p : nullptr; v.nbox = has_boxes ? nbox.p : nullptr;
     v.mnx = info.min_pt[0]; v.mny = info.min_pt[1]; v.mnz = info.min_pt[2];
     v.W = (int)info.width; v.H = (int)info.height; v.D = (int)info.depth;
     v.cell = info.cell_size; v.inv_cell = info.inv_cell_size; v.n_pts = (int)info.n_pts;
@@ -144,6 +149,19 @@ __device__ __forceinline__ float dist2_exact( const float4& r, float px, float p
 {
   float vx = __fsub_rn( r.x, px ), vy = __fsub_rn( r.y, py ), vz = __fsub_rn( r.z, pz );
   return __fadd_rn( __fadd_rn( __fmul_rn( vx, vx ), __fmul_rn( vy, vy ) ), __fmul_rn( vz, vz ) );
+}
+
+// Conservative squared distance between a query and the axis-aligned bounding box of a set of points (cbox / nbox), as
+// ordered bits: never above the dist2_exact of any point of the set.  lo <= p <= hi per axis for every point p, rounding
+// is monotone and the operations and their order are dist2_exact's (no FMA: -fmad=false), so already the plain sum is a
+// lower bound; 5 mantissa bits are dropped on top of that.  An empty set (lo = +inf, hi = -inf) gives +inf.
+__device__ __forceinline__ uint32_t box_gap_bits( const float4& lo, const float4& hi, float px, float py, float pz )
+{
+  const float dx = fmaxf( fmaxf( __fsub_rn( lo.x, px ), __fsub_rn( px, hi.x ) ), 0.0f );
+  const float dy = fmaxf( fmaxf( __fsub_rn( lo.y, py ), __fsub_rn( py, hi.y ) ), 0.0f );
+  const float dz = fmaxf( fmaxf( __fsub_rn( lo.z, pz ), __fsub_rn( pz, hi.z ) ), 0.0f );
+  const float s = __fadd_rn( __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) ), __fmul_rn( dz, dz ) );
+  return __float_as_uint( s ) & 0xffffffe0u;
 }
 
 __device__ __forceinline__ float dot3_exact( float ax, float ay, float az, float bx, float by, float bz )

@@ -238,17 +238,20 @@ __device__ __forceinline__ void db_mbar_wait( uint64_t* bar, unsigned parity )
   asm volatile( "{\n\t.reg .pred p;\n\tDB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DB_DONE;\n\tbra DB_WAIT;\n\tDB_DONE:\n\t}"
                 ::"r"( db_smem_u32( bar ) ), "r"( parity ) : "memory" );
 }
-// same with a back-off between probes: the producer warp waits for whole items to be consumed and must not eat issue slots
-__device__ __forceinline__ void db_mbar_wait_backoff( uint64_t* bar, unsigned parity )
+// the producer warp waits for whole items to be consumed (tens of microseconds): the probe carries a suspend-time hint, so
+// the hardware parks the warp instead of letting it spin through issue slots; one lane probes, the warp follows
+__device__ __forceinline__ void db_mbar_wait_parked( uint64_t* bar, unsigned parity )
 {
-  for( ;; )
+  if( ( threadIdx.x & 31 ) == 0 )
   {
-    unsigned ok;
-    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                  : "=r"( ok ) : "r"( db_smem_u32( bar ) ), "r"( parity ) : "memory" );
-    if( ok ) { return; }
-    __nanosleep( 2000 ); // an item keeps the compute warps busy for tens of microseconds
+    unsigned ok = 0;
+    while( !ok )
+    {
+      asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"( ok ) : "r"( db_smem_u32( bar ) ), "r"( parity ), "r"( 20000u ) : "memory" );
+    }
   }
+  __syncwarp();
 }
 // 1-D bulk-async copy global -> shared (bytes a multiple of 16, both addresses 16-byte aligned), completion on the mbarrier
 __device__ __forceinline__ void db_bulk_g2s( void* dst, const void* src, unsigned bytes, uint64_t* bar )
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
     for( unsigned it = 0;; ++it )
     {
       const int b = it & 1;
-      if( it >= 2 ) { db_mbar_wait_backoff( &S.empty[b], ( ( it >> 1 ) - 1 ) & 1 ); } // the compute warps left this buffer
+      if( it >= 2 ) { db_mbar_wait_parked( &S.empty[b], ( ( it >> 1 ) - 1 ) & 1 ); } // the compute warps left this buffer
       unsigned item = 0;
       if( lane == 0 ) { item = atomicAdd( &ctr->item_cursor, 1u ); }
       item = __shfl_sync( RS_FULL, item, 0 );

@@ -219,6 +219,14 @@ __global__ void db_scatter_kernel( const DbCounters* __restrict__ ctr, const uin
   }
 }
 
+// -DRS_DB_STATS: work census of the search kernel (diagnostic builds only; printed by dense_binned_run)
+#ifdef RS_DB_STATS
+__device__ unsigned long long g_db_stats[8];
+#define DB_STAT( i, v ) atomicAdd( &g_db_stats[i], (unsigned long long)( v ) )
+#else
+#define DB_STAT( i, v ) do { } while( 0 )
+#endif
+
 // ------------------------------------------------------------------------------------------------ B: staged search
 __device__ __forceinline__ uint32_t db_smem_u32( const void* p ) { return (uint32_t)__cvta_generic_to_shared( p ); }
 __device__ __forceinline__ void db_mbar_init( uint64_t* bar, unsigned count )
@@ -453,6 +461,10 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
         if( want ) { want = box_gap_bits( B.blo[e], B.bhi[e], px, py, pz ) < (uint32_t)( best >> 32 ); } // all its points are farther
         if( want && !cone_possible_loaded( B.cone[e], cull, nx, ny, nz ) ) { want = false; closer += cn; } // none can be compatible
         if( !__any_sync( RS_FULL, want ) ) { continue; }
+#ifdef RS_DB_STATS
+        if( want ) { DB_STAT( 2, 1 ); DB_STAT( 3, cn ); }
+        if( lane == 0 ) { DB_STAT( 4, 1 ); DB_STAT( 5, cn ); }
+#endif
         const uint32_t gs = B.gs[e];
         const float4* __restrict__ rp = recs + ( staged ? B.so[e] : gs );
         const float4* __restrict__ np = nrm + ( staged ? B.so[e] : gs );
@@ -479,6 +491,11 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
       }
       const uint32_t dcb = (uint32_t)( best >> 32 );
       bool found = qv && dcb < r2bits;
+#ifdef RS_DB_STATS
+      if( qv ) { DB_STAT( 0, 1 ); DB_STAT( 1, found ? 1 : 0 ); }
+      if( lane == 0 ) { DB_STAT( 6, 1 ); }
+      if( found && closer >= uk ) { DB_STAT( 7, 1 ); }
+#endif
       // ---- rank of the winner under the k-cap (fewer than k points strictly closer): exact count only where the bound allows k
       const bool need = found && closer >= uk;
       if( __any_sync( RS_FULL, need ) )
@@ -737,6 +754,17 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
       RS_CHECK_LAUNCH();
     }
   }
+#ifdef RS_DB_STATS
+  {
+    unsigned long long h[8];
+    cudaStreamSynchronize( st );
+    cudaMemcpyFromSymbol( h, g_db_stats, sizeof( h ) );
+    fprintf( stderr, "dense search stats (cumulative): queries %llu found %llu (%.1f%%) | per query: cells swept %.2f records %.1f | per warp round (%llu rounds): cells %.2f records %.1f | "
+                     "lane efficiency %.1f%% | rank counts needed %llu\n", h[0], h[1], 100.0 * h[1] / (double)std::max( h[0], 1ull ), h[2] / (double)std::max( h[0], 1ull ),
+             h[3] / (double)std::max( h[0], 1ull ), h[6], h[4] / (double)std::max( h[6], 1ull ), h[5] / (double)std::max( h[6], 1ull ),
+             100.0 * h[3] / ( 32.0 * std::max( h[5], 1ull ) ), h[7] );
+  }
+#endif
   return RSGPU_OK;
 }
 } // namespace

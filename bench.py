@@ -31,6 +31,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before torch creates the CUDA context (rescan_b200/api.py)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -61,6 +63,11 @@ def workload_config(name, world, nms=True, exchange="nvlink", scaling="strong"):
             "stages": "grid build, dense search lvl 4, verification lvl 3/2, top-k" + (", NMS" if nms else "") + ", ICP, rescoring lvl 1"
                       + (", NMS" if nms else "") + ", sort",
             "l2": "flushed between steps (256 MiB write inside the timed region); working set is L2-resident within a step"}
+
+
+def synth_objects(name):
+    from rescan_b200 import synth
+    return int(synth.CONFIGS[name]["scene"]["n_objects"])
 
 
 def build_workload(name, world, scaling="strong"):
@@ -415,8 +422,8 @@ def main():
         if args.exchange == "nvlink":
             try:
                 from rescan_b200 import peerx
-                peer = peerx.PeerExchange(dist, rank, world, local_rank)
-                exchange_name = "nvlink (peer-mapped slots, copy engines; rescan_b200/peerx.py)"
+                peer = peerx.PeerExchange(dist, rank, world, local_rank, n_slots=max(64, synth_objects(name)))
+                exchange_name = "nvlink (one peer-mapped slot per object chain, copy engines, no collective order; rescan_b200/peerx.py)"
             except Exception as e:
                 print(f"bench.py: peer exchange unavailable ({e}); falling back to the host exchange", file=sys.stderr)
                 args.exchange = "host"

@@ -287,16 +287,20 @@ int rsgpu_plane_inlier_counts( const float* pts, const uint8_t* active, int32_t 
    of apps/pose_proposal/main.cpp:175-204, the refined rows.  rsgpu_peer_* is that all-gather over NVLink without an SM-resident
    collective kernel: every rank's receive area is mapped by all peers (CUDA IPC), payloads and round flags are written by
    copy engines, one warp waits for the flags.
-     rsgpu_peer_init      allocates this rank's area (slot_bytes = largest payload of one rank) and returns its IPC handle
-                          (rsgpu_peer_handle_bytes() bytes) for the caller to distribute (set-up, any transport);
+     rsgpu_peer_init      allocates this rank's area: n_slots independent exchange slots (one per object chain in flight; each
+                          double-buffered), slot_bytes = largest payload of one rank in one exchange; returns the area's IPC
+                          handle (rsgpu_peer_handle_bytes() bytes) for the caller to distribute (set-up, any transport);
      rsgpu_peer_open      handles = world x rsgpu_peer_handle_bytes() bytes, rank-major;
-     rsgpu_peer_allgather collective: `nbytes` (equal on every rank) from host `send` -> host `recv` [world][nbytes];
+     rsgpu_peer_allgather all-gather on slot `slot`: `nbytes` (equal on every rank) from host `send` -> host `recv`
+                          [world][nbytes].  seq = 1, 2, 3, ... counts the uses of THIS slot (identical on every rank).  Exchanges
+                          on different slots are independent: they may be issued from different host threads in any order,
+                          every rank in its own order (no global collective order).  Runs on the calling thread's lane stream.
                           timeout_s <= 0 means 30 s; a peer that never sends gives RSGPU_ERR_CUDA, not a hang;
      rsgpu_peer_close     every rank must have left its last rsgpu_peer_allgather (caller barrier) before any rank closes. */
 int rsgpu_peer_handle_bytes( void );
-int rsgpu_peer_init( int32_t rank, int32_t world, int64_t slot_bytes, void* handle_out );
+int rsgpu_peer_init( int32_t rank, int32_t world, int32_t n_slots, int64_t slot_bytes, void* handle_out );
 int rsgpu_peer_open( const void* handles );
-int rsgpu_peer_allgather( const void* send, int64_t nbytes, void* recv, double timeout_s );
+int rsgpu_peer_allgather( int32_t slot, uint32_t seq, const void* send, int64_t nbytes, void* recv, double timeout_s );
 int rsgpu_peer_close( void );
 
 #ifdef __cplusplus

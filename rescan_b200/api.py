@@ -22,6 +22,12 @@ Nothing in this module imports or calls ``oracle/``.
 """
 from __future__ import annotations
 
+import os as _os
+
+# tens of streams per process (one object chain per lane): more hardware channels than the default 8, so that unrelated
+# streams do not queue behind one another.  Effective only before the process creates its CUDA context.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import ctypes as C
 import os
 import numpy as np
@@ -115,9 +121,9 @@ SIGNATURES = {
     "rsgpu_neighborhood": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp]),
     "rsgpu_plane_inlier_counts": (_int, [_vp, _vp, _i32, _vp, _i32, _f32, _vp]),
     "rsgpu_peer_handle_bytes": (_int, []),
-    "rsgpu_peer_init": (_int, [_i32, _i32, _i64, _vp]),
+    "rsgpu_peer_init": (_int, [_i32, _i32, _i32, _i64, _vp]),
     "rsgpu_peer_open": (_int, [_vp]),
-    "rsgpu_peer_allgather": (_int, [_vp, _i64, _vp, C.c_double]),
+    "rsgpu_peer_allgather": (_int, [_i32, C.c_uint32, _vp, _i64, _vp, C.c_double]),
     "rsgpu_peer_close": (_int, []),
 }
 

@@ -603,7 +603,11 @@ __global__ void __launch_bounds__( 128 ) db_reduce_kernel( const uint32_t* __res
   if( lane == 0 ) { scores[pl] = (float)( sum / (double)n_obj ); } // (:156)
 }
 
-// scratch of one dense launch (per calling thread / lane, kept between calls: the pool hands the same blocks back)
+// scratch of the dense launches of one calling thread (= lane).  Kept between calls and only ever grown: ~1.4 GB per lane at
+// C3 size, and handing blocks of that size back to the stream-ordered pool after every launch makes the pool serve one
+// lane's next allocation from another lane's freed block - which it orders behind that lane's pending work
+// (cudaMemPoolReuseAllowInternalDependencies), i.e. a cross-lane dependency nobody asked for.  "dense_scratch" = "pool"
+// restores per-launch allocation (A/B).
 struct DbScratch
 {
   DevBuf<float4> upos, unor;
@@ -651,13 +655,13 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   P.chunk_poses_max = (size_t)tpc * n_rot;
   P.entries_max = P.chunk_poses_max * (size_t)n;
   P.items_max = P.entries_max / DB_QCHUNK + P.n_cells + 2;
-  RS_CUDA( S.upos.alloc( (size_t)n * n_rot ) ); RS_CUDA( S.unor.alloc( (size_t)n * n_rot ) );
-  RS_CUDA( S.bins.alloc( P.n_bins ) ); RS_CUDA( S.offs.alloc( P.n_bins ) );
-  RS_CUDA( S.pose_base.alloc( P.chunk_poses_max ) ); RS_CUDA( S.pose_cnt.alloc( P.chunk_poses_max ) );
-  RS_CUDA( S.queue.alloc( P.entries_max ) ); RS_CUDA( S.qbin.alloc( P.entries_max ) ); RS_CUDA( S.sorted.alloc( P.entries_max ) );
-  RS_CUDA( S.items.alloc( P.items_max ) ); RS_CUDA( S.terms.alloc( P.entries_max ) ); RS_CUDA( S.ctr.alloc( 1 ) );
+  RS_CUDA( S.upos.reserve( (size_t)n * n_rot ) ); RS_CUDA( S.unor.reserve( (size_t)n * n_rot ) );
+  RS_CUDA( S.bins.reserve( P.n_bins ) ); RS_CUDA( S.offs.reserve( P.n_bins ) );
+  RS_CUDA( S.pose_base.reserve( P.chunk_poses_max ) ); RS_CUDA( S.pose_cnt.reserve( P.chunk_poses_max ) );
+  RS_CUDA( S.queue.reserve( P.entries_max ) ); RS_CUDA( S.qbin.reserve( P.entries_max ) ); RS_CUDA( S.sorted.reserve( P.entries_max ) );
+  RS_CUDA( S.items.reserve( P.items_max ) ); RS_CUDA( S.terms.reserve( P.entries_max ) ); RS_CUDA( S.ctr.reserve( 1 ) );
   RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, P.scan_bytes, S.bins.p, S.offs.p, (int64_t)P.n_bins, rt().stream ) );
-  RS_CUDA( S.scan_tmp.alloc( P.scan_bytes ) );
+  RS_CUDA( S.scan_tmp.reserve( P.scan_bytes ) );
   return RSGPU_OK;
 }
 

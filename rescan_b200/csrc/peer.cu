@@ -2,83 +2,92 @@
 //
 // What travels: the per-object survivor lists of mgs_propose_poses (reference apps/pose_proposal/pose_proposal.cpp:348-359:
 // {xform, score} records + their dense pose ids), and later the ICP-refined rows (apps/pose_proposal/main.cpp:195-201) - a few KB
-// per step.  NCCL's all-gather for them needs most of an SM per channel and, issued mid-step, waits behind the thousands of
-// pending blocks of the dense search (14-18 ms, profiles/step_trace_r01_n2.txt).  Here every rank owns a receive area in
-// its HBM that all peers map through CUDA IPC; an all-gather is then
-//     my bytes -> slot [round % RING][my rank] of EVERY rank's area     (cudaMemcpyAsync peer copies: copy engines over NVLink)
-//     the round number -> flag [round % RING][my rank] of every rank     (a second, stream-ordered 4-byte peer copy)
-//     one 32-thread kernel on the receiver that spins until all flags of the round carry its number (with a time-out)
-// so the data path uses copy engines only and one warp for the wait.  One process per GPU; the IPC handles are exchanged
-// once at start-up by the caller (torch.distributed all_gather_object in rescan_b200/peerx.py) - set-up, not data path.
+// per object.  NCCL's all-gather for them needs most of an SM per channel and, issued mid-step, waits behind the thousands
+// of pending blocks of the dense search (14-18 ms, profiles/step_trace_r01_n2.txt); and a collective imposes ONE order of
+// exchanges on all ranks, which serialises the objects' chains.  Here every rank owns a receive area in its HBM that all
+// peers map through CUDA IPC, addressed by (slot, rank): an all-gather of slot s is
+//     my bytes -> [s][my rank] of EVERY rank's area       (cudaMemcpyAsync peer copies: copy engines over NVLink, no SM)
+//     host wait for those copies, then the sequence number -> flag [s][my rank] of every rank, in SHARED HOST MEMORY
+//     the receiver's host thread polls its own flags of slot s, then copies the slot out of its HBM
+// Exchanges of DIFFERENT slots share nothing: every object's chain (search -> exchange -> NMS -> refine -> exchange)
+// runs on its own host thread / stream and meets its peers whenever they get there.
 //
-// Ring: a rank can be at most one round ahead of the slowest rank when it SENDS (it cannot finish round s + 1 without
-// that rank's round-s + 1 data, which is sent after that rank read round s), so two buffers would do; RING = 4.
+// Why the flags are not in HBM with a kernel waiting on them (the first version): with one waiting kernel per chain in
+// flight, two ranks dead-lock through the GPU's hardware queues - the streams of a process are multiplexed onto a few
+// channels (CUDA_DEVICE_MAX_CONNECTIONS), so rank A's copy for object j can sit in a channel behind A's spinning wait for
+// object k while rank B's copy for object k sits behind B's wait for object j (observed: both ranks time out in the row
+// exchange of C3 with 8 lanes).  With the flags in host memory NOTHING ever waits on the device: the data plane is copy
+// engines over NVLink, the control plane is one 4-byte store per peer.
+//
+// One process per GPU on one host; the handles (CUDA IPC handle of the area + name of the flag segment) are exchanged once
+// at start-up by the caller (torch.distributed all_gather_object in rescan_b200/peerx.py) - set-up, not data path.
+//
+// Re-use of a slot: the caller passes a sequence number that grows by one per use of the slot.  Slots are double-buffered
+// by the parity of that number: a rank can send use q + 2 only after it received every peer's part of use q + 1, which a
+// peer sends only after it has read use q out of its area - so a write never lands on data still being read.
 #include "rsgpu_internal.cuh"
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
-#include <vector>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 using namespace rs;
 
 namespace
 {
-constexpr int RING = 4;
 constexpr int MAX_WORLD = 16;
+constexpr int NAME_BYTES = 64;
+
+struct PeerHandle // what the ranks hand round at set-up
+{
+  cudaIpcMemHandle_t mem;
+  char flags_name[NAME_BYTES];
+};
 
 struct PeerState
 {
-  int rank = -1, world = 0;
-  size_t slot_bytes = 0;            // capacity of one rank's slot in one ring buffer
-  unsigned char* area = nullptr;    // [RING][world][slot_bytes] received payloads   (cudaMalloc: IPC needs a plain allocation)
-  uint32_t* flags = nullptr;        // [RING][world] round numbers
-  unsigned char* send = nullptr;    // [RING][slot_bytes] my payload staged in HBM
-  uint32_t* seqs = nullptr;         // [RING] the round number as device words (source of the flag copies)
-  int* status = nullptr;            // wait kernel outcome
+  int rank = -1, world = 0, n_slots = 0;
+  size_t slot_bytes = 0;            // capacity of one rank's payload in one slot
+  unsigned char* base = nullptr;    // one IPC allocation: area [2][n_slots][world][slot_bytes]
+  unsigned char* send = nullptr;    // [2][n_slots][slot_bytes] my payload staged in HBM
   unsigned char* peer_area[MAX_WORLD] = {};
-  uint32_t* peer_flags[MAX_WORLD] = {};
   void* peer_base[MAX_WORLD] = {};  // what cudaIpcOpenMemHandle returned (to close it)
-  unsigned char* base = nullptr;    // one allocation: area | flags
-  size_t flags_off = 0;
-  cudaStream_t st = nullptr;
-  unsigned char* h_send = nullptr;  // pinned staging [RING][slot_bytes]
-  unsigned char* h_recv = nullptr;  // pinned [world][slot_bytes]
-  uint32_t* h_seq = nullptr;        // pinned [RING]
-  int* h_status = nullptr;
-  uint32_t round = 0;
+  uint32_t* peer_flags[MAX_WORLD] = {}; // every rank's flag segment [2][n_slots][MAX_WORLD], mapped from shared host memory
+  size_t flag_bytes = 0;
+  char flags_name[NAME_BYTES] = {};
+  unsigned char* h_send = nullptr;  // pinned [2][n_slots][slot_bytes]
+  unsigned char* h_recv = nullptr;  // pinned [2][n_slots][world][slot_bytes]
+  cudaStream_t st = nullptr;        // for callers without a lane
   bool open = false;
 };
 PeerState g_peer;
-std::mutex g_peer_mu;
+std::mutex g_peer_mu; // set-up / tear-down only; the exchanges of different slots share nothing
 
-// lane r < world waits until flags[r] == want; status 0 = ok, 1 = timed out (peer died / never sent)
-__global__ void __launch_bounds__( 32 ) peer_wait_kernel( const volatile uint32_t* flags, uint32_t want, int world, long long timeout_cycles,
-                                                          int* __restrict__ status )
+void unmap_flags( PeerState& p )
 {
-  const int lane = threadIdx.x;
-  bool ok = true;
-  if( lane < world )
+  for( int r = 0; r < MAX_WORLD; ++r )
   {
-    const long long t0 = clock64();
-    while( flags[lane] != want )
-    {
-      if( clock64() - t0 > timeout_cycles ) { ok = false; break; }
-      __nanosleep( 200 );
-    }
+    if( p.peer_flags[r] ) { munmap( p.peer_flags[r], p.flag_bytes ); p.peer_flags[r] = nullptr; }
   }
-  __threadfence_system();
-  const unsigned all = __ballot_sync( RS_FULL, ok );
-  if( lane == 0 ) { *status = all == RS_FULL ? 0 : 1; }
+  if( p.flags_name[0] ) { shm_unlink( p.flags_name ); p.flags_name[0] = 0; }
 }
 } // namespace
 
 extern "C" {
 
-int rsgpu_peer_handle_bytes( void ) { return (int)sizeof( cudaIpcMemHandle_t ); }
+int rsgpu_peer_handle_bytes( void ) { return (int)sizeof( PeerHandle ); }
 
-/* allocate this rank's receive area and return its IPC handle (rsgpu_peer_handle_bytes() bytes) */
-int rsgpu_peer_init( int32_t rank, int32_t world, int64_t slot_bytes, void* handle_out )
+/* allocate this rank's receive area + flag segment and return their handle (rsgpu_peer_handle_bytes() bytes) */
+int rsgpu_peer_init( int32_t rank, int32_t world, int32_t n_slots, int64_t slot_bytes, void* handle_out )
 {
-  if( rank < 0 || world < 1 || world > MAX_WORLD || rank >= world || slot_bytes <= 0 || !handle_out )
+  if( rank < 0 || world < 1 || world > MAX_WORLD || rank >= world || slot_bytes <= 0 || n_slots < 1 || !handle_out )
   {
     return fail( RSGPU_ERR_INVALID, "rsgpu_peer_init: bad argument (world <= 16)" );
   }
@@ -86,32 +95,38 @@ int rsgpu_peer_init( int32_t rank, int32_t world, int64_t slot_bytes, void* hand
   std::lock_guard<std::mutex> lk( g_peer_mu );
   PeerState& p = g_peer;
   if( p.base ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_init: already initialised (rsgpu_peer_close first)" ); }
-  p.rank = rank; p.world = world;
+  p.rank = rank; p.world = world; p.n_slots = n_slots;
   p.slot_bytes = ( (size_t)slot_bytes + 255 ) / 256 * 256;
-  const size_t area_bytes = (size_t)RING * world * p.slot_bytes;
-  p.flags_off = area_bytes;
-  RS_CUDA( cudaMalloc( (void**)&p.base, area_bytes + sizeof( uint32_t ) * RING * MAX_WORLD ) );
-  RS_CUDA( cudaMemset( p.base, 0, area_bytes + sizeof( uint32_t ) * RING * MAX_WORLD ) );
-  p.area = p.base; p.flags = (uint32_t*)( p.base + p.flags_off );
-  RS_CUDA( cudaMalloc( (void**)&p.send, (size_t)RING * p.slot_bytes ) );
-  RS_CUDA( cudaMalloc( (void**)&p.seqs, sizeof( uint32_t ) * RING ) );
-  RS_CUDA( cudaMalloc( (void**)&p.status, sizeof( int ) ) );
-  RS_CUDA( cudaHostAlloc( (void**)&p.h_send, (size_t)RING * p.slot_bytes, cudaHostAllocDefault ) );
-  RS_CUDA( cudaHostAlloc( (void**)&p.h_recv, (size_t)world * p.slot_bytes, cudaHostAllocDefault ) );
-  RS_CUDA( cudaHostAlloc( (void**)&p.h_seq, sizeof( uint32_t ) * RING, cudaHostAllocDefault ) );
-  RS_CUDA( cudaHostAlloc( (void**)&p.h_status, sizeof( int ), cudaHostAllocDefault ) );
+  const size_t area_bytes = (size_t)2 * n_slots * world * p.slot_bytes;
+  p.flag_bytes = sizeof( uint32_t ) * 2 * (size_t)n_slots * MAX_WORLD;
+  // the flag segment: POSIX shared memory, zero-filled, mapped by every rank of the host
+  snprintf( p.flags_name, NAME_BYTES, "/rsgpu_peer_%d_%d_%llx", (int)getpid(), (int)rank,
+            (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count() );
+  const int fd = shm_open( p.flags_name, O_CREAT | O_EXCL | O_RDWR, 0600 );
+  if( fd < 0 ) { p.flags_name[0] = 0; return fail( RSGPU_ERR_INVALID, "rsgpu_peer_init: shm_open failed (no /dev/shm?)" ); }
+  if( ftruncate( fd, (off_t)p.flag_bytes ) != 0 ) { close( fd ); unmap_flags( p ); return fail( RSGPU_ERR_OOM, "rsgpu_peer_init: ftruncate of the flag segment failed" ); }
+  void* fl = mmap( nullptr, p.flag_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0 );
+  close( fd );
+  if( fl == MAP_FAILED ) { unmap_flags( p ); return fail( RSGPU_ERR_OOM, "rsgpu_peer_init: mmap of the flag segment failed" ); }
+  p.peer_flags[rank] = (uint32_t*)fl;
+  RS_CUDA( cudaMalloc( (void**)&p.base, area_bytes ) ); // cudaMalloc: IPC needs a plain allocation
+  RS_CUDA( cudaMemset( p.base, 0, area_bytes ) );
+  RS_CUDA( cudaMalloc( (void**)&p.send, (size_t)2 * n_slots * p.slot_bytes ) );
+  RS_CUDA( cudaHostAlloc( (void**)&p.h_send, (size_t)2 * n_slots * p.slot_bytes, cudaHostAllocDefault ) );
+  RS_CUDA( cudaHostAlloc( (void**)&p.h_recv, (size_t)2 * n_slots * world * p.slot_bytes, cudaHostAllocDefault ) );
   int least = 0, greatest = 0;
   if( cudaDeviceGetStreamPriorityRange( &least, &greatest ) != cudaSuccess ) { cudaGetLastError(); least = greatest = 0; }
   RS_CUDA( cudaStreamCreateWithPriority( &p.st, cudaStreamNonBlocking, greatest ) );
-  cudaIpcMemHandle_t h;
-  RS_CUDA( cudaIpcGetMemHandle( &h, p.base ) );
+  PeerHandle h;
+  memset( &h, 0, sizeof( h ) );
+  RS_CUDA( cudaIpcGetMemHandle( &h.mem, p.base ) );
+  memcpy( h.flags_name, p.flags_name, NAME_BYTES );
   memcpy( handle_out, &h, sizeof( h ) );
   RS_CUDA( cudaDeviceSynchronize() );
-  p.round = 0;
   return RSGPU_OK;
 }
 
-/* handles = world x rsgpu_peer_handle_bytes() bytes, rank-major (this rank's own entry is ignored) */
+/* map every peer's area and flag segment; handles = world x rsgpu_peer_handle_bytes() bytes in rank order */
 int rsgpu_peer_open( const void* handles )
 {
   RS_TRY( ensure_device() );
@@ -120,66 +135,83 @@ int rsgpu_peer_open( const void* handles )
   if( !p.base || !handles ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_open: rsgpu_peer_init first" ); }
   for( int r = 0; r < p.world; ++r )
   {
-    if( r == p.rank ) { p.peer_area[r] = p.area; p.peer_flags[r] = p.flags; continue; }
-    cudaIpcMemHandle_t h;
+    if( r == p.rank ) { p.peer_area[r] = p.base; continue; }
+    PeerHandle h;
     memcpy( &h, (const unsigned char*)handles + sizeof( h ) * (size_t)r, sizeof( h ) );
+    h.flags_name[NAME_BYTES - 1] = 0;
     void* base = nullptr;
-    RS_CUDA( cudaIpcOpenMemHandle( &base, h, cudaIpcMemLazyEnablePeerAccess ) );
+    RS_CUDA( cudaIpcOpenMemHandle( &base, h.mem, cudaIpcMemLazyEnablePeerAccess ) );
     p.peer_base[r] = base;
     p.peer_area[r] = (unsigned char*)base;
-    p.peer_flags[r] = (uint32_t*)( (unsigned char*)base + p.flags_off );
+    const int fd = shm_open( h.flags_name, O_RDWR, 0600 );
+    if( fd < 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_open: a peer's flag segment cannot be opened (ranks on different hosts?)" ); }
+    void* fl = mmap( nullptr, p.flag_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0 );
+    close( fd );
+    if( fl == MAP_FAILED ) { return fail( RSGPU_ERR_OOM, "rsgpu_peer_open: mmap of a peer's flag segment failed" ); }
+    p.peer_flags[r] = (uint32_t*)fl;
   }
   p.open = true;
   return RSGPU_OK;
 }
 
-/* all-gather of `nbytes` (the same on every rank, <= the slot size) from host memory `send` into host memory `recv`
-   (world x nbytes, rank-major).  Collective: every rank calls it the same number of times in the same order. */
-int rsgpu_peer_allgather( const void* send, int64_t nbytes, void* recv, double timeout_s )
+/* all-gather of `nbytes` (the same on every rank, <= the slot size) of slot `slot` from host memory `send` into host memory
+   `recv` (world x nbytes, rank-major).  seq = how many times this slot has been used before, plus one (identical on every
+   rank).  Exchanges of different slots may run concurrently from different host threads, in any order. */
+int rsgpu_peer_allgather( int32_t slot, uint32_t seq, const void* send, int64_t nbytes, void* recv, double timeout_s )
 {
   RS_TRY( ensure_device() );
-  std::lock_guard<std::mutex> lk( g_peer_mu );
   PeerState& p = g_peer;
   if( !p.open ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: rsgpu_peer_open first" ); }
+  if( slot < 0 || slot >= p.n_slots || seq == 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: slot out of range / seq 0" ); }
   if( nbytes < 0 || (size_t)nbytes > p.slot_bytes || ( nbytes > 0 && ( !send || !recv ) ) )
   {
     return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: payload larger than the slot size given to rsgpu_peer_init" );
   }
-  RS_CUDA( cudaSetDevice( rt().device ) );
-  const uint32_t round = ++p.round;
-  const int buf = (int)( round % RING );
+  // the calling thread's own stream when it is attached to a lane (so concurrent exchanges do not queue behind one another)
+  cudaStream_t st = rt().stream ? rt().stream : p.st;
+  const size_t s = (size_t)( seq & 1u ) * p.n_slots + (size_t)slot; // double-buffered by the parity of seq
   const size_t nb = (size_t)nbytes;
-  unsigned char* hs = p.h_send + (size_t)buf * p.slot_bytes;
-  unsigned char* ds = p.send + (size_t)buf * p.slot_bytes;
-  if( nb ) { memcpy( hs, send, nb ); }
-  p.h_seq[buf] = round;
-  if( nb ) { RS_CUDA( cudaMemcpyAsync( ds, hs, nb, cudaMemcpyHostToDevice, p.st ) ); }
-  RS_CUDA( cudaMemcpyAsync( p.seqs + buf, p.h_seq + buf, sizeof( uint32_t ), cudaMemcpyHostToDevice, p.st ) );
-  // payload to every rank's slot [buf][my rank] (NVLink, copy engines), then - stream-ordered behind it - the flag
-  for( int k = 0; k < p.world; ++k )
+  unsigned char* hs = p.h_send + s * p.slot_bytes;
+  unsigned char* ds = p.send + s * p.slot_bytes;
+  unsigned char* hr = p.h_recv + s * p.world * p.slot_bytes;
+  if( nb )
   {
-    const int r = ( p.rank + k ) % p.world; // start with my own area, spread the peers
-    unsigned char* dst = p.peer_area[r] + ( (size_t)buf * p.world + p.rank ) * p.slot_bytes;
-    if( nb ) { RS_CUDA( cudaMemcpyAsync( dst, ds, nb, cudaMemcpyDeviceToDevice, p.st ) ); }
+    memcpy( hs, send, nb );
+    RS_CUDA( cudaMemcpyAsync( ds, hs, nb, cudaMemcpyHostToDevice, st ) );
+    // payload to [s][my rank] of every rank's area (NVLink, copy engines)
+    for( int k = 0; k < p.world; ++k )
+    {
+      const int r = ( p.rank + k ) % p.world; // start with my own area, spread the peers
+      unsigned char* dst = p.peer_area[r] + ( s * p.world + p.rank ) * p.slot_bytes;
+      RS_CUDA( cudaMemcpyAsync( dst, ds, nb, cudaMemcpyDeviceToDevice, st ) );
+    }
+    RS_CUDA( rs::stream_sync( st ) ); // the copies have landed ...
   }
-  for( int k = 0; k < p.world; ++k )
+  for( int k = 0; k < p.world; ++k )    // ... before any peer can see the flag
   {
     const int r = ( p.rank + k ) % p.world;
-    RS_CUDA( cudaMemcpyAsync( p.peer_flags[r] + (size_t)buf * MAX_WORLD + p.rank, p.seqs + buf, sizeof( uint32_t ), cudaMemcpyDeviceToDevice, p.st ) );
+    __atomic_store_n( p.peer_flags[r] + s * MAX_WORLD + p.rank, seq, __ATOMIC_RELEASE );
   }
-  int clock_khz = 1965000;
-  cudaDeviceGetAttribute( &clock_khz, cudaDevAttrClockRate, rt().device );
-  const long long timeout_cycles = (long long)( ( timeout_s > 0 ? timeout_s : 30.0 ) * 1e3 * (double)clock_khz );
-  peer_wait_kernel<<<1, 32, 0, p.st>>>( p.flags + (size_t)buf * MAX_WORLD, round, p.world, timeout_cycles, p.status );
-  RS_CHECK_LAUNCH();
-  RS_CUDA( cudaMemcpyAsync( p.h_status, p.status, sizeof( int ), cudaMemcpyDeviceToHost, p.st ) );
-  for( int r = 0; r < p.world && nb; ++r )
+  // wait for every rank's flag of this use: spin briefly, then yield / sleep (a peer may still be searching)
+  const uint32_t* mine = p.peer_flags[p.rank] + s * MAX_WORLD;
+  const auto t0 = std::chrono::steady_clock::now();
+  const double limit = timeout_s > 0 ? timeout_s : 30.0;
+  int have = 0;
+  for( unsigned spins = 0;; ++spins )
   {
-    RS_CUDA( cudaMemcpyAsync( p.h_recv + (size_t)r * nb, p.area + ( (size_t)buf * p.world + r ) * p.slot_bytes, nb, cudaMemcpyDeviceToHost, p.st ) );
+    while( have < p.world && __atomic_load_n( mine + have, __ATOMIC_ACQUIRE ) == seq ) { ++have; }
+    if( have == p.world ) { break; }
+    const double waited = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+    if( waited > limit ) { return fail( RSGPU_ERR_CUDA, "rsgpu_peer_allgather: timed out waiting for a peer's payload" ); }
+    if( waited > 50e-6 ) { std::this_thread::sleep_for( std::chrono::microseconds( waited > 2e-3 ? 100 : 20 ) ); }
   }
-  RS_CUDA( rs::stream_sync( p.st ) );
-  if( *p.h_status != 0 ) { return fail( RSGPU_ERR_CUDA, "rsgpu_peer_allgather: timed out waiting for a peer's payload" ); }
-  if( nb ) { memcpy( recv, p.h_recv, nb * (size_t)p.world ); }
+  if( nb )
+  {
+    // the `nb` used bytes of every rank's row of the slot, packed, in one copy
+    RS_CUDA( cudaMemcpy2DAsync( hr, nb, p.base + s * p.world * p.slot_bytes, p.slot_bytes, nb, (size_t)p.world, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( rs::stream_sync( st ) );
+    memcpy( recv, hr, nb * (size_t)p.world );
+  }
   return RSGPU_OK;
 }
 
@@ -187,14 +219,15 @@ int rsgpu_peer_close( void )
 {
   std::lock_guard<std::mutex> lk( g_peer_mu );
   PeerState& p = g_peer;
-  if( !p.base ) { return RSGPU_OK; }
+  if( !p.base ) { unmap_flags( p ); return RSGPU_OK; }
   cudaSetDevice( rt().device );
-  if( p.st ) { cudaStreamSynchronize( p.st ); }
+  cudaDeviceSynchronize();
   for( int r = 0; r < p.world; ++r ) { if( p.peer_base[r] ) { cudaIpcCloseMemHandle( p.peer_base[r] ); } }
-  cudaFree( p.base ); cudaFree( p.send ); cudaFree( p.seqs ); cudaFree( p.status );
-  cudaFreeHost( p.h_send ); cudaFreeHost( p.h_recv ); cudaFreeHost( p.h_seq ); cudaFreeHost( p.h_status );
+  cudaFree( p.base ); cudaFree( p.send );
+  cudaFreeHost( p.h_send ); cudaFreeHost( p.h_recv );
   if( p.st ) { cudaStreamDestroy( p.st ); }
   cudaGetLastError();
+  unmap_flags( p );
   p = PeerState();
   return RSGPU_OK;
 }

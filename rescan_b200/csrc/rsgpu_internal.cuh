@@ -57,6 +57,12 @@ struct DevBuf
     n = count;
     return cudaMallocAsync( (void**)&p, sizeof( T ) * ( count ? count : 1 ), rt().stream );
   }
+  // grow-only variant for scratch that a thread keeps between calls: reallocates only when `count` exceeds the capacity
+  cudaError_t reserve( size_t count )
+  {
+    if( p && count <= n ) { return cudaSuccess; }
+    return alloc( count );
+  }
 };
 
 // scoped per-kernel event timer (active only when profiling is enabled)

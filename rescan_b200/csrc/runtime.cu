@@ -161,6 +161,10 @@ int ensure_device()
   const int gen = g_dev_generation.load( std::memory_order_acquire );
   if( bound_generation == gen ) { return RSGPU_OK; }
   std::call_once( g_dev_once, []() {
+    // One object chain per lane = tens of streams per process; the default of 8 hardware channels makes unrelated streams
+    // queue behind one another (a lane's short high-priority launches behind another lane's dense search).  Only effective
+    // when this runs before the process creates its CUDA context; never overrides the user's own setting.
+    setenv( "CUDA_DEVICE_MAX_CONNECTIONS", "32", 0 );
     int n = 0;
     if( cudaGetDeviceCount( &n ) != cudaSuccess ) { cudaGetLastError(); n = 0; }
     g_dev_count.store( n );

@@ -311,7 +311,10 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
   // "dense_impl" = "warp" asks for the first design (one warp per pose, score_kernel_g) or the input is outside its envelope
   if( grid_mode && group_impl && option( "dense_impl" ) != "warp" && dense_binned_supported( obj, scene, ps ) )
   {
-    DbScratch S; DbPlan P;
+    static thread_local DbScratch tl_scratch; // released with the thread (after the context is gone the free fails harmlessly)
+    DbScratch pool_scratch;
+    DbScratch& S = option( "dense_scratch" ) == "pool" ? pool_scratch : tl_scratch;
+    DbPlan P;
     RS_TRY( dense_binned_alloc( S, P, obj, scene, ps, n_poses ) );
     const cudaStream_t lane_st2 = st;
     if( bulk_stream() != st )
@@ -336,7 +339,7 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
       cudaStreamWaitEvent( lane_st2, join, 0 );
       cudaEventDestroy( join );
     }
-    RS_CUDA( rs::stream_sync( lane_st2, true ) ); // the scratch dies here
+    RS_CUDA( rs::stream_sync( lane_st2, true ) ); // the scratch is free for this thread's next launch
     return status;
   }
   if( group_impl && n_split < ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP ) { n_split = ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP; }

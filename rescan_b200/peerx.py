@@ -1,7 +1,11 @@
 """All-gather of the pose-sharded step's small lists over NVLink, one process per GPU (include/rsgpu.h rsgpu_peer_*,
-rescan_b200/csrc/peer.cu): every rank's receive area in HBM is mapped by all peers through CUDA IPC, the payloads and round
-flags are written by copy engines, one warp waits.  What is exchanged is the survivor list of mgs_propose_poses (reference
-apps/pose_proposal/pose_proposal.cpp:348-359) and the refined rows of apps/pose_proposal/main.cpp:195-201.
+rescan_b200/csrc/peer.cu): every rank's receive area in HBM is mapped by all peers through CUDA IPC, the payloads and
+sequence flags are written by copy engines, one warp waits.  What is exchanged is the survivor list of mgs_propose_poses
+(reference apps/pose_proposal/pose_proposal.cpp:348-359) and the refined rows of apps/pose_proposal/main.cpp:195-201.
+
+The area is divided into SLOTS, one per object chain: exchanges on different slots share nothing, so every object's chain
+(search -> top-k exchange -> NMS -> refinement of this rank's share -> row exchange -> NMS) runs on its own lane thread and
+meets its peers whenever they get there - no global order of collectives (rescan_b200/pipeline.py).
 
 torch.distributed is used ONCE, at construction, to hand the 64-byte IPC handles round (all_gather_object) and for the
 barrier before the areas are freed; the data path never touches it."""
@@ -15,13 +19,14 @@ from . import api
 
 
 class PeerExchange:
-    def __init__(self, dist, rank, world, local_rank=None, slot_bytes=4 << 20, timeout_s=30.0):
+    def __init__(self, dist, rank, world, local_rank=None, n_slots=64, slot_bytes=64 << 10, timeout_s=30.0):
         self.dist, self.rank, self.world, self.timeout_s = dist, int(rank), int(world), float(timeout_s)
-        self.slot_bytes = int(slot_bytes)
+        self.n_slots, self.slot_bytes = int(n_slots), int(slot_bytes)
+        self._seq = [0] * self.n_slots  # uses of each slot so far; a slot is driven by one thread at a time
         L = api.lib()
         hb = L.rsgpu_peer_handle_bytes()
         mine = (C.c_ubyte * hb)()
-        api._check(L.rsgpu_peer_init(self.rank, self.world, self.slot_bytes, C.cast(mine, C.c_void_p)))
+        api._check(L.rsgpu_peer_init(self.rank, self.world, self.n_slots, self.slot_bytes, C.cast(mine, C.c_void_p)))
         self._live = True
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(mine))  # set-up only
@@ -31,14 +36,24 @@ class PeerExchange:
         api._check(L.rsgpu_peer_open(C.cast(buf, C.c_void_p)))
         dist.barrier()
 
-    def allgather(self, buf):
-        """equally sized byte buffers -> uint8 [world, nbytes]; every rank calls this in the same order"""
+    def allgather(self, buf, slot=0):
+        """equally sized byte buffers -> uint8 [world, nbytes] on `slot`; the uses of ONE slot are ordered identically on every
+        rank, different slots are independent (any thread, any order).  Payloads above the slot size go in pieces."""
         send = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
-        if send.nbytes > self.slot_bytes:
-            raise ValueError(f"peer exchange: payload of {send.nbytes} bytes exceeds the slot size {self.slot_bytes}")
+        slot = int(slot) % self.n_slots
         recv = np.empty((self.world, send.nbytes), np.uint8)
-        api._check(api.lib().rsgpu_peer_allgather(api._ptr(send), send.nbytes, api._ptr(recv), self.timeout_s))
+        L = api.lib()
+        for lo in range(0, max(send.nbytes, 1), self.slot_bytes):
+            piece = send[lo: lo + self.slot_bytes]
+            got = np.empty((self.world, piece.nbytes), np.uint8)
+            self._seq[slot] += 1
+            api._check(L.rsgpu_peer_allgather(slot, self._seq[slot], api._ptr(piece), piece.nbytes, api._ptr(got), self.timeout_s))
+            recv[:, lo: lo + piece.nbytes] = got
         return recv
+
+    def slot(self, slot):
+        """the exchange interface of pipeline._allgather_bytes bound to one slot"""
+        return _Slot(self, slot)
 
     def close(self):
         if getattr(self, "_live", False):
@@ -47,3 +62,11 @@ class PeerExchange:
                 self.dist.barrier()  # nobody may still be writing into an area that is about to be freed
             finally:
                 api.lib().rsgpu_peer_close()
+
+
+class _Slot:
+    def __init__(self, peer, slot):
+        self.peer, self.index = peer, int(slot)
+
+    def allgather(self, buf):
+        return self.peer.allgather(buf, self.index)

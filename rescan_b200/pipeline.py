@@ -320,9 +320,30 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
             return staged(k, "nms2", finish, m, props, ids, cand, upd)
         res = _run(pool, chain, list(enumerate(dyn)), big_first)
         out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
+    elif hasattr(host_group, "slot"):
+        # Pose-sharded over peer-mapped slots (peerx.PeerExchange): every object's chain is independent of the others - its
+        # two exchanges use the object's own slot, so a lane meets its peers whenever they get to that object and nothing
+        # orders the objects globally.  (No deadlock: every rank starts the chains in the same order and a lane takes the next
+        # object only when it finished one, so the earliest unfinished object is in flight on every rank.)
+        if len(dyn) > host_group.n_slots:
+            raise ValueError(f"peer exchange has {host_group.n_slots} slots for {len(dyn)} dynamic objects")
+
+        def chain(k, m):
+            slot = host_group.slot(k)
+            props, ids = staged(k, "search", search, m)
+            gp, gi = staged(k, "xchg_topk", exchange_topk, [props], [ids], top_k, dist, "cpu", slot)
+            props, ids = gp[0], gi[0]
+            if not do_icp:
+                return suppress(m, props, ids)
+            props, ids, cand = staged(k, "nms1", candidates, k, m, props, ids)
+            mine = staged(k, "refine", refine, m, props, cand[rank::world])  # this rank's interleaved share of the merged list
+            upd = staged(k, "xchg_rows", exchange_rows, [mine], [len(cand)], world, dist, "cpu", slot)[0]
+            return staged(k, "nms2", finish, m, props, ids, cand, upd)
+        res = _run(pool, chain, list(enumerate(dyn)), big_first)
+        out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
     else:
-        # Pose-sharded: the per-translation arg-max and the verification are rank-local, the per-object top-k lists are
-        # merged across ranks.  The objects go through in groups so that the refinement of one group overlaps the dense
+        # Pose-sharded with a COLLECTIVE transport (gloo / NCCL): the per-translation arg-max and the verification are
+        # rank-local, the per-object top-k lists are merged across ranks.  The objects go through in groups so that the refinement of one group overlaps the dense
         # search of the next: every collective is issued by THIS thread in a fixed order (top-k of group 0, 1, ..., then
         # the refined rows of group 0, 1, ...), identical on every rank whatever the timing of the lanes.
         n_groups = min(int(os.environ.get("RSGPU_GROUPS", "4")), max(1, len(dyn)))

@@ -1,4 +1,6 @@
-"""host-side stage trace of one pose-sharded step on every rank (torchrun):  torchrun ... scripts/trace_ranks.py [C2]"""
+"""host-side stage trace of one pose-sharded step on every rank (torchrun):  torchrun ... scripts/trace_ranks.py [C2|C3]
+   TRACE_EXCHANGE=peer (default: one peer-mapped slot per object chain) | gloo | nccl;  TRACE_FULL=1 prints every event"""
+import collections
 import os
 import sys
 
@@ -13,26 +15,42 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 api.set_device(local)
 dev = torch.device("cuda", local)
-if os.environ.get("TRACE_HP") == "1":
-    os.environ["TORCH_NCCL_HIGH_PRIORITY"] = "1"
 dist.init_process_group("nccl", device_id=dev)
 cfg = synth.CONFIGS[name]
 scene = synth.make_scene(**cfg["scene"])
 rot = posegrid.rotation_xforms(cfg["n_rot"])
-trans = synth.translation_seeds(scene.scan, cfg["n_seeds"] * world)
+trans = synth.translation_seeds(scene.scan, cfg["n_seeds"])  # one fixed problem, sharded (strong scaling)
 models = pipeline.upload_objects(scene.objects)
 args = ((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.nor(2)), models, rot, trans)
-hg = dist.new_group(backend="gloo") if os.environ.get("TRACE_GLOO") == "1" else None
-kw = dict(top_k=64, nms_dist=0.2, rank=rank, world=world, dist=dist, device=dev, host_group=hg)
-for _ in range(3):
+mode = os.environ.get("TRACE_EXCHANGE", "peer")
+hg = dist.new_group(backend="gloo") if mode == "gloo" else None
+peer = None
+if mode == "peer":
+    from rescan_b200 import peerx
+    peer = peerx.PeerExchange(dist, rank, world, local, n_slots=max(64, len(models)))
+kw = dict(top_k=64, nms_dist=0.2, rank=rank, world=world, dist=dist, device=dev, host_group=hg, peer=peer)
+for _ in range(2):
     pipeline.run_step(*args, **kw)
 dist.barrier()
 torch.cuda.synchronize()
+api.profile_reset()
+api.profile_enable(True)
 tr = pipeline.run_step(*args, trace=True, **kw).trace
+api.profile_enable(False)
+prof = {n: round(api.profile_get(n)[0], 1) for n in ("score_dense", "dense_prefilter", "dense_search", "score", "icp", "overlap")}
 for r in range(world):
     dist.barrier()
     if r == rank:
-        print(f"--- rank {rank}", flush=True)
+        print(f"--- rank {rank}  kernels (overlapping lanes, ms) {prof}", flush=True)
+        by = collections.defaultdict(list)
         for k, stage, a, b in tr:
-            print(f"  obj {k:2d} {stage:9s} {a * 1e3:7.2f} -> {b * 1e3:7.2f} ms  ({(b - a) * 1e3:6.2f})", flush=True)
+            by[stage].append((a, b))
+            if os.environ.get("TRACE_FULL") == "1":
+                print(f"  obj {k:2d} {stage:9s} {a * 1e3:7.2f} -> {b * 1e3:7.2f} ms  ({(b - a) * 1e3:6.2f})", flush=True)
+        for stage, v in by.items():
+            d = [b - a for a, b in v]
+            print(f"  {stage:10s} n {len(v):3d}  sum {sum(d) * 1e3:8.1f}  mean {sum(d) / len(d) * 1e3:7.2f}  max {max(d) * 1e3:7.2f}  "
+                  f"first start {min(a for a, b in v) * 1e3:7.1f}  last end {max(b for a, b in v) * 1e3:7.1f}", flush=True)
+if peer is not None:
+    peer.close()
 dist.destroy_process_group()

@@ -301,6 +301,14 @@ int rsgpu_peer_handle_bytes( void );
 int rsgpu_peer_init( int32_t rank, int32_t world, int32_t n_slots, int64_t slot_bytes, void* handle_out );
 int rsgpu_peer_open( const void* handles );
 int rsgpu_peer_allgather( int32_t slot, uint32_t seq, const void* send, int64_t nbytes, void* recv, double timeout_s );
+/* the two halves of an exchange, for rooted patterns (gather to the rank that owns an object's chain, broadcast of its result):
+     rsgpu_peer_put  use `seq` of `slot`: `nbytes` (may differ between ranks) from host `send` into this rank's row of the slot
+                     on every rank whose bit is set in dst_mask; returns when the payload has landed - it never waits for a peer;
+     rsgpu_peer_get  waits until every rank in src_mask has put use `seq` of `slot`, then copies the rows to host `recv`
+                     [world][row_bytes] and their lengths to nbytes_out[world] (0 for ranks outside the mask).
+   Every rank in a use's src_mask must be a sender of that use to this rank; a slot's uses are numbered identically on all ranks. */
+int rsgpu_peer_put( int32_t slot, uint32_t seq, uint32_t dst_mask, const void* send, int64_t nbytes );
+int rsgpu_peer_get( int32_t slot, uint32_t seq, uint32_t src_mask, void* recv, int64_t row_bytes, int64_t* nbytes_out, double timeout_s );
 int rsgpu_peer_close( void );
 
 #ifdef __cplusplus

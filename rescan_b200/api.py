@@ -124,6 +124,8 @@ SIGNATURES = {
     "rsgpu_peer_init": (_int, [_i32, _i32, _i32, _i64, _vp]),
     "rsgpu_peer_open": (_int, [_vp]),
     "rsgpu_peer_allgather": (_int, [_i32, C.c_uint32, _vp, _i64, _vp, C.c_double]),
+    "rsgpu_peer_put": (_int, [_i32, C.c_uint32, C.c_uint32, _vp, _i64]),
+    "rsgpu_peer_get": (_int, [_i32, C.c_uint32, C.c_uint32, _vp, _i64, _vp, C.c_double]),
     "rsgpu_peer_close": (_int, []),
 }
 

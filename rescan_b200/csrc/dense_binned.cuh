@@ -655,11 +655,19 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   P.chunk_poses_max = (size_t)tpc * n_rot;
   P.entries_max = P.chunk_poses_max * (size_t)n;
   P.items_max = P.entries_max / DB_QCHUNK + P.n_cells + 2;
-  RS_CUDA( S.upos.reserve( (size_t)n * n_rot ) ); RS_CUDA( S.unor.reserve( (size_t)n * n_rot ) );
+  // capacities that do not depend on the object, so that a lane's scratch is allocated ONCE per scan size: every object's
+  // worst case is just under `cap` entries, each by a different margin - growing the buffers by those margins meant
+  // freeing and re-allocating a gigabyte per lane whenever a slightly bigger object came along (steps of 100-500 ms
+  // instead of 33 on C2 until every lane had met the biggest one)
+  const size_t entries_alloc = std::max( cap, P.entries_max );
+  const size_t poses_alloc = std::max( (size_t)DB_POSE_MAX, P.chunk_poses_max );
+  const size_t items_alloc = entries_alloc / DB_QCHUNK + P.n_cells + 2;
+  const size_t cloud_alloc = std::max( (size_t)n * n_rot, (size_t)DB_MAX_PTS * 128 );
+  RS_CUDA( S.upos.reserve( cloud_alloc ) ); RS_CUDA( S.unor.reserve( cloud_alloc ) );
   RS_CUDA( S.bins.reserve( P.n_bins ) ); RS_CUDA( S.offs.reserve( P.n_bins ) );
-  RS_CUDA( S.pose_base.reserve( P.chunk_poses_max ) ); RS_CUDA( S.pose_cnt.reserve( P.chunk_poses_max ) );
-  RS_CUDA( S.queue.reserve( P.entries_max ) ); RS_CUDA( S.qbin.reserve( P.entries_max ) ); RS_CUDA( S.sorted.reserve( P.entries_max ) );
-  RS_CUDA( S.items.reserve( P.items_max ) ); RS_CUDA( S.terms.reserve( P.entries_max ) ); RS_CUDA( S.ctr.reserve( 1 ) );
+  RS_CUDA( S.pose_base.reserve( poses_alloc ) ); RS_CUDA( S.pose_cnt.reserve( poses_alloc ) );
+  RS_CUDA( S.queue.reserve( entries_alloc ) ); RS_CUDA( S.qbin.reserve( entries_alloc ) ); RS_CUDA( S.sorted.reserve( entries_alloc ) );
+  RS_CUDA( S.items.reserve( items_alloc ) ); RS_CUDA( S.terms.reserve( entries_alloc ) ); RS_CUDA( S.ctr.reserve( 1 ) );
   RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, P.scan_bytes, S.bins.p, S.offs.p, (int64_t)P.n_bins, rt().stream ) );
   RS_CUDA( S.scan_tmp.reserve( P.scan_bytes ) );
   return RSGPU_OK;

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 using namespace rs;
 
@@ -289,7 +290,7 @@ __device__ __forceinline__ void icp_correspond_batch( const GridView& g, const f
   unsigned long long seedkey = ~0ull; float seeddot = 0.f;
   if( fastq && warm )
   {
-    const uint32_t prev = cm[i].x;
+    const uint32_t prev = __ldcg( &cm[i] ).x; // written by another block in the previous iteration: never through L1
     if( prev != 0xffffffffu )
     {
       const float4 rec = __ldg( g.recs + prev ), mm = __ldg( g.nrm + prev );
@@ -345,14 +346,14 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   if( EXACT )
   {
     int mine = 0;
-    for( int i = tid; i < c1n; i += ICP_THREADS ) { mine += cm[i].x != 0xffffffffu; }
+    for( int i = tid; i < c1n; i += ICP_THREADS ) { mine += __ldcg( &cm[i] ).x != 0xffffffffu; }
     {
       double v[1] = { (double)mine };
       block_reduce<1>( v, sh );
       nc = (int)sh.out[0];
     }
     ordered_sums<2, false>( c1n,
-      [&]( int i ) { CorrIn1 in; in.pos = cm[i].x; in.d = cq[i].w; return in; },
+      [&]( int i ) { CorrIn1 in; in.pos = __ldcg( &cm[i] ).x; in.d = __ldcg( &cq[i] ).w; return in; },
       [&]( const CorrIn1& in, float* t ) { if( in.pos != 0xffffffffu ) { t[0] = in.d; t[1] = __fmul_rn( in.d, in.d ); } },
       tile, fout, dout );
     sum_d = fout[0]; sum_dd = fout[1];
@@ -362,7 +363,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
     double v[3] = { 0, 0, 0 };
     for( int i = tid; i < c1n; i += ICP_THREADS )
     {
-      if( cm[i].x != 0xffffffffu ) { float d = cq[i].w; v[0] += 1.0; v[1] += (double)d; v[2] += (double)__fmul_rn( d, d ); }
+      if( __ldcg( &cm[i] ).x != 0xffffffffu ) { float d = __ldcg( &cq[i] ).w; v[0] += 1.0; v[1] += (double)d; v[2] += (double)__fmul_rn( d, d ); }
     }
     block_reduce<3>( v, sh );
     nc = (int)sh.out[0]; sum_d = (float)sh.out[1]; sum_dd = (float)sh.out[2];
@@ -384,7 +385,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   if( EXACT )
   {
     ordered_sums<7, false>( c1n,
-      [&]( int i ) { CorrIn2 in; in.m = cm[i]; in.q = cq[i]; in.p2 = cp[i]; return in; },
+      [&]( int i ) { CorrIn2 in; in.m = __ldcg( &cm[i] ); in.q = __ldcg( &cq[i] ); in.p2 = __ldcg( &cp[i] ); return in; },
       [&]( const CorrIn2& in, float* t ) {
         if( in.m.x == 0xffffffffu ) { return; }
         const float w = weight( in.q, in.m );
@@ -400,11 +401,11 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
     double v[7] = { 0, 0, 0, 0, 0, 0, 0 };
     for( int i = tid; i < c1n; i += ICP_THREADS )
     {
-      uint2 m = cm[i];
+      uint2 m = __ldcg( &cm[i] );
       if( m.x == 0xffffffffu ) { continue; }
-      float4 q = cq[i];
+      float4 q = __ldcg( &cq[i] );
       float w = weight( q, m );
-      float4 p2 = cp[i];
+      float4 p2 = __ldcg( &cp[i] );
       v[0] += (double)w;
       v[1] += (double)__fmul_rn( q.x, w ); v[2] += (double)__fmul_rn( q.y, w ); v[3] += (double)__fmul_rn( q.z, w );
       v[4] += (double)__fmul_rn( p2.x, w ); v[5] += (double)__fmul_rn( p2.y, w ); v[6] += (double)__fmul_rn( p2.z, w );
@@ -421,7 +422,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   __syncthreads();
   // ---- (B3) normal equations (icp.h:226-252): TL = sum w c c^T, TR = sum w c n^T, BR = sum w n n^T, b = sum w [c;n] (d.n)
   // 29 terms per correspondence: TL (6 unique), TR (9), BR (6 unique), b (6), w (d.n)^2, w
-  auto load29 = [&]( int i ) { CorrIn3 in; in.m = cm[i]; in.q = cq[i]; in.p2 = cp[i]; in.nn = cn[i]; return in; };
+  auto load29 = [&]( int i ) { CorrIn3 in; in.m = __ldcg( &cm[i] ); in.q = __ldcg( &cq[i] ); in.p2 = __ldcg( &cp[i] ); in.nn = __ldcg( &cn[i] ); return in; };
   auto terms29 = [&]( const CorrIn3& in, float* t ) -> bool {
     const uint2 m = in.m;
     if( m.x == 0xffffffffu ) { return false; }
@@ -632,6 +633,125 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_solve_kernel( GridView g, c
   }
 }
 
+// ---- variant 3 (default): ONE persistent launch per batch, driven by a device-side work queue.  The iteration-
+// synchronous split needs two launches per iteration and a host look at the running count every four: with eight objects'
+// batches in flight that is ~1 300 launches per C2 step funnelled through the driver from eight host threads, and every
+// one of them queues for an SM slot behind the dense search's resident blocks - the eight ICP batches of a step then take
+// as long side by side as one after the other (measured: 12-16 ms each in flight together, 3 ms alone).  Here nothing
+// returns to the host between the first search and the last solve:
+//   * a work item = (alignment, chunk of 8 x pts_per_task consecutive object points); the queue is a plain array that is
+//     only ever appended to (capacity = every chunk of every possible iteration), `tail` reserves, `head` hands out
+//     tickets, a consumer waits until ITS slot is published;
+//   * a block takes an item and its eight warps search 8 x pts_per_task correspondences (icp_correspond_batch);
+//   * the block that completes an alignment's last chunk of the iteration (per-alignment arrival counter) runs the
+//     reference-order sums, the 6x6 solve and the update for it (icp_update), and - unless the stopping rule fired -
+//     appends the alignment's chunks for the next iteration; alignments advance independently of one another;
+//   * the block that retires the last alignment appends one TERMINATE item per block of the grid.
+// No block ever waits for a block that is not running (an item exists only after it has been published, and whoever holds
+// one is resident), so the grid needs no co-residency and can be smaller or larger than the machine.  Per-alignment
+// scratch written by one block and read by another goes through L2 only (__ldcg / volatile; plain stores are write-through).
+struct IcpQueue
+{
+  unsigned head, tail, remaining, pad;
+};
+constexpr unsigned ICPQ_EMPTY = 0xffffffffu, ICPQ_TERMINATE = 0xfffffffeu;
+constexpr int ICPQ_CHUNK_BITS = 13; // chunks per alignment < 8192 (1 M points at 16 per task x 8 warps), alignments < 2^19 - 1
+
+template <bool EXACT>
+__global__ void __launch_bounds__( ICP_THREADS, 2 ) icp_persistent_kernel( GridView g, const IcpBlock* __restrict__ blocks, IcpState* state,
+                                                                         const unsigned* __restrict__ n_chunks, unsigned* arrived, IcpQueue* q,
+                                                                         unsigned* items, int pts_per_task, const float* __restrict__ T2i, float dot_thr,
+                                                                         int max_iter, float4* scratch_q, uint2* scratch_m, float4* scratch_p, float4* scratch_n )
+{
+  extern __shared__ __align__( 16 ) float tile[]; // solve: two tiles of the ordered sums; search: the warps' cell tables and slots
+  __shared__ IcpShared sh;
+  __shared__ float fout[32];
+  __shared__ double dout[32];
+  __shared__ float s_T[16], s_M[16];
+  __shared__ unsigned s_item, s_last, s_base;
+  uint4* s_cand = (uint4*)tile;                                                                          // [ICP_WARPS][CAND_WORDS]
+  unsigned char* s_slot = (unsigned char*)( s_cand + ICP_WARPS * rsg::GroupCfg<ICP_G>::CAND_WORDS );      // [ICP_WARPS][32]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if( tid < 16 ) { s_M[tid] = T2i[tid]; }
+  volatile unsigned* vitems = items;
+  for( ;; )
+  {
+    if( tid == 0 )
+    {
+      const unsigned ticket = atomicAdd( &q->head, 1u );
+      unsigned it;
+      while( ( it = vitems[ticket] ) == ICPQ_EMPTY ) { __nanosleep( 100 ); }
+      __threadfence(); // the state the publisher wrote before the item
+      s_item = it;
+    }
+    __syncthreads();
+    const unsigned item = s_item;
+    if( item == ICPQ_TERMINATE ) { break; }
+    const int a = (int)( item >> ICPQ_CHUNK_BITS ), chunk = (int)( item & ( ( 1u << ICPQ_CHUNK_BITS ) - 1u ) );
+    const IcpBlock blk = blocks[a];
+    const volatile IcpState* vs = state + a;
+    if( tid < 16 ) { s_T[tid] = vs->T[tid]; }
+    const float cur_max_dist = vs->max_dist;
+    const int cur_steps = vs->steps;
+    __syncthreads();
+    // ---- (A) this chunk's correspondences
+    {
+      const double radius = (double)cur_max_dist;
+      const float r2f = (float)__dmul_rn( radius, radius );
+      const int ib = ( chunk * ICP_WARPS + warp ) * pts_per_task;
+      if( ib < blk.n )
+      {
+        icp_correspond_batch( g, s_T, s_M, blk.p1, blk.n1, blk.n, ib, pts_per_task, cur_steps > 0, radius, r2f, dot_thr,
+                              scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, scratch_p + blk.scratch_off, scratch_n + blk.scratch_off,
+                              s_cand + warp * rsg::GroupCfg<ICP_G>::CAND_WORDS, s_slot + warp * 32 );
+      }
+    }
+    __threadfence(); // every thread's correspondences are in L2 before the arrival is counted
+    __syncthreads();
+    if( tid == 0 )
+    {
+      const unsigned old = atomicAdd( arrived + a, 1u );
+      s_last = old + 1u == n_chunks[a] ? 1u : 0u;
+      if( s_last ) { arrived[a] = 0u; }
+      __threadfence(); // the other blocks' correspondences, counted before ours
+    }
+    __syncthreads();
+    if( !s_last ) { continue; }
+    // ---- (B) + (C): this block completed the alignment's iteration
+    if( tid < 16 ) { sh.T[tid] = vs->T[tid]; }
+    if( tid == 0 ) { sh.max_dist = cur_max_dist; sh.prev_err = vs->err; sh.err = vs->err; sh.stop = 0; sh.steps = cur_steps; }
+    __syncthreads();
+    const bool updated = icp_update<EXACT>( g, blk.n, scratch_q + blk.scratch_off, scratch_m + blk.scratch_off, scratch_p + blk.scratch_off,
+                                                scratch_n + blk.scratch_off, cur_steps, sh, tile, fout, dout );
+    __syncthreads();
+    const bool more = updated && !sh.stop && cur_steps + 1 < max_iter;
+    if( tid < 16 ) { state[a].T[tid] = sh.T[tid]; }
+    if( tid == 0 )
+    {
+      state[a].max_dist = sh.max_dist; state[a].prev_err = sh.prev_err; state[a].err = sh.err; state[a].steps = sh.steps;
+      state[a].active = more ? 1 : 0;
+    }
+    __threadfence(); // the new state before the items that announce it
+    __syncthreads();
+    if( more )
+    {
+      const unsigned nch = n_chunks[a];
+      if( tid == 0 ) { s_base = atomicAdd( &q->tail, nch ); }
+      __syncthreads();
+      for( unsigned c = tid; c < nch; c += ICP_THREADS ) { vitems[s_base + c] = ( (unsigned)a << ICPQ_CHUNK_BITS ) | c; }
+    }
+    else if( tid == 0 )
+    {
+      if( atomicSub( &q->remaining, 1u ) == 1u )
+      {
+        const unsigned base = atomicAdd( &q->tail, gridDim.x );
+        for( unsigned c = 0; c < gridDim.x; ++c ) { vitems[base + c] = ICPQ_TERMINATE; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // msh_mat4_inverse (msh_vec_math.h:1818-1917): cofactor expansion over 2x2 minors, all float, each cofactor
 // a three-term expression evaluated left to right, scaled by 1.0f/det
 float tri( float a, float x, float b, float y, float c, float z, int s2, int s3 )
@@ -724,8 +844,11 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   if( max_iter <= 0 ) { max_iter = 100; }
   // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
   const bool exact = option( "icp_sums" ) != "fp64";
-  // RSGPU_ICP_IMPL=block selects one resident block per alignment instead of the iteration-synchronous split
-  const bool split = option( "icp_impl" ) != "block";
+  // "icp_impl": default = one persistent launch with a device-side work queue; "split" = two launches per iteration over all
+  // running alignments (round 1's default); "block" = one resident block per alignment
+  const std::string impl = option( "icp_impl" );
+  const bool split = impl != "block";
+  bool persistent = split && impl != "split";
   cudaStream_t st = rt().stream;
   float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
   mat4_inverse_ref( T2 ? T2 : ident, T2i );
@@ -778,7 +901,74 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   const size_t tile_bytes = 2 * sizeof( float ) * ICP_THREADS * TILE_LD; // two tiles (ordered_sums)
   const float dot_thr = compat_threshold_acosf( max_angle );
   std::vector<float> herr( total ); std::vector<int> hit( total );
-  if( split )
+  // the persistent variant's work list: chunks of ICP_WARPS x TPT points per alignment, every chunk of every possible iteration
+  std::vector<unsigned> h_chunks( persistent ? total : 0 );
+  size_t chunks_total = 0, live = 0;
+  if( persistent )
+  {
+    for( size_t i = 0; i < total; ++i )
+    {
+      const size_t c = ( (size_t)( hb[i].n > 0 ? hb[i].n : 0 ) + (size_t)ICP_WARPS * TPT - 1 ) / ( (size_t)ICP_WARPS * TPT );
+      if( c >= ( (size_t)1 << ICPQ_CHUNK_BITS ) || total >= ( (size_t)1 << ( 32 - ICPQ_CHUNK_BITS ) ) - 2 ) { persistent = false; break; }
+      h_chunks[i] = (unsigned)c; chunks_total += c; live += c > 0;
+    }
+    if( chunks_total * (size_t)max_iter + 4096 > ( (size_t)1 << 28 ) ) { persistent = false; } // queue above 1 GB: use the split variant
+  }
+  if( persistent && live > 0 )
+  {
+    DevBuf<IcpState> dS; DevBuf<unsigned> dchunks, darrived, ditems; DevBuf<IcpQueue> dq;
+    int n_sm = 148;
+    cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, rt().device );
+    // blocks of the launch: enough to search every alignment's chunks of one iteration at once, capped - the batches of
+    // other objects and the dense search want the SMs too ("icp_ctas")
+    unsigned n_ctas = 96;
+    { const std::string o = option( "icp_ctas" ); if( !o.empty() ) { n_ctas = (unsigned)std::max( 1, atoi( o.c_str() ) ); } }
+    n_ctas = (unsigned)std::min<size_t>( n_ctas, chunks_total );
+    const size_t q_cap = chunks_total * (size_t)max_iter + n_ctas;
+    RS_CUDA( dS.alloc( total ) ); RS_CUDA( dchunks.alloc( total ) ); RS_CUDA( darrived.alloc( total ) ); RS_CUDA( ditems.alloc( q_cap ) ); RS_CUDA( dq.alloc( 1 ) );
+    RS_CUDA( cudaMemcpyAsync( dS.p, hs.data(), sizeof( IcpState ) * total, cudaMemcpyHostToDevice, st ) );
+    RS_CUDA( cudaMemcpyAsync( dchunks.p, h_chunks.data(), sizeof( unsigned ) * total, cudaMemcpyHostToDevice, st ) );
+    RS_CUDA( cudaMemsetAsync( darrived.p, 0, sizeof( unsigned ) * total, st ) );
+    RS_CUDA( cudaMemsetAsync( ditems.p, 0xff, sizeof( unsigned ) * q_cap, st ) ); // ICPQ_EMPTY
+    std::vector<unsigned> first; first.reserve( chunks_total );
+    for( size_t i = 0; i < total; ++i ) { for( unsigned c = 0; c < h_chunks[i]; ++c ) { first.push_back( ( (unsigned)i << ICPQ_CHUNK_BITS ) | c ); } }
+    RS_CUDA( cudaMemcpyAsync( ditems.p, first.data(), sizeof( unsigned ) * first.size(), cudaMemcpyHostToDevice, st ) );
+    IcpQueue hq; hq.head = 0; hq.tail = (unsigned)first.size(); hq.remaining = (unsigned)live; hq.pad = 0;
+    RS_CUDA( cudaMemcpyAsync( dq.p, &hq, sizeof( hq ), cudaMemcpyHostToDevice, st ) );
+    const size_t search_bytes = sizeof( uint4 ) * ICP_WARPS * rsg::GroupCfg<ICP_G>::CAND_WORDS + ICP_WARPS * 32;
+    const size_t smem = exact ? std::max( tile_bytes, search_bytes ) : search_bytes;
+    {
+      static std::once_flag once;
+      cudaError_t ae = cudaSuccess;
+      std::call_once( once, [&]() {
+        ae = cudaFuncSetAttribute( icp_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max( tile_bytes, search_bytes ) );
+        if( ae == cudaSuccess ) { ae = cudaFuncSetAttribute( icp_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_bytes ); }
+      } );
+      RS_CUDA( ae );
+    }
+    {
+      ProfScope prof( "icp" );
+      if( exact )
+      {
+        icp_persistent_kernel<true><<<n_ctas, ICP_THREADS, smem, st>>>( scan->view(), dB.p, dS.p, dchunks.p, darrived.p, dq.p, ditems.p, TPT, dT2i.p, dot_thr, max_iter,
+                                                                          sq.p, sm.p, sp.p, sn.p );
+      }
+      else
+      {
+        icp_persistent_kernel<false><<<n_ctas, ICP_THREADS, smem, st>>>( scan->view(), dB.p, dS.p, dchunks.p, darrived.p, dq.p, ditems.p, TPT, dT2i.p, dot_thr, max_iter,
+                                                                           sq.p, sm.p, sp.p, sn.p );
+      }
+      RS_CHECK_LAUNCH();
+    }
+    RS_CUDA( cudaMemcpyAsync( hs.data(), dS.p, sizeof( IcpState ) * total, cudaMemcpyDeviceToHost, st ) );
+    RS_CUDA( rs::stream_sync( st, true ) );
+    for( size_t i = 0; i < total; ++i ) { memcpy( &hT[i * 16], hs[i].T, 64 ); herr[i] = hs[i].err; hit[i] = hs[i].steps; }
+  }
+  else if( persistent ) // nothing but empty clouds: the reference leaves every one with err = 1e6 and its pose untouched (icp.h:444-456)
+  {
+    for( size_t i = 0; i < total; ++i ) { herr[i] = 1e6f; hit[i] = 0; }
+  }
+  else if( split )
   {
     DevBuf<IcpState> dS;
     RS_CUDA( dS.alloc( total ) );

@@ -26,7 +26,9 @@
 // by the parity of that number: a rank can send use q + 2 only after it received every peer's part of use q + 1, which a
 // peer sends only after it has read use q out of its area - so a write never lands on data still being read.
 #include "rsgpu_internal.cuh"
+#include <algorithm>
 #include <atomic>
+#include <string>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -98,7 +100,7 @@ int rsgpu_peer_init( int32_t rank, int32_t world, int32_t n_slots, int64_t slot_
   p.rank = rank; p.world = world; p.n_slots = n_slots;
   p.slot_bytes = ( (size_t)slot_bytes + 255 ) / 256 * 256;
   const size_t area_bytes = (size_t)2 * n_slots * world * p.slot_bytes;
-  p.flag_bytes = sizeof( uint32_t ) * 2 * (size_t)n_slots * MAX_WORLD;
+  p.flag_bytes = sizeof( uint32_t ) * 2 * ( 2 * (size_t)n_slots * MAX_WORLD ); // flags [2][n_slots][MAX_WORLD] | lengths, same shape
   // the flag segment: POSIX shared memory, zero-filled, mapped by every rank of the host
   snprintf( p.flags_name, NAME_BYTES, "/rsgpu_peer_%d_%d_%llx", (int)getpid(), (int)rank,
             (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count() );
@@ -154,63 +156,121 @@ int rsgpu_peer_open( const void* handles )
   return RSGPU_OK;
 }
 
-/* all-gather of `nbytes` (the same on every rank, <= the slot size) of slot `slot` from host memory `send` into host memory
-   `recv` (world x nbytes, rank-major).  seq = how many times this slot has been used before, plus one (identical on every
-   rank).  Exchanges of different slots may run concurrently from different host threads, in any order. */
-int rsgpu_peer_allgather( int32_t slot, uint32_t seq, const void* send, int64_t nbytes, void* recv, double timeout_s )
+namespace
+{
+inline uint32_t* flag_of( PeerState& p, int owner_rank, size_t s, int writer ) { return p.peer_flags[owner_rank] + s * MAX_WORLD + writer; }
+inline uint32_t* len_of( PeerState& p, int owner_rank, size_t s, int writer )
+{
+  return p.peer_flags[owner_rank] + (size_t)2 * p.n_slots * MAX_WORLD + s * MAX_WORLD + writer;
+}
+inline int check_slot( PeerState& p, const char* what, int32_t slot, uint32_t seq )
+{
+  if( !p.open ) { return fail( RSGPU_ERR_INVALID, std::string( what ) + ": rsgpu_peer_open first" ); }
+  if( slot < 0 || slot >= p.n_slots || seq == 0 ) { return fail( RSGPU_ERR_INVALID, std::string( what ) + ": slot out of range / seq 0" ); }
+  return RSGPU_OK;
+}
+} // namespace
+
+/* use `seq` of slot `slot`, sending side: `nbytes` (<= the slot size; may differ from rank to rank) from host memory `send`
+   into this rank's row of the slot in the area of every rank whose bit is set in dst_mask, then - once the copies have
+   landed - the length and the sequence number into those ranks' flag segments.  Does not wait for anybody. */
+int rsgpu_peer_put( int32_t slot, uint32_t seq, uint32_t dst_mask, const void* send, int64_t nbytes )
 {
   RS_TRY( ensure_device() );
   PeerState& p = g_peer;
-  if( !p.open ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: rsgpu_peer_open first" ); }
-  if( slot < 0 || slot >= p.n_slots || seq == 0 ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: slot out of range / seq 0" ); }
-  if( nbytes < 0 || (size_t)nbytes > p.slot_bytes || ( nbytes > 0 && ( !send || !recv ) ) )
+  RS_TRY( check_slot( p, "rsgpu_peer_put", slot, seq ) );
+  if( nbytes < 0 || (size_t)nbytes > p.slot_bytes || ( nbytes > 0 && !send ) )
   {
-    return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: payload larger than the slot size given to rsgpu_peer_init" );
+    return fail( RSGPU_ERR_INVALID, "rsgpu_peer_put: payload larger than the slot size given to rsgpu_peer_init" );
   }
   // the calling thread's own stream when it is attached to a lane (so concurrent exchanges do not queue behind one another)
   cudaStream_t st = rt().stream ? rt().stream : p.st;
   const size_t s = (size_t)( seq & 1u ) * p.n_slots + (size_t)slot; // double-buffered by the parity of seq
   const size_t nb = (size_t)nbytes;
-  unsigned char* hs = p.h_send + s * p.slot_bytes;
-  unsigned char* ds = p.send + s * p.slot_bytes;
-  unsigned char* hr = p.h_recv + s * p.world * p.slot_bytes;
   if( nb )
   {
+    unsigned char* hs = p.h_send + s * p.slot_bytes;
+    unsigned char* ds = p.send + s * p.slot_bytes;
     memcpy( hs, send, nb );
     RS_CUDA( cudaMemcpyAsync( ds, hs, nb, cudaMemcpyHostToDevice, st ) );
-    // payload to [s][my rank] of every rank's area (NVLink, copy engines)
-    for( int k = 0; k < p.world; ++k )
+    for( int k = 0; k < p.world; ++k ) // payload to [s][my rank] of the destinations' areas (NVLink, copy engines)
     {
       const int r = ( p.rank + k ) % p.world; // start with my own area, spread the peers
-      unsigned char* dst = p.peer_area[r] + ( s * p.world + p.rank ) * p.slot_bytes;
-      RS_CUDA( cudaMemcpyAsync( dst, ds, nb, cudaMemcpyDeviceToDevice, st ) );
+      if( !( ( dst_mask >> r ) & 1u ) ) { continue; }
+      RS_CUDA( cudaMemcpyAsync( p.peer_area[r] + ( s * p.world + p.rank ) * p.slot_bytes, ds, nb, cudaMemcpyDeviceToDevice, st ) );
     }
     RS_CUDA( rs::stream_sync( st ) ); // the copies have landed ...
   }
-  for( int k = 0; k < p.world; ++k )    // ... before any peer can see the flag
+  for( int k = 0; k < p.world; ++k )   // ... before any peer can see the flag
   {
     const int r = ( p.rank + k ) % p.world;
-    __atomic_store_n( p.peer_flags[r] + s * MAX_WORLD + p.rank, seq, __ATOMIC_RELEASE );
+    if( !( ( dst_mask >> r ) & 1u ) ) { continue; }
+    __atomic_store_n( len_of( p, r, s, p.rank ), (uint32_t)nb, __ATOMIC_RELAXED );
+    __atomic_store_n( flag_of( p, r, s, p.rank ), seq, __ATOMIC_RELEASE );
   }
-  // wait for every rank's flag of this use: spin briefly, then yield / sleep (a peer may still be searching)
-  const uint32_t* mine = p.peer_flags[p.rank] + s * MAX_WORLD;
+  return RSGPU_OK;
+}
+
+/* use `seq` of slot `slot`, receiving side: waits until every rank whose bit is set in src_mask has put its payload, then
+   copies the rows into host memory `recv` [world][row_bytes] (rows of ranks outside the mask are left untouched) and their
+   lengths into nbytes_out[world] (0 outside the mask).  timeout_s <= 0 means 30 s. */
+int rsgpu_peer_get( int32_t slot, uint32_t seq, uint32_t src_mask, void* recv, int64_t row_bytes, int64_t* nbytes_out, double timeout_s )
+{
+  RS_TRY( ensure_device() );
+  PeerState& p = g_peer;
+  RS_TRY( check_slot( p, "rsgpu_peer_get", slot, seq ) );
+  if( row_bytes < 0 || !nbytes_out || ( row_bytes > 0 && !recv ) ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_get: bad argument" ); }
+  cudaStream_t st = rt().stream ? rt().stream : p.st;
+  const size_t s = (size_t)( seq & 1u ) * p.n_slots + (size_t)slot;
+  // wait for the flags of this use: spin briefly, then sleep (a peer may still be searching)
   const auto t0 = std::chrono::steady_clock::now();
   const double limit = timeout_s > 0 ? timeout_s : 30.0;
   int have = 0;
-  for( unsigned spins = 0;; ++spins )
+  for( ;; )
   {
-    while( have < p.world && __atomic_load_n( mine + have, __ATOMIC_ACQUIRE ) == seq ) { ++have; }
+    while( have < p.world && ( !( ( src_mask >> have ) & 1u ) || __atomic_load_n( flag_of( p, p.rank, s, have ), __ATOMIC_ACQUIRE ) == seq ) ) { ++have; }
     if( have == p.world ) { break; }
     const double waited = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
-    if( waited > limit ) { return fail( RSGPU_ERR_CUDA, "rsgpu_peer_allgather: timed out waiting for a peer's payload" ); }
+    if( waited > limit ) { return fail( RSGPU_ERR_CUDA, "rsgpu_peer_get: timed out waiting for a peer's payload" ); }
     if( waited > 50e-6 ) { std::this_thread::sleep_for( std::chrono::microseconds( waited > 2e-3 ? 100 : 20 ) ); }
   }
-  if( nb )
+  size_t widest = 0;
+  for( int r = 0; r < p.world; ++r )
   {
-    // the `nb` used bytes of every rank's row of the slot, packed, in one copy
-    RS_CUDA( cudaMemcpy2DAsync( hr, nb, p.base + s * p.world * p.slot_bytes, p.slot_bytes, nb, (size_t)p.world, cudaMemcpyDeviceToHost, st ) );
+    const size_t len = ( ( src_mask >> r ) & 1u ) ? (size_t)__atomic_load_n( len_of( p, p.rank, s, r ), __ATOMIC_RELAXED ) : 0;
+    if( len > (size_t)row_bytes ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_get: a peer's payload is longer than row_bytes" ); }
+    nbytes_out[r] = (int64_t)len;
+    widest = std::max( widest, len );
+  }
+  if( widest )
+  {
+    unsigned char* hr = p.h_recv + s * p.world * p.slot_bytes;
+    // the used bytes of every rank's row of the slot, packed, in one copy
+    RS_CUDA( cudaMemcpy2DAsync( hr, widest, p.base + s * p.world * p.slot_bytes, p.slot_bytes, widest, (size_t)p.world, cudaMemcpyDeviceToHost, st ) );
     RS_CUDA( rs::stream_sync( st ) );
-    memcpy( recv, hr, nb * (size_t)p.world );
+    for( int r = 0; r < p.world; ++r )
+    {
+      if( nbytes_out[r] > 0 ) { memcpy( (unsigned char*)recv + (size_t)r * (size_t)row_bytes, hr + (size_t)r * widest, (size_t)nbytes_out[r] ); }
+    }
+  }
+  return RSGPU_OK;
+}
+
+/* all-gather of `nbytes` (the same on every rank, <= the slot size) of slot `slot` from host memory `send` into host memory
+   `recv` (world x nbytes, rank-major): a put to every rank followed by a get from every rank.  seq = how many times this
+   slot has been used before, plus one (identical on every rank).  Exchanges of different slots may run concurrently from
+   different host threads, in any order. */
+int rsgpu_peer_allgather( int32_t slot, uint32_t seq, const void* send, int64_t nbytes, void* recv, double timeout_s )
+{
+  PeerState& p = g_peer;
+  RS_TRY( check_slot( p, "rsgpu_peer_allgather", slot, seq ) );
+  const uint32_t all = p.world >= 32 ? 0xffffffffu : ( ( 1u << p.world ) - 1u );
+  RS_TRY( rsgpu_peer_put( slot, seq, all, send, nbytes ) );
+  int64_t lens[MAX_WORLD];
+  RS_TRY( rsgpu_peer_get( slot, seq, all, recv, nbytes, lens, timeout_s ) );
+  for( int r = 0; r < p.world; ++r )
+  {
+    if( lens[r] != nbytes ) { return fail( RSGPU_ERR_INVALID, "rsgpu_peer_allgather: the ranks sent payloads of different sizes" ); }
   }
   return RSGPU_OK;
 }

@@ -326,6 +326,14 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
       cudaStreamWaitEvent( st, fork, 0 );
       cudaEventDestroy( fork );
     }
+    // One dense search at a time: each one fills the GPU on its own, so launches of several lanes side by side only
+    // interleave their blocks and ALL finish late (C2, 8 lanes: every search done at 12-17 ms instead of one every 1.6 ms),
+    // and the latency-bound chains behind them (verification, NMS, ICP) then all start together and fight for launch
+    // slots.  Taken in turn, the first object's chain runs beside the second object's search, and so on.
+    // "dense_serial" = "0" restores the free-for-all (A/B).
+    static std::mutex dense_mu;
+    std::unique_lock<std::mutex> dense_lock( dense_mu, std::defer_lock );
+    if( option( "dense_serial" ) != "0" ) { dense_lock.lock(); }
     int status;
     {
       ProfScope prof( "score_dense", st );
@@ -339,7 +347,9 @@ int score_launch( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const Pos
       cudaStreamWaitEvent( lane_st2, join, 0 );
       cudaEventDestroy( join );
     }
-    RS_CUDA( rs::stream_sync( lane_st2, true ) ); // the scratch is free for this thread's next launch
+    const cudaError_t se = rs::stream_sync( lane_st2, true ); // the scratch is free for this thread's next launch
+    if( dense_lock.owns_lock() ) { dense_lock.unlock(); }
+    RS_CUDA( se );
     return status;
   }
   if( group_impl && n_split < ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP ) { n_split = ( obj->n + SC_LIST_CAP - 1 ) / SC_LIST_CAP; }

@@ -19,7 +19,7 @@ from . import api
 
 
 class PeerExchange:
-    def __init__(self, dist, rank, world, local_rank=None, n_slots=64, slot_bytes=64 << 10, timeout_s=30.0):
+    def __init__(self, dist, rank, world, local_rank=None, n_slots=64, slot_bytes=256 << 10, timeout_s=30.0):
         self.dist, self.rank, self.world, self.timeout_s = dist, int(rank), int(world), float(timeout_s)
         self.n_slots, self.slot_bytes = int(n_slots), int(slot_bytes)
         self._seq = [0] * self.n_slots  # uses of each slot so far; a slot is driven by one thread at a time
@@ -50,6 +50,35 @@ class PeerExchange:
             api._check(L.rsgpu_peer_allgather(slot, self._seq[slot], api._ptr(piece), piece.nbytes, api._ptr(got), self.timeout_s))
             recv[:, lo: lo + piece.nbytes] = got
         return recv
+
+    # ---- rooted patterns: the two halves of one use of a slot (gather to an owner, broadcast from it)
+    def begin_use(self, slot):
+        """number of the next use of `slot`; every rank numbers a slot's uses identically, whatever its role in them"""
+        slot = int(slot) % self.n_slots
+        self._seq[slot] += 1
+        return self._seq[slot]
+
+    @staticmethod
+    def _mask(ranks):
+        m = 0
+        for r in ranks:
+            m |= 1 << int(r)
+        return m
+
+    def put(self, slot, seq, dst_ranks, buf):
+        """this rank's payload of use `seq` into its row of `slot` on the ranks `dst_ranks`; never waits for a peer"""
+        send = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+        if send.nbytes > self.slot_bytes:
+            raise ValueError(f"peer exchange: payload of {send.nbytes} bytes exceeds the slot size {self.slot_bytes} (PeerExchange(slot_bytes=...))")
+        api._check(api.lib().rsgpu_peer_put(int(slot) % self.n_slots, int(seq), self._mask(dst_ranks), api._ptr(send), send.nbytes))
+
+    def get(self, slot, seq, src_ranks):
+        """waits for the payloads the ranks `src_ranks` put for use `seq` of `slot` -> {rank: uint8 array}"""
+        rows = np.empty((self.world, self.slot_bytes), np.uint8)
+        lens = np.zeros(self.world, np.int64)
+        api._check(api.lib().rsgpu_peer_get(int(slot) % self.n_slots, int(seq), self._mask(src_ranks), api._ptr(rows), self.slot_bytes,
+                                            api._ptr(lens), self.timeout_s))
+        return {int(r): rows[int(r), : int(lens[int(r)])].copy() for r in src_ranks}
 
     def slot(self, slot):
         """the exchange interface of pipeline._allgather_bytes bound to one slot"""

@@ -321,26 +321,55 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         res = _run(pool, chain, list(enumerate(dyn)), big_first)
         out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
     elif hasattr(host_group, "slot"):
-        # Pose-sharded over peer-mapped slots (peerx.PeerExchange): every object's chain is independent of the others - its
-        # two exchanges use the object's own slot, so a lane meets its peers whenever they get to that object and nothing
-        # orders the objects globally.  (No deadlock: every rank starts the chains in the same order and a lane takes the next
-        # object only when it finished one, so the earliest unfinished object is in flight on every rank.)
-        if len(dyn) > host_group.n_slots:
-            raise ValueError(f"peer exchange has {host_group.n_slots} slots for {len(dyn)} dynamic objects")
+        # Pose-sharded over peer-mapped slots (peerx.PeerExchange).  Every object has an OWNER rank: all ranks search their
+        # block of translations for it and put their top-k list into the owner's area (a gather: nobody but the owner
+        # waits); the owner merges, suppresses, refines ALL survivors, rescoring and second NMS included, and puts the final
+        # list into every rank's area, where it is picked up at the end of the step.  The chain behind the search is
+        # latency-bound (a few dozen dependent ICP iterations, greedy NMS rounds), so refining 1/N of every object's
+        # candidates on every rank - the first version - left each rank with ALL the chains; with owners a rank runs 1/N of
+        # them, and the NMS is no longer replicated.  Exchanges use the object's own slot, so nothing orders the objects
+        # globally.  (No deadlock: every rank starts the chains in the same order, only owners ever wait, and the earliest
+        # object some rank has not searched yet is never behind a blocked lane of that rank - everything ahead of it has
+        # been searched by all ranks, so the gathers its lanes wait for complete.)
+        peer = host_group
+        if len(dyn) > peer.n_slots:
+            raise ValueError(f"peer exchange has {peer.n_slots} slots for {len(dyn)} dynamic objects")
+        owner = [0] * len(dyn)
+        for pos, k in enumerate(big_first):
+            owner[k] = pos % world  # the big objects (long ICP chains) dealt round the ranks
+        everyone = list(range(world))
+        uses = {k: (peer.begin_use(k), peer.begin_use(k)) for k in range(len(dyn))}  # (gather, broadcast) of this step
+
+        def pack(props, ids):
+            return np.concatenate([np.asarray(ids, np.int64).view(np.uint8), np.ascontiguousarray(props, np.float32).reshape(-1).view(np.uint8)])
+
+        def unpack(buf):
+            n = len(buf) // (8 + 4 * api.POSE_FLOATS)
+            return buf[8 * n:].view(np.float32).reshape(n, api.POSE_FLOATS).copy(), buf[: 8 * n].view(np.int64).copy()
 
         def chain(k, m):
-            slot = host_group.slot(k)
+            use_gather, use_bcast = uses[k]
             props, ids = staged(k, "search", search, m)
-            gp, gi = staged(k, "xchg_topk", exchange_topk, [props], [ids], top_k, dist, "cpu", slot)
-            props, ids = gp[0], gi[0]
+            staged(k, "put_topk", peer.put, k, use_gather, [owner[k]], pack(props, ids))
+            if owner[k] != rank:
+                return None
+            got = staged(k, "gather", peer.get, k, use_gather, everyone)
+            lists = [unpack(got[r]) for r in everyone]
+            props, ids = merge_topk([l[0] for l in lists], [l[1] for l in lists], top_k)
             if not do_icp:
-                return suppress(m, props, ids)
-            props, ids, cand = staged(k, "nms1", candidates, k, m, props, ids)
-            mine = staged(k, "refine", refine, m, props, cand[rank::world])  # this rank's interleaved share of the merged list
-            upd = staged(k, "xchg_rows", exchange_rows, [mine], [len(cand)], world, dist, "cpu", slot)[0]
-            return staged(k, "nms2", finish, m, props, ids, cand, upd)
+                props, ids = suppress(m, props, ids)
+            else:
+                props, ids, cand = staged(k, "nms1", candidates, k, m, props, ids)
+                upd = staged(k, "refine", refine, m, props, cand)
+                props, ids = staged(k, "nms2", finish, m, props, ids, cand, upd)
+            staged(k, "bcast", peer.put, k, use_bcast, [r for r in everyone if r != rank], pack(props, ids))
+            return props, ids
         res = _run(pool, chain, list(enumerate(dyn)), big_first)
-        out_props, out_ids = [r[0] for r in res], [r[1] for r in res]
+        out_props, out_ids = [None] * len(dyn), [None] * len(dyn)
+        for k, r in enumerate(res):
+            if r is None:  # another rank's object: its final list has been (or is being) put into this rank's area
+                r = unpack(staged(k, "collect", peer.get, k, uses[k][1], [owner[k]])[owner[k]])
+            out_props[k], out_ids[k] = r
     else:
         # Pose-sharded with a COLLECTIVE transport (gloo / NCCL): the per-translation arg-max and the verification are
         # rank-local, the per-object top-k lists are merged across ranks.  The objects go through in groups so that the refinement of one group overlaps the dense

@@ -22,7 +22,7 @@ args = ((scene.scan.pos(1), scene.scan.nor(1)), (scene.scan.pos(2), scene.scan.n
 if n_steps > 1:
     pipeline.run_step(*args, top_k=64, nms_dist=NMS, lanes=LANES)  # warm-up
 api.profile_reset()
-api.profile_enable(True)
+api.profile_enable(os.environ.get("STEP_PROFILE", "1") != "0")
 t0 = time.perf_counter()
 for _ in range(n_steps):
     res = pipeline.run_step(*args, top_k=64, nms_dist=NMS, lanes=LANES)

@@ -21,7 +21,7 @@ def scene():
 @pytest.fixture(autouse=True)
 def _restore_options():
     yield
-    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps"):
+    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps", "icp_ctas", "dense_scratch"):
         api.set_option(name, None)
 
 
@@ -133,10 +133,21 @@ def test_icp_variants_bit_identical(scene):
         starts.append(np.stack([common.colmajor(m) for _, m in common.perturbed_poses(rng, type("S", (), {"objects": [o]})(), 5, 0.03, 0.08)]))
     ang = np.float32(np.deg2rad(60.0))
     base = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
-    api.set_option("icp_impl", "block")
-    alt = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
-    for (Ta, ea, ia), (Tb, eb, ib) in zip(base, alt):
-        assert (ia == ib).all() and (ea == eb).all() and (Ta == Tb).all()
+    # default = one persistent launch with a device work queue; "split" = two launches per iteration; "block" = one resident
+    # block per alignment; "icp_ctas" = size of the persistent grid (1 block: every chunk and every solve on the same block)
+    for opt, val in (("icp_impl", "block"), ("icp_impl", "split"), ("icp_ctas", "1"), ("icp_ctas", "7"), ("icp_ctas", "512")):
+        api.set_option(opt, val)
+        alt = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
+        api.set_option(opt, None)
+        for (Ta, ea, ia), (Tb, eb, ib) in zip(base, alt):
+            assert (ia == ib).all() and (ea == eb).all() and (Ta == Tb).all(), (opt, val)
+    # an iteration cap below the natural count stops both variants at the same iteration
+    o = objs[0]
+    a = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
+    api.set_option("icp_impl", "split")
+    b = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
+    api.set_option("icp_impl", None)
+    assert (a[2] == b[2]).all() and (a[0] == b[0]).all() and (a[1] == b[1]).all() and int(a[2].max()) <= 7
     assert max(int(i.max()) for _, _, i in base) > 6
 
 

@@ -40,7 +40,7 @@ constexpr int DB_PTS_BITS = 12;                   // object points per cloud on 
 constexpr int DB_MAX_PTS = 1 << DB_PTS_BITS;
 constexpr uint32_t DB_POSE_MAX = 1u << ( 32 - DB_PTS_BITS ); // poses per chunk
 constexpr uint32_t DB_DONE = 0xffffffffu;
-constexpr int DB_NCLS = 8;                        // sub-bins per cell: the query normal's dominant axis and sign (6 used)
+constexpr int DB_NCLS = 64;                       // sub-bins per ACTIVE cell: octant of the query inside the cell x class of its normal
 
 // ------------------------------------------------------------------------------------------------ P: rotated clouds
 __global__ void db_prepare_kernel( const float* __restrict__ pos, const float* __restrict__ nor, int n, const float* __restrict__ rots, int n_rot,
@@ -100,7 +100,7 @@ struct DbCounters
 // around the clamped home cell: last-bit cases) - they go to the generic search.
 template <int WARPS>
 __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g, DbPoseGrid pg, long long pose0, unsigned n_chunk_poses, ScoreParams sp,
-                                                                      double prune_cnt, int n_pad, DbCounters* __restrict__ ctr,
+                                                                      double prune_cnt, int n_pad, int sub_mode, DbCounters* __restrict__ ctr,
                                                                       uint32_t* __restrict__ bins, uint32_t* __restrict__ pose_base,
                                                                       uint32_t* __restrict__ pose_cnt, uint2* __restrict__ queue,
                                                                       uint2* __restrict__ qbin )
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
   const float tx = __ldg( pg.trans + 3 * t ), ty = __ldg( pg.trans + 3 * t + 1 ), tz = __ldg( pg.trans + 3 * t + 2 );
   const float4* __restrict__ up = pg.upos + (size_t)r * pg.n;
   const float4* __restrict__ un = pg.unor + (size_t)r * pg.n;
-  const uint32_t n_cells = (uint32_t)g.W * (uint32_t)g.H * (uint32_t)g.D;
+  const uint32_t n_cells = g.n_active; // bins are indexed by the rank of the home cell among the active cells
   int n_list = 0;
   for( int ib = 0; ib < pg.n; ib += 32 )
   {
@@ -162,11 +162,16 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
             const float4 lo = __ldg( g.nbox + 2 * (size_t)ccid ), hi = __ldg( g.nbox + 2 * (size_t)ccid + 1 );
             active = box_gap_bits( lo, hi, px, py, pz ) < __float_as_uint( sp.r2f );
           }
-          // sub-bin: dominant axis and sign of the query normal (queries of a warp of the search then face the same way, so
-          // the per-cell normal-cone culling skips whole cells)
+          // sub-bin = (octant of the query inside its home cell, class of its normal).  The 32 queries a warp of the search
+          // takes are consecutive in this order: same octant = the same three faces / three edges / one corner of the
+          // block are near, so the lanes agree on which cells are worth sweeping; same dominant axis and sign of the
+          // normal = the per-cell normal-cone test skips the same cells.  (Order only: results do not depend on it.)
           const float ax = fabsf( nx ), ay = fabsf( ny ), az = fabsf( nz );
           const int cls = ay >= ax && ay >= az ? ( ny < 0.f ? 1 : 0 ) : ( ax >= az ? ( nx < 0.f ? 3 : 2 ) : ( nz < 0.f ? 5 : 4 ) );
-          bin = ccid * DB_NCLS + (uint32_t)cls;
+          const float icell = (float)g.inv_cell;
+          const int oct = ( w.qx * icell - (float)ccx >= 0.5f ? 1 : 0 ) | ( w.qy * icell - (float)ccy >= 0.5f ? 2 : 0 ) | ( w.qz * icell - (float)ccz >= 0.5f ? 4 : 0 );
+          const int sub = sub_mode == 1 ? cls : ( sub_mode == 2 ? oct * 8 : oct * 8 + cls );
+          if( active ) { bin = __ldg( g.crank + ccid ) * DB_NCLS + (uint32_t)sub; }
         }
       }
     }
@@ -197,9 +202,9 @@ __global__ void __launch_bounds__( 32 * WARPS ) db_prefilter_kernel( GridView g,
 
 // ------------------------------------------------------------------------------------------------ S: items + scatter
 // bins has been scanned (exclusive) into offs; one thread per cell appends the cell's work items
-__global__ void db_items_kernel( const uint32_t* __restrict__ offs, uint32_t n_cells, DbCounters* __restrict__ ctr, uint2* __restrict__ items )
+__global__ void db_items_kernel( const uint32_t* __restrict__ offs, uint32_t n_cells /* active */, DbCounters* __restrict__ ctr, uint2* __restrict__ items )
 {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; // rank of an active cell
   if( c >= n_cells ) { return; }
   const uint32_t a = offs[(size_t)c * DB_NCLS], b = offs[(size_t)( c + 1 ) * DB_NCLS];
   if( a == b ) { return; }
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
         break;
       }
       const uint2 im = __ldg( items + item );
-      const uint32_t c0 = im.x;
+      const uint32_t c0 = __ldg( g.acells + im.x ); // item = (rank of the active cell, first query)
       const int c0x = (int)( c0 % (uint32_t)g.W ); const uint32_t rr = c0 / (uint32_t)g.W;
       const int c0y = (int)( rr % (uint32_t)g.H ), c0z = (int)( rr / (uint32_t)g.H );
       uint32_t s = 0, n = 0;
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, Db
       if( lane < 27 ) { B.gs[lane] = s; B.cn[lane] = n; B.so[lane] = so; B.cone[lane] = cone; B.blo[lane] = blo; B.bhi[lane] = bhi; }
       if( lane == 0 )
       {
-        B.cell = c0; B.q_begin = im.y; const uint32_t qe = __ldg( offs + (size_t)( c0 + 1 ) * DB_NCLS ); B.q_end = min( im.y + (uint32_t)DB_QCHUNK, qe );
+        B.cell = c0; B.q_begin = im.y; const uint32_t qe = __ldg( offs + (size_t)( im.x + 1 ) * DB_NCLS ); B.q_end = min( im.y + (uint32_t)DB_QCHUNK, qe );
         B.staged = staged ? 1u : 0u;
       }
       __syncwarp(); // the block description of all lanes is ordered before lane 0's (releasing) arrive
@@ -622,15 +627,16 @@ struct DbScratch
 // chunk (every point of every pose survives the prefilter) fits the queue - nothing can overflow, nothing is re-tried.
 struct DbPlan
 {
-  size_t n_cells = 0, n_bins = 0, entries_max = 0, items_max = 0, chunk_poses_max = 0, scan_bytes = 0;
+  size_t n_cells = 0, n_active = 0, n_bins = 0, entries_max = 0, items_max = 0, chunk_poses_max = 0, scan_bytes = 0;
   long long trans_per_chunk = 0, n_trans = 0;
 };
 
 bool dense_binned_supported( const rsgpu_cloud_t* obj, const rsgpu_grid_t* scene, const PoseSource& ps )
 {
   const size_t n_cells = (size_t)scene->info.width * scene->info.height * scene->info.depth;
-  return obj->n >= 1 && obj->n <= DB_MAX_PTS && ps.n_rot >= 1 && ps.n_rot <= 4096 && n_cells * DB_NCLS + 2 < ( (size_t)1 << 28 ) && scene->has_normals &&
-         scene->info.n_pts > 0;
+  (void)n_cells;
+  return obj->n >= 1 && obj->n <= DB_MAX_PTS && ps.n_rot >= 1 && ps.n_rot <= 4096 && (size_t)scene->n_active * DB_NCLS + 2 < ( (size_t)1 << 28 ) &&
+         scene->has_normals && scene->info.n_pts > 0 && scene->crank.p && scene->n_active > 0;
 }
 
 // allocations of a launch (on the calling thread's stream: BEFORE the launch is forked to the bulk stream, so that the
@@ -640,7 +646,8 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   const int n = obj->n, n_rot = ps.n_rot;
   P.n_cells = (size_t)scene->info.width * scene->info.height * scene->info.depth;
   P.n_trans = n_poses / n_rot;
-  P.n_bins = P.n_cells * DB_NCLS + 2; // + the fallback bin + the end of the scan
+  P.n_active = scene->n_active;
+  P.n_bins = P.n_active * DB_NCLS + 2; // + the fallback bin + the end of the scan
   size_t cap = (size_t)32 << 20;
   {
     const std::string o = option( "dense_cap" );
@@ -654,14 +661,14 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   P.trans_per_chunk = tpc;
   P.chunk_poses_max = (size_t)tpc * n_rot;
   P.entries_max = P.chunk_poses_max * (size_t)n;
-  P.items_max = P.entries_max / DB_QCHUNK + P.n_cells + 2;
+  P.items_max = P.entries_max / DB_QCHUNK + P.n_active + 2;
   // capacities that do not depend on the object, so that a lane's scratch is allocated ONCE per scan size: every object's
   // worst case is just under `cap` entries, each by a different margin - growing the buffers by those margins meant
   // freeing and re-allocating a gigabyte per lane whenever a slightly bigger object came along (steps of 100-500 ms
   // instead of 33 on C2 until every lane had met the biggest one)
   const size_t entries_alloc = std::max( cap, P.entries_max );
   const size_t poses_alloc = std::max( (size_t)DB_POSE_MAX, P.chunk_poses_max );
-  const size_t items_alloc = entries_alloc / DB_QCHUNK + P.n_cells + 2;
+  const size_t items_alloc = entries_alloc / DB_QCHUNK + P.n_active + 2;
   const size_t cloud_alloc = std::max( (size_t)n * n_rot, (size_t)DB_MAX_PTS * 128 );
   RS_CUDA( S.upos.reserve( cloud_alloc ) ); RS_CUDA( S.unor.reserve( cloud_alloc ) );
   RS_CUDA( S.bins.reserve( P.n_bins ) ); RS_CUDA( S.offs.reserve( P.n_bins ) );
@@ -678,7 +685,9 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
                       double prune_thr, float* d_scores, cudaStream_t st )
 {
   const GridView g = scene->view();
-  const size_t n_cells = P.n_cells;
+  const size_t n_cells = P.n_active; // everything below indexes bins by active rank
+  int sub_mode = 0; // "dense_sub": default octant x normal class; "n" = normal class only; "o" = octant only (A/B)
+  { const std::string o = option( "dense_sub" ); sub_mode = o == "n" ? 1 : ( o == "o" ? 2 : 0 ); }
   const int n = obj->n, n_rot = ps.n_rot;
   size_t scan_bytes = P.scan_bytes;
   db_prepare_kernel<<<( n * n_rot + 255 ) / 256, 256, 0, st>>>( obj->pos.p, obj->nor.p, n, ps.rots, n_rot, S.upos.p, S.unor.p );
@@ -717,12 +726,12 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
       const unsigned blocks = ( n_chunk + pf_warps - 1 ) / pf_warps;
       if( pf_warps == 4 )
       {
-        db_prefilter_kernel<4><<<blocks, 128, pf_smem, st>>>( g, pg, pose0, n_chunk, sp, prune_cnt, n_pad, S.ctr.p, S.bins.p, S.pose_base.p, S.pose_cnt.p,
+        db_prefilter_kernel<4><<<blocks, 128, pf_smem, st>>>( g, pg, pose0, n_chunk, sp, prune_cnt, n_pad, sub_mode, S.ctr.p, S.bins.p, S.pose_base.p, S.pose_cnt.p,
                                                               S.queue.p, S.qbin.p );
       }
       else
       {
-        db_prefilter_kernel<2><<<blocks, 64, pf_smem, st>>>( g, pg, pose0, n_chunk, sp, prune_cnt, n_pad, S.ctr.p, S.bins.p, S.pose_base.p, S.pose_cnt.p,
+        db_prefilter_kernel<2><<<blocks, 64, pf_smem, st>>>( g, pg, pose0, n_chunk, sp, prune_cnt, n_pad, sub_mode, S.ctr.p, S.bins.p, S.pose_base.p, S.pose_cnt.p,
                                                              S.queue.p, S.qbin.p );
       }
       RS_CHECK_LAUNCH();

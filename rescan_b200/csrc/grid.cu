@@ -7,6 +7,7 @@
 #include "rsgpu_internal.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -101,6 +102,16 @@ __global__ void occ27_kernel( const uint32_t* __restrict__ cell_start, int W, in
       total += cell_start[rowbase + x1 + 1] - cell_start[rowbase + x0];
     }
   occ[c] = total;
+}
+
+struct NonZero
+{
+  __host__ __device__ uint32_t operator()( uint32_t v ) const { return v != 0u ? 1u : 0u; }
+};
+__global__ void active_cells_kernel( const uint32_t* __restrict__ occ27, const uint32_t* __restrict__ crank, size_t n_cells, uint32_t* __restrict__ acells )
+{
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if( c < n_cells && occ27[c] != 0u ) { acells[crank[c]] = (uint32_t)c; }
 }
 
 // bounding box of the points of every cell (cbox) and of every 3x3x3 block of cells (nbox): {lo, hi} pairs, empty = {+inf, -inf}
@@ -324,6 +335,25 @@ int build_from_device( const float* d_pts, int32_t n, float radius, rsgpu_grid_t
     RS_CUDA( g->occ27.alloc( n_cells ) );
     occ27_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->cell_start.p, (int)dim[0], (int)dim[1], (int)dim[2], g->occ27.p );
     RS_CHECK_LAUNCH();
+    // ranks of the cells with a non-empty 3x3x3 block (the bins of the dense pose search are indexed by them: 64 sub-bins
+    // per ACTIVE cell instead of 8 per cell of the whole table)
+    {
+      RS_CUDA( g->crank.alloc( n_cells + 1 ) );
+      size_t rank_bytes = 0;
+      auto flags = thrust::make_transform_iterator( (const uint32_t*)g->occ27.p, NonZero() );
+      RS_CUDA( cub::DeviceScan::ExclusiveSum( nullptr, rank_bytes, flags, g->crank.p, (int64_t)n_cells, st ) );
+      DevBuf<unsigned char> tmp3;
+      RS_CUDA( tmp3.alloc( rank_bytes ) );
+      RS_CUDA( cub::DeviceScan::ExclusiveSum( tmp3.p, rank_bytes, flags, g->crank.p, (int64_t)n_cells, st ) );
+      uint32_t last_rank = 0, last_occ = 0;
+      RS_CUDA( cudaMemcpyAsync( &last_rank, g->crank.p + ( n_cells - 1 ), 4, cudaMemcpyDeviceToHost, st ) );
+      RS_CUDA( cudaMemcpyAsync( &last_occ, g->occ27.p + ( n_cells - 1 ), 4, cudaMemcpyDeviceToHost, st ) );
+      RS_CUDA( rs::stream_sync( st ) );
+      g->n_active = last_rank + ( last_occ != 0 ? 1u : 0u );
+      RS_CUDA( g->acells.alloc( g->n_active ) );
+      active_cells_kernel<<<(unsigned)( ( n_cells + 255 ) / 256 ), 256, 0, st>>>( g->occ27.p, g->crank.p, n_cells, g->acells.p );
+      RS_CHECK_LAUNCH();
+    }
     // point bounding boxes per cell / per 3x3x3 block (distance culling of the dense pose search); skipped for very large
     // tables (64 B per cell)
     if( n_cells <= ( (size_t)1 << 25 ) )

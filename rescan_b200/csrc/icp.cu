@@ -24,9 +24,16 @@
 
 using namespace rs;
 
+#ifndef RS_ICP_THREADS
+#define RS_ICP_THREADS 256
+#endif
 namespace
 {
-constexpr int ICP_THREADS = 256;
+// Block size of the ICP kernels (-DRS_ICP_THREADS=128 builds the lean variant: <= 20 KB of shared memory per block, which
+// fits on an SM next to the three resident blocks of the dense pose search; measured on C2 it changes nothing at eight
+// lanes (33.9 vs 33.4 ms per step) and costs the solve 10 % alone, because a tile of 64 rows pays the stage barrier three
+// times as often - DESIGN.md 8b).
+constexpr int ICP_THREADS = RS_ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int ICP_MAX_NV = 32;
 constexpr int ICP_G = 4;       // lanes per correspondence search (nearest_group.cuh)
@@ -201,7 +208,7 @@ __device__ __forceinline__ void ordered_sums( int n, LoadFn load_fn, TermFn term
   // asked) the two fp64 sums of the error term (icp.h:250-253: columns NV-2, NV-1), and every other thread owns one
   // row per tile: it turns the inputs it loaded during the previous tile into the terms of tile s and issues the loads
   // of tile s + 1, so a whole tile time hides the memory latency.
-  constexpr int FIRST_FILL = WITH_F64 ? 2 : 1;
+  constexpr int FIRST_FILL = 2;                     // warp 1 is idle in the passes without fp64 sums (the tile size is fixed)
   constexpr int TR = ICP_THREADS - 32 * FIRST_FILL; // rows per tile = fill threads
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ft = tid - 32 * FIRST_FILL;
@@ -217,7 +224,7 @@ __device__ __forceinline__ void ordered_sums( int n, LoadFn load_fn, TermFn term
       {
         const int inext = ( s + 1 ) * TR + ft;
         if( inext < n ) { other = load_fn( inext ); }
-        float* buf = tile + ( s & 1 ) * ( ICP_THREADS * TILE_LD );
+        float* buf = tile + ( s & 1 ) * ( TR * TILE_LD );
         float t[NV];
 #pragma unroll
         for( int v = 0; v < NV; ++v ) { t[v] = 0.0f; }
@@ -228,13 +235,13 @@ __device__ __forceinline__ void ordered_sums( int n, LoadFn load_fn, TermFn term
     }
     else if( s >= 1 )
     {
-      const float* buf = tile + ( ( s - 1 ) & 1 ) * ( ICP_THREADS * TILE_LD );
+      const float* buf = tile + ( ( s - 1 ) & 1 ) * ( TR * TILE_LD );
       const int rows = min( TR, n - ( s - 1 ) * TR );
       if( warp == 0 )
       {
         if( lane < NV ) { fa = chain_sum<float>( fa, buf + lane, rows ); }
       }
-      else if( lane < 2 ) { da = chain_sum<double>( da, buf + ( NV - 2 + lane ), rows ); } // WITH_F64, warp 1
+      else if( WITH_F64 && lane < 2 ) { da = chain_sum<double>( da, buf + ( NV - 2 + lane ), rows ); } // warp 1
     }
     __syncthreads();
   };
@@ -354,7 +361,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
     }
     ordered_sums<2, false>( c1n,
       [&]( int i ) { CorrIn1 in; in.pos = __ldcg( &cm[i] ).x; in.d = __ldcg( &cq[i] ).w; return in; },
-      [&]( const CorrIn1& in, float* t ) { if( in.pos != 0xffffffffu ) { t[0] = in.d; t[1] = __fmul_rn( in.d, in.d ); } },
+      [&]( const CorrIn1& in, float* t ) { if( in.pos == 0xffffffffu ) { return false; } t[0] = in.d; t[1] = __fmul_rn( in.d, in.d ); return true; },
       tile, fout, dout );
     sum_d = fout[0]; sum_dd = fout[1];
   }
@@ -387,11 +394,12 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
     ordered_sums<7, false>( c1n,
       [&]( int i ) { CorrIn2 in; in.m = __ldcg( &cm[i] ); in.q = __ldcg( &cq[i] ); in.p2 = __ldcg( &cp[i] ); return in; },
       [&]( const CorrIn2& in, float* t ) {
-        if( in.m.x == 0xffffffffu ) { return; }
+        if( in.m.x == 0xffffffffu ) { return false; }
         const float w = weight( in.q, in.m );
         t[0] = w;
         t[1] = __fmul_rn( in.q.x, w ); t[2] = __fmul_rn( in.q.y, w ); t[3] = __fmul_rn( in.q.z, w );
         t[4] = __fmul_rn( in.p2.x, w ); t[5] = __fmul_rn( in.p2.y, w ); t[6] = __fmul_rn( in.p2.z, w );
+        return true;
       }, tile, fout, dout );
 #pragma unroll
     for( int j = 0; j < 7; ++j ) { s7[j] = fout[j]; }
@@ -458,7 +466,7 @@ __device__ __forceinline__ bool icp_update( const GridView& g, int c1n, const fl
   };
   if( EXACT )
   {
-    ordered_sums<29, true>( c1n, load29, [&]( const CorrIn3& in, float* t ) { terms29( in, t ); }, tile, fout, dout );
+    ordered_sums<29, true>( c1n, load29, [&]( const CorrIn3& in, float* t ) { return terms29( in, t ); }, tile, fout, dout );
     if( tid < 27 ) { sh.out[tid] = (double)fout[tid]; }
     if( tid == 27 || tid == 28 ) { sh.out[tid] = dout[tid]; }
     __syncthreads();
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_kernel( GridView g, const I
 {
   const IcpBlock blk = blocks[blockIdx.x];
   __shared__ IcpShared sh;
-  extern __shared__ float tile[]; // EXACT: 2 * ICP_THREADS * TILE_LD floats
+  extern __shared__ float tile[]; // EXACT: 2 * ( ICP_THREADS - 64 ) * TILE_LD floats
   __shared__ float fout[32];
   __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
   __shared__ unsigned char s_slot[ICP_WARPS][32];
@@ -658,7 +666,7 @@ constexpr unsigned ICPQ_EMPTY = 0xffffffffu, ICPQ_TERMINATE = 0xfffffffeu;
 constexpr int ICPQ_CHUNK_BITS = 13; // chunks per alignment < 8192 (1 M points at 16 per task x 8 warps), alignments < 2^19 - 1
 
 template <bool EXACT>
-__global__ void __launch_bounds__( ICP_THREADS, 2 ) icp_persistent_kernel( GridView g, const IcpBlock* __restrict__ blocks, IcpState* state,
+__global__ void __launch_bounds__( ICP_THREADS, 512 / ICP_THREADS ) icp_persistent_kernel( GridView g, const IcpBlock* __restrict__ blocks, IcpState* state,
                                                                          const unsigned* __restrict__ n_chunks, unsigned* arrived, IcpQueue* q,
                                                                          unsigned* items, int pts_per_task, const float* __restrict__ T2i, float dot_thr,
                                                                          int max_iter, float4* scratch_q, uint2* scratch_m, float4* scratch_p, float4* scratch_n )
@@ -844,11 +852,13 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   if( max_iter <= 0 ) { max_iter = 100; }
   // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
   const bool exact = option( "icp_sums" ) != "fp64";
-  // "icp_impl": default = one persistent launch with a device-side work queue; "split" = two launches per iteration over all
-  // running alignments (round 1's default); "block" = one resident block per alignment
+  // "icp_impl": default ("split") = two launches per iteration over all running alignments; "persistent" = one launch per
+  // batch with a device-side work queue (no host in the loop; measured slower on one GPU - its hand-offs cost more than the
+  // launches they replace, and resident blocks that mostly wait take issue slots from the dense search - kept for hosts
+  // whose cores are oversubscribed by ranks x lanes); "block" = one resident block per alignment
   const std::string impl = option( "icp_impl" );
   const bool split = impl != "block";
-  bool persistent = split && impl != "split";
+  bool persistent = impl == "persistent";
   cudaStream_t st = rt().stream;
   float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 }, T2i[16];
   mat4_inverse_ref( T2 ? T2 : ident, T2i );
@@ -898,7 +908,7 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   RS_CUDA( sq.alloc( scratch ) ); RS_CUDA( sm.alloc( scratch ) ); RS_CUDA( sp.alloc( scratch ) ); RS_CUDA( sn.alloc( scratch ) );
   RS_CUDA( cudaMemcpyAsync( dB.p, hb.data(), sizeof( IcpBlock ) * total, cudaMemcpyHostToDevice, st ) );
   RS_CUDA( cudaMemcpyAsync( dT2i.p, T2i, 64, cudaMemcpyHostToDevice, st ) );
-  const size_t tile_bytes = 2 * sizeof( float ) * ICP_THREADS * TILE_LD; // two tiles (ordered_sums)
+  const size_t tile_bytes = 2 * sizeof( float ) * ( ICP_THREADS - 64 ) * TILE_LD; // two tiles of ICP_THREADS - 64 rows (ordered_sums: warps 0 and 1 sum, the others fill)
   const float dot_thr = compat_threshold_acosf( max_angle );
   std::vector<float> herr( total ); std::vector<int> hit( total );
   // the persistent variant's work list: chunks of ICP_WARPS x TPT points per alignment, every chunk of every possible iteration
@@ -921,7 +931,7 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
     cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, rt().device );
     // blocks of the launch: enough to search every alignment's chunks of one iteration at once, capped - the batches of
     // other objects and the dense search want the SMs too ("icp_ctas")
-    unsigned n_ctas = 96;
+    unsigned n_ctas = 96 * ( 256 / ICP_THREADS );
     { const std::string o = option( "icp_ctas" ); if( !o.empty() ) { n_ctas = (unsigned)std::max( 1, atoi( o.c_str() ) ); } }
     n_ctas = (unsigned)std::min<size_t>( n_ctas, chunks_total );
     const size_t q_cap = chunks_total * (size_t)max_iter + n_ctas;

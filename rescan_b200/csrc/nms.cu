@@ -190,19 +190,51 @@ struct OverlapBatch
     return RSGPU_OK;
   }
 
+  // mshgeo_bbox_intersect (msh_geometry.h:1010-1015) of the posed level-3 boxes: without it the overlap is 0 (intersect.h:363-366)
+  bool boxes_intersect( int a, int b ) const
+  {
+    const float* ba = &boxes[6 * (size_t)a]; const float* bb = &boxes[6 * (size_t)b];
+    for( int k = 0; k < 3; ++k ) { if( !( ba[3 + k] >= bb[k] && bb[3 + k] >= ba[k] ) ) { return false; } }
+    return true;
+  }
+  // bytes of voxel scratch the pair needs (0: boxes do not intersect)
+  unsigned long long pair_scratch( int a, int b, float voxel ) const
+  {
+    if( !boxes_intersect( a, b ) ) { return 0; }
+    const float* ba = &boxes[6 * (size_t)a]; const float* bb = &boxes[6 * (size_t)b];
+    unsigned long long cells = 2;
+    for( int k = 0; k < 3; ++k )
+    {
+      volatile float mn = std::min( ba[k], bb[k] ), mx = std::max( ba[3 + k], bb[3 + k] );
+      mn = mn - 0.3f; mx = mx + 0.3f;
+      volatile float w = mx - mn;
+      volatile float q = w / voxel;
+      const int r = (int)ceilf( q ) + 1;
+      cells *= (unsigned long long)( r > 0 ? r : 0 );
+    }
+    return cells;
+  }
+
   // overlap factors of pose `ref` against the poses listed in `others` -> out[j]
   int run( int ref, const std::vector<int>& others, float voxel, int inside, int normalize_by_smaller, std::vector<float>& out )
   {
+    std::vector<int> as( others.size(), ref );
+    return run_pairs( as, others, voxel, inside, normalize_by_smaller, out );
+  }
+
+  // overlap factors of the pairs (as[j], bs[j]) -> out[j], all in ONE launch (one block per pair whose boxes intersect)
+  int run_pairs( const std::vector<int>& as, const std::vector<int>& bs, float voxel, int inside, int normalize_by_smaller, std::vector<float>& out )
+  {
+    const std::vector<int>& others = bs;
     out.assign( others.size(), 0.0f );
     std::vector<PairDesc> pairs; std::vector<int> slot;
     unsigned long long off = 0;
-    const float* ba = &boxes[6 * (size_t)ref];
     for( size_t j = 0; j < others.size(); ++j )
     {
+      const int ref = as[j];
+      const float* ba = &boxes[6 * (size_t)ref];
       const float* bb = &boxes[6 * (size_t)others[j]];
-      bool isect = true; // mshgeo_bbox_intersect (msh_geometry.h:1010-1015)
-      for( int a = 0; a < 3; ++a ) { if( !( ba[3 + a] >= bb[a] && bb[3 + a] >= ba[a] ) ) { isect = false; } }
-      if( !isect ) { continue; } // overlap = 0 (:363-366)
+      if( !boxes_intersect( ref, others[j] ) ) { continue; } // overlap = 0 (:363-366)
       PairDesc pd; pd.a = ref; pd.b = others[j];
       int res[3];
       for( int a = 0; a < 3; ++a )
@@ -271,6 +303,46 @@ int rsgpu_nms( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1, const float
   std::vector<uint8_t> mark( n, 0 ); // 0 unmarked, 1 keep, 2 discard (pose_proposal.cpp:384-389)
   std::vector<float> cpos( (size_t)n * 3 );
   for( int i = 0; i < n; ++i ) { host_xf_point( proposals + RSGPU_POSE_FLOATS * (size_t)i, centroid, &cpos[3 * (size_t)i] ); }
+  auto centroid_dist = [&]( int a, int b ) {
+    volatile float dx = cpos[3 * (size_t)a] - cpos[3 * (size_t)b], dy = cpos[3 * (size_t)a + 1] - cpos[3 * (size_t)b + 1],
+                   dz = cpos[3 * (size_t)a + 2] - cpos[3 * (size_t)b + 2];
+    volatile float s = dx * dx; volatile float t = dy * dy; s = s + t; t = dz * dz; s = s + t;
+    return (float)sqrt( (double)s ); // msh_vec3_norm (msh_vec_math.h:988-991)
+  };
+  // The greedy loop asks for overlap( best, i ) only where i survives the distance and score tests against `best`
+  // (pose_proposal.cpp:410-424).  Which pose becomes `best` in which round is not known up front, but every pair the loop can
+  // ever ask for is among {i < j : both scores >= 0.01, centroids >= dist_threshold apart, posed boxes intersect}; the factor
+  // is symmetric in the pair (union box, max of the two counts), so all of them go into ONE launch and the loop below
+  // runs on the host without touching the device again: two host waits per call instead of one per kept pose.  Lists whose
+  // pair set is too big for that (top_k = 0: thousands of survivors) take the round-by-round path.
+  constexpr size_t NMS_MAX_PAIRS = 8192;
+  constexpr unsigned long long NMS_MAX_SCRATCH = 1ull << 29;
+  std::vector<int> pa, pb;
+  bool all_pairs = option( "nms_impl" ) != "rounds" && (size_t)n * ( (size_t)n - 1 ) / 2 <= 4 * NMS_MAX_PAIRS;
+  if( all_pairs )
+  {
+    unsigned long long scratch = 0;
+    for( int i = 0; i < n && all_pairs; ++i )
+    {
+      if( proposals[RSGPU_POSE_FLOATS * (size_t)i + 16] < 0.01f ) { continue; }
+      for( int j = i + 1; j < n; ++j )
+      {
+        if( proposals[RSGPU_POSE_FLOATS * (size_t)j + 16] < 0.01f || centroid_dist( i, j ) < dist_threshold ) { continue; }
+        const unsigned long long need = ob.pair_scratch( i, j, 0.1f );
+        if( !need ) { continue; }
+        pa.push_back( i ); pb.push_back( j ); scratch += need;
+        if( pa.size() > NMS_MAX_PAIRS || scratch > NMS_MAX_SCRATCH ) { all_pairs = false; break; }
+      }
+    }
+  }
+  std::vector<float> pair_ov;
+  std::vector<int> pair_at; // [i * n + j], i < j -> index into pair_ov, -1 = not needed / boxes apart (overlap 0)
+  if( all_pairs )
+  {
+    RS_TRY( ob.run_pairs( pa, pb, 0.1f, 1, 0, pair_ov ) );
+    pair_at.assign( (size_t)n * n, -1 );
+    for( size_t p = 0; p < pa.size(); ++p ) { pair_at[(size_t)pa[p] * n + pb[p]] = (int)p; }
+  }
   int marked = 0;
   std::vector<int> others; std::vector<float> overlap;
   while( marked != n )
@@ -289,14 +361,21 @@ int rsgpu_nms( const rsgpu_cloud_t* lvl3, const rsgpu_cloud_t* lvl1, const float
     for( int i = 0; i < n; ++i )
     {
       if( mark[i] != 0 ) { continue; }
-      volatile float dx = cpos[3 * (size_t)best] - cpos[3 * (size_t)i], dy = cpos[3 * (size_t)best + 1] - cpos[3 * (size_t)i + 1],
-                     dz = cpos[3 * (size_t)best + 2] - cpos[3 * (size_t)i + 2];
-      volatile float s = dx * dx; volatile float t = dy * dy; s = s + t; t = dz * dz; s = s + t;
-      const float dist = (float)sqrt( (double)s ); // msh_vec3_norm (msh_vec_math.h:988-991)
+      const float dist = centroid_dist( best, i );
       if( dist < dist_threshold || proposals[RSGPU_POSE_FLOATS * (size_t)i + 16] < 0.01f ) { mark[i] = 2; marked++; }
       else { others.push_back( i ); }
     }
-    RS_TRY( ob.run( best, others, 0.1f, 1, 0, overlap ) );
+    if( all_pairs )
+    {
+      overlap.assign( others.size(), 0.0f );
+      for( size_t j = 0; j < others.size(); ++j )
+      {
+        const int lo = std::min( best, others[j] ), hi = std::max( best, others[j] );
+        const int at = pair_at[(size_t)lo * n + hi];
+        if( at >= 0 ) { overlap[j] = pair_ov[at]; }
+      }
+    }
+    else { RS_TRY( ob.run( best, others, 0.1f, 1, 0, overlap ) ); }
     for( size_t j = 0; j < others.size(); ++j )
     {
       if( overlap[j] > 0.5f ) { mark[others[j]] = 2; marked++; }

@@ -101,6 +101,10 @@ struct GridView
   const float4* __restrict__ ncone;   // the same for all normals in the 3x3x3 block around each cell
   const float4* __restrict__ cbox;    // per cell: bounding box of ITS POINTS, {lo.xyz, -} at 2c, {hi.xyz, -} at 2c + 1 (lo > hi: empty); may be nullptr
   const float4* __restrict__ nbox;    // the same for the points of the 3x3x3 block around each cell; may be nullptr
+  const uint32_t* __restrict__ crank; // per cell: its index among the cells with a non-empty 3x3x3 block ("active": the only cells a
+                                      // query with any neighbour can call home), undefined for the others; may be nullptr
+  const uint32_t* __restrict__ acells; // active rank -> cell id
+  uint32_t n_active;
   float mnx, mny, mnz;
   int W, H, D;
   double cell, inv_cell;
@@ -116,6 +120,8 @@ struct rsgpu_grid
   rs::DevBuf<float4> cone;
   rs::DevBuf<float4> ncone;
   rs::DevBuf<float4> cbox, nbox;
+  rs::DevBuf<uint32_t> crank, acells;
+  uint32_t n_active = 0;
   bool has_boxes = false;
   bool has_cone = false;
   bool has_normals = false;
@@ -125,6 +131,7 @@ struct rsgpu_grid
     GridView v;
     v.recs = recs.p; v.nrm = has_normals ? nrm.p : nullptr; v.cell_start = cell_start.p; v.occ27 = occ27.p; v.cone = ( has_normals && has_cone ) ? cone.p : nullptr; v.ncone = v.cone ? ncone.p : nullptr;
     v.cbox = has_boxes ? cbox.p : nullptr; v.nbox = has_boxes ? nbox.p : nullptr;
+    v.crank = crank.p; v.acells = acells.p; v.n_active = n_active;
     v.mnx = info.min_pt[0]; v.mny = info.min_pt[1]; v.mnz = info.min_pt[2];
     v.W = (int)info.width; v.H = (int)info.height; v.D = (int)info.depth;
     v.cell = info.cell_size; v.inv_cell = info.inv_cell_size; v.n_pts = (int)info.n_pts;

@@ -65,3 +65,30 @@ def test_nms_edge_cases():
     far = synth.yaw_pose(0.3, 2.0, 1.5)
     failed[2, :16] = common.colmajor(far)
     assert api.non_maxima_suppression(c3, c1, cen, failed).tolist() == O.nms(o.cloud.pos(3), o.cloud.pos(1), cen, failed).tolist()
+
+
+def test_nms_one_launch_equals_round_by_round():
+    """default: every pair the greedy loop can ask for in ONE overlap launch; "nms_impl" = "rounds": one launch per kept pose
+    (round 1).  Same keep vector, also for a list too long for the one-launch path (400 poses -> round by round either way)."""
+    scene = common.small_scene()
+    rng = np.random.default_rng(17)
+    n_diff = 0
+    for o in scene.objects:
+        for n in (3, 64, 150, 400):
+            props = np.zeros((n, 17), np.float32)
+            for j in range(n):
+                d = synth.yaw_pose(rng.uniform(-3.1, 3.1), rng.uniform(-0.7, 0.7), rng.uniform(-0.7, 0.7), rng.uniform(-0.02, 0.02))
+                props[j, :16] = common.colmajor((d.astype(np.float64) @ o.pose.astype(np.float64)).astype(np.float32))
+                props[j, 16] = np.float32(rng.uniform(0.0, 1.0)) if j % 7 else np.float32(-1.0)
+            props[n // 2, 16] = props[n // 3, 16]  # a tie: first index wins
+            c3, c1 = api.PointCloud(o.cloud.pos(3), o.cloud.nor(3)), api.PointCloud(o.cloud.pos(1), o.cloud.nor(1))
+            cen = O.centroid(o.cloud.pos(0))
+            a = api.non_maxima_suppression(c3, c1, cen, props, 0.2)
+            api.set_option("nms_impl", "rounds")
+            b = api.non_maxima_suppression(c3, c1, cen, props, 0.2)
+            api.set_option("nms_impl", None)
+            assert (a == b).all(), (o.uidx, n)
+            n_diff += int(a.sum())
+            if n == 64:
+                assert (a == O.nms(o.cloud.pos(3), o.cloud.pos(1), cen, props, 0.2)).all()
+    assert n_diff > 0

@@ -21,7 +21,7 @@ def scene():
 @pytest.fixture(autouse=True)
 def _restore_options():
     yield
-    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps", "icp_ctas", "dense_scratch"):
+    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps", "icp_ctas", "dense_scratch", "dense_sub", "dense_serial", "nms_impl"):
         api.set_option(name, None)
 
 
@@ -80,7 +80,8 @@ def test_scoring_variants_bit_identical(scene):
     W = {"dense_impl": "warp"}  # the first design of the dense search (one warp per pose); the default is the cell-binned one
     for opts in ({"score_impl": "coop"}, {"prune": "0"}, W, dict(W, prune="0"), dict(W, score_g="8"), dict(W, score_minb="4", score_warps="4"),
                  dict(W, score_warps="2"), dict(W, score_warps="1", score_minb="16"), dict(W, search="lane"), {"score_g": "8"}, {"search": "lane"},
-                 {"dense_cap": "20000"}, {"dense_cap": "300000", "dense_bps": "1"}, {"dense_bps": "6", "prune": "0"}):
+                 {"dense_cap": "20000"}, {"dense_cap": "300000", "dense_bps": "1"}, {"dense_bps": "6", "prune": "0"}, {"dense_sub": "n"}, {"dense_sub": "o"},
+                 {"dense_serial": "0"}):
         for k, v in opts.items():
             api.set_option(k, v)
         s = api.score_pose_grid(c4, grid, rots, trans)
@@ -133,18 +134,20 @@ def test_icp_variants_bit_identical(scene):
         starts.append(np.stack([common.colmajor(m) for _, m in common.perturbed_poses(rng, type("S", (), {"objects": [o]})(), 5, 0.03, 0.08)]))
     ang = np.float32(np.deg2rad(60.0))
     base = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
-    # default = one persistent launch with a device work queue; "split" = two launches per iteration; "block" = one resident
+    # default = two launches per iteration; "persistent" = one launch with a device work queue; "block" = one resident
     # block per alignment; "icp_ctas" = size of the persistent grid (1 block: every chunk and every solve on the same block)
-    for opt, val in (("icp_impl", "block"), ("icp_impl", "split"), ("icp_ctas", "1"), ("icp_ctas", "7"), ("icp_ctas", "512")):
+    for opt, val in (("icp_impl", "block"), ("icp_impl", "persistent"), ("icp_ctas", "1"), ("icp_ctas", "7"), ("icp_ctas", "512")):
+        api.set_option("icp_impl", "persistent")
         api.set_option(opt, val)
         alt = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
         api.set_option(opt, None)
+        api.set_option("icp_impl", None)
         for (Ta, ea, ia), (Tb, eb, ib) in zip(base, alt):
             assert (ia == ib).all() and (ea == eb).all() and (Ta == Tb).all(), (opt, val)
     # an iteration cap below the natural count stops both variants at the same iteration
     o = objs[0]
     a = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
-    api.set_option("icp_impl", "split")
+    api.set_option("icp_impl", "persistent")
     b = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
     api.set_option("icp_impl", None)
     assert (a[2] == b[2]).all() and (a[0] == b[0]).all() and (a[1] == b[1]).all() and int(a[2].max()) <= 7

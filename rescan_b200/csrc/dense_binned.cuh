@@ -32,9 +32,18 @@
 
 namespace
 {
-constexpr int DB_WARPS = 4;                       // compute warps of the search kernel
+#ifndef RS_DB_WARPS
+#define RS_DB_WARPS 8
+#endif
+constexpr int DB_WARPS = RS_DB_WARPS;             // compute warps of the search kernel
 constexpr int DB_THREADS = 32 * ( DB_WARPS + 1 ); // + the producer warp
-constexpr int DB_CAP = 1024;                      // points staged per buffer (records + normals: 32 KB)
+#ifndef RS_DB_CAP
+#define RS_DB_CAP 1024
+#endif
+#ifndef RS_DB_BPS
+#define RS_DB_BPS 3
+#endif
+constexpr int DB_CAP = RS_DB_CAP;                 // points staged per buffer (records + normals: 32 B each)
 constexpr int DB_QCHUNK = 512;                    // queries per work item
 constexpr int DB_PTS_BITS = 12;                   // object points per cloud on this path: <= 4096
 constexpr int DB_MAX_PTS = 1 << DB_PTS_BITS;
@@ -296,7 +305,7 @@ struct DbSmem
 // visiting order of the 27 cells (index (dz*3 + dy)*3 + dx): own cell, faces, edges, corners
 __constant__ unsigned char kDbOrder[27] = { 13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25, 0, 2, 6, 8, 18, 20, 24, 26 };
 
-__global__ void __launch_bounds__( DB_THREADS ) db_search_kernel( GridView g, DbPoseGrid pg, long long pose0, ScoreParams sp, DbCounters* __restrict__ ctr,
+__global__ void __launch_bounds__( DB_THREADS, RS_DB_BPS ) db_search_kernel( GridView g, DbPoseGrid pg, long long pose0, ScoreParams sp, DbCounters* __restrict__ ctr,
                                                                   const uint2* __restrict__ items, const uint32_t* __restrict__ offs,
                                                                   const uint2* __restrict__ sorted, double* __restrict__ terms )
 {
@@ -648,7 +657,7 @@ int dense_binned_alloc( DbScratch& S, DbPlan& P, const rsgpu_cloud_t* obj, const
   P.n_trans = n_poses / n_rot;
   P.n_active = scene->n_active;
   P.n_bins = P.n_active * DB_NCLS + 2; // + the fallback bin + the end of the scan
-  size_t cap = (size_t)32 << 20;
+  size_t cap = (size_t)64 << 20; // queue entries per chunk (32 B of scratch each, per lane): C2 objects and an eighth of C3 go through in one chunk
   {
     const std::string o = option( "dense_cap" );
     if( !o.empty() ) { cap = (size_t)atoll( o.c_str() ); }
@@ -709,7 +718,7 @@ int dense_binned_run( DbScratch& S, const DbPlan& P, const rsgpu_cloud_t* obj, c
     } );
     RS_CUDA( ae );
   }
-  int search_blocks_per_sm = 3;
+  int search_blocks_per_sm = RS_DB_BPS;
   {
     const std::string o = option( "dense_bps" );
     if( !o.empty() ) { search_blocks_per_sm = std::max( 1, atoi( o.c_str() ) ); }

@@ -90,3 +90,51 @@ def icp_align(obj, scan, T1, max_dist, max_angle, T2=None, max_iter=0):
 def compute_object_alignment_scores(obj, scene, xforms, max_n_neigh=64, radius=0.1):
     x = np.asarray(xforms, np.float32).reshape(-1, 16)
     return (0.5 + 0.4 * _score_of(len(obj), x[:, 12:15])).astype(np.float32)
+
+
+class FilePeer:
+    """stand-in for rescan_b200.peerx.PeerExchange on the CPU tier: the same slot / use / put / get protocol, the payloads as
+    files in a directory every rank sees (put = atomic rename, get = poll), so that the owner-per-object schedule of
+    pipeline.run_step can run with world_size > 1 without CUDA IPC"""
+
+    def __init__(self, root, rank, world, n_slots=64, timeout_s=60.0):
+        import os
+        self.root, self.rank, self.world, self.n_slots, self.timeout_s = root, int(rank), int(world), int(n_slots), timeout_s
+        self._seq = [0] * self.n_slots
+        os.makedirs(root, exist_ok=True)
+
+    def begin_use(self, slot):
+        self._seq[slot % self.n_slots] += 1
+        return self._seq[slot % self.n_slots]
+
+    def _path(self, slot, seq, src, dst):
+        import os
+        return os.path.join(self.root, f"s{slot}_u{seq}_from{src}_to{dst}.bin")
+
+    def put(self, slot, seq, dst_ranks, buf):
+        import os
+        data = np.ascontiguousarray(buf).view(np.uint8).reshape(-1).tobytes()
+        for d in dst_ranks:
+            p = self._path(slot, seq, self.rank, d)
+            with open(p + ".tmp", "wb") as f:
+                f.write(data)
+            os.replace(p + ".tmp", p)
+
+    def get(self, slot, seq, src_ranks):
+        import os
+        import time
+        out, t0 = {}, time.time()
+        for s in src_ranks:
+            p = self._path(slot, seq, s, self.rank)
+            while not os.path.exists(p):
+                if time.time() - t0 > self.timeout_s:
+                    raise TimeoutError(p)
+                time.sleep(0.001)
+            out[int(s)] = np.fromfile(p, np.uint8)
+        return out
+
+    def slot(self, k):
+        raise NotImplementedError
+
+    def close(self):
+        pass

@@ -81,7 +81,7 @@ def _step_worker(rank, world, port, out, lanes):
     dist.destroy_process_group()
 
 
-def _fake_step(rank, world, dist_mod, lanes):
+def _fake_step(rank, world, dist_mod, lanes, peer_dir=None):
     from tests import fake_api
     pipeline.api = fake_api
     pipeline._POOLS.clear()
@@ -93,7 +93,36 @@ def _fake_step(rank, world, dist_mod, lanes):
     scan = (np.zeros((50, 3), np.float32), np.zeros((50, 3), np.float32))
     prev = [rng.uniform(0, 6, (1, 16)).astype(np.float32) for _ in range(6)]
     return pipeline.run_step(scan, scan, models, rots, trans, top_k=16, nms_dist=0.2, previous=prev, rank=rank, world=world,
-                             dist=dist_mod, device=torch.device("cpu"), lanes=lanes)
+                             dist=dist_mod, device=torch.device("cpu"), lanes=lanes,
+                             peer=fake_api.FilePeer(peer_dir, rank, world) if peer_dir else None)
+
+
+def _owner_worker(rank, world, out, lanes):
+    """the owner-per-object schedule (the product's multi-GPU path: pipeline.run_step with a peer exchange) on CPU; no
+    torch.distributed on the data path at all"""
+    res = _fake_step(rank, world, None, lanes, peer_dir=os.path.join(out, f"peer_w{world}_l{lanes}"))
+    np.savez(os.path.join(out, f"o{rank}_{world}_{lanes}.npz"), **{f"p{k}": p for k, p in enumerate(res.proposals)},
+             **{f"i{k}": i for k, i in enumerate(res.pose_ids)}, n_eval=res.n_evaluations)
+
+
+def test_owner_per_object_step_on_cpu(tmp_path):
+    """pipeline.run_step over a peer exchange (gather of the top-k lists to the object's owner rank, owner refines, broadcast),
+    world_size 2 and 3, serial and with lanes: every rank ends with the single-rank lists, and the refinement work is split"""
+    try:
+        ref = _fake_step(0, 1, None, 1)
+        for world, lanes in ((2, 1), (2, 4), (3, 4)):
+            mp.spawn(_owner_worker, args=(world, str(tmp_path), lanes), nprocs=world, join=True)
+            evals = []
+            for rank in range(world):
+                z = np.load(tmp_path / f"o{rank}_{world}_{lanes}.npz")
+                evals.append(int(z["n_eval"]))
+                for k, (p, i) in enumerate(zip(ref.proposals, ref.pose_ids)):
+                    assert z[f"p{k}"].shape == p.shape and (z[f"p{k}"] == p).all() and (z[f"i{k}"] == i).all(), (world, lanes, rank, k)
+            assert sum(evals) == ref.n_evaluations and min(evals) > 0
+    finally:
+        import rescan_b200.api as real_api
+        pipeline.api = real_api
+        pipeline._POOLS.clear()
 
 
 def test_pose_sharded_step_host_logic_on_cpu(tmp_path):

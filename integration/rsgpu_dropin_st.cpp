@@ -25,6 +25,7 @@
 #include <sys/mman.h>
 #include <unordered_set>
 #include <utility>
+#include <thread>
 #include <vector>
 
 #include "msh/msh_std.h"
@@ -365,7 +366,36 @@ rspf_smooth_labels( rsdb_t* rsdb, rs_pointcloud_t* in_pc )
   std::vector<uint8_t> label_is_static( n_labels, 0 );
   for( int32_t i = 0; i < n_pts; ++i ) { label_is_static[labels[i]] = rsdb_is_class_static( rsdb, label_to_class[labels[i]] ) ? 1 : 0; }
   int32_t* data_cost = (int32_t*)result_buffer( (size_t)n_pts * n_labels * sizeof( int32_t ) );
-  if( n_pts > 0 ) { RSGPU_OR_DIE( rsgpu_unary_costs( labels.data(), label_is_static.data(), n_pts, n_labels, data_cost ) ); }
+  // gco reads the V x L table from HOST memory.  Filling it on the device (rsgpu_unary_costs: 0.04 ms of kernel) and copying
+  // 4 V L bytes back costs six times the reference's own host loop inside this executable (114 vs 19 ms at C2 size,
+  // profiles/dropin_r01.md: first touch of 61 MB of fresh pages behind a PCIe copy), so at THIS call site the table is
+  // written where it is consumed - by all host cores, rows in blocks, from the labels the GPU produced;
+  // RSGPU_DROPIN_UNARY=gpu takes the device path (same bytes: tests/test_gpu_dropin.py compares the labels gco returns).
+  const char* unary_env = getenv( "RSGPU_DROPIN_UNARY" );
+  if( n_pts > 0 && unary_env && strcmp( unary_env, "gpu" ) == 0 )
+  {
+    RSGPU_OR_DIE( rsgpu_unary_costs( labels.data(), label_is_static.data(), n_pts, n_labels, data_cost ) );
+  }
+  else if( n_pts > 0 )
+  {
+    const int n_threads = (int)std::max( 1u, std::min( 16u, std::thread::hardware_concurrency() ) );
+    std::vector<std::thread> pool;
+    for( int t = 0; t < n_threads; ++t )
+    {
+      pool.emplace_back( [&, t]() {
+        const int32_t lo = (int32_t)( (int64_t)n_pts * t / n_threads ), hi = (int32_t)( (int64_t)n_pts * ( t + 1 ) / n_threads );
+        for( int32_t i = lo; i < hi; ++i )
+        {
+          const int32_t own = labels[i];
+          const int32_t cost = own == 0 ? 1 : ( label_is_static[own] ? 15 : 30 ); // (:930-933: unlabelled wins over static)
+          int32_t* row = data_cost + (size_t)i * n_labels;
+          for( int32_t l = 0; l < n_labels; ++l ) { row[l] = cost; }
+          row[own] = 0;
+        }
+      } );
+    }
+    for( size_t t = 0; t < pool.size(); ++t ) { pool[t].join(); }
+  }
   // Potts pairwise term (:941-950)
   const int32_t edge_cost = 10;
   int32_t* smooth_cost = (int32_t*)malloc( (size_t)n_labels * n_labels * sizeof( int32_t ) );

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <mutex>
 #include "rsgpu.h"
 
 #define RS_FULL 0xffffffffu
@@ -122,6 +123,13 @@ struct rsgpu_grid
   rs::DevBuf<float4> cbox, nbox;
   rs::DevBuf<uint32_t> crank, acells;
   uint32_t n_active = 0;
+  // second copy of the records for radius searches on grids with hundreds of points per cell (csrc/search.cu): every cell's
+  // records ordered by 4x4x4 sub-cell (then original index), sub_off[c * 64 + s] = first record of sub-cell s of cell c.
+  // Built on the first such search (the handle is logically const: the result of a search does not depend on it).
+  mutable rs::DevBuf<float4> sub_recs;
+  mutable rs::DevBuf<uint32_t> sub_off;
+  mutable int sub_state = 0; // 0 not built, 1 built, -1 not worth it / too large
+  mutable std::mutex sub_mu;
   bool has_boxes = false;
   bool has_cone = false;
   bool has_normals = false;

@@ -9,6 +9,9 @@
 // rows come out ascending and ties are broken by the lower original index, deterministically.
 #include "rsgpu_internal.cuh"
 #include "warplist.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -97,6 +100,120 @@ __global__ void __launch_bounds__( 128 ) radius_search_kernel( GridView g, const
         uint32_t cs = __shfl_sync( RS_FULL, s, src ), ce = __shfl_sync( RS_FULL, t, src );
         if( lane == src ) { gbits = RS_INF_BITS; }
         sweep_cell<EPL>( g, cs, ce, px, py, pz, true, r2f, k, lane, list, thr, seen );
+      }
+    }
+    uint32_t count = seen < (uint32_t)k ? seen : (uint32_t)k;
+    write_row<EPL>( list, lane, count, qi, k, out_d2, out_idx );
+    if( lane == 0 && out_nn ) { out_nn[qi] = count; }
+    local_total += count;
+  }
+  if( lane == 0 && local_total ) { atomicAdd( total, local_total ); }
+}
+
+// ---- sub-cell variant: grids whose cells hold hundreds of points (the reference fixes the cell edge at 2 x the build radius,
+// so a 10 M-point scan searched with r = 0.10 m has ~500 points per cell and ~2 000 candidates per query, of which the
+// k = 64 nearest lie within ~2 cm).  The warp-per-query kernel above is then bound by instruction issue on candidates that
+// cannot make the list (profiles/kernels_r02.md: 8 160 warp instructions per query, 72 % issue-active, 14 % of the DRAM peak).
+// Here every cell's records are kept a second time ordered by 4x4x4 sub-cell; a query ranks the 64 sub-cells of a window
+// cell by their gap (two per lane), sweeps them nearest first and stops at the first one that cannot beat the list's
+// last entry - the reference's own pruning rule (msh_hash_grid.h:1232-1236) one level down.  Same rows as the flat kernel:
+// every pruned sub-cell holds only points that are out of range or behind the k-th best (its box is shrunk by a
+// margin far above the float error of the sub-cell assignment, so the gap is a true lower bound).
+constexpr int SUB_N = 4;                    // sub-cells per axis
+constexpr int SUB_CELLS = SUB_N * SUB_N * SUB_N;
+
+__global__ void sub_key_kernel( const float4* __restrict__ recs, const uint32_t* __restrict__ cell_start, size_t n_cells, int W, int H,
+                                float mnx, float mny, float mnz, float inv_cell, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                uint32_t* __restrict__ counts )
+{
+  // one thread per cell walks its records (cells hold at most a few thousand points; the build runs once per grid)
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if( c >= n_cells ) { return; }
+  const uint32_t s = cell_start[c], t = cell_start[c + 1];
+  if( s == t ) { return; }
+  const int cx = (int)( c % (size_t)W ), cy = (int)( ( c / (size_t)W ) % (size_t)H ), cz = (int)( c / ( (size_t)W * H ) );
+  for( uint32_t p = s; p < t; ++p )
+  {
+    const float4 r = recs[p];
+    const int sx = min( max( (int)floorf( ( ( r.x - mnx ) * inv_cell - (float)cx ) * (float)SUB_N ), 0 ), SUB_N - 1 );
+    const int sy = min( max( (int)floorf( ( ( r.y - mny ) * inv_cell - (float)cy ) * (float)SUB_N ), 0 ), SUB_N - 1 );
+    const int sz = min( max( (int)floorf( ( ( r.z - mnz ) * inv_cell - (float)cz ) * (float)SUB_N ), 0 ), SUB_N - 1 );
+    const uint32_t sub = (uint32_t)( ( sz * SUB_N + sy ) * SUB_N + sx );
+    keys[p] = (uint32_t)c * SUB_CELLS + sub;
+    vals[p] = p;
+    atomicAdd( counts + c * SUB_CELLS + sub, 1u );
+  }
+}
+__global__ void sub_gather_kernel( const float4* __restrict__ recs, const uint32_t* __restrict__ order, int n, float4* __restrict__ out )
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i < n ) { out[i] = recs[order[i]]; }
+}
+
+template <int EPL>
+__global__ void __launch_bounds__( 128 ) radius_search_sub_kernel( GridView g, const float4* __restrict__ sub_recs, const uint32_t* __restrict__ sub_off,
+                                                                   const float* __restrict__ q, size_t nq, double radius, float r2f, int k,
+                                                                   float* __restrict__ out_d2, int32_t* __restrict__ out_idx,
+                                                                   unsigned long long* __restrict__ out_nn, unsigned long long* __restrict__ total )
+{
+  const int lane = threadIdx.x & 31;
+  size_t warp = ( blockIdx.x * (size_t)blockDim.x + threadIdx.x ) >> 5;
+  size_t n_warps = ( gridDim.x * (size_t)blockDim.x ) >> 5;
+  unsigned long long local_total = 0;
+  GridView gs = g; gs.recs = sub_recs; // sweep_cell reads g.recs
+  const float cellf = (float)g.cell, subf = cellf * ( 1.0f / (float)SUB_N );
+  // float error of the sub-cell assignment grows with the cell index (cancellation in q / cell - c): 1e-3 cells covers 2 000 cells per axis
+  const float margin = cellf * fmaxf( 1e-3f, 5e-7f * (float)max( g.W, max( g.H, g.D ) ) );
+  const uint32_t r2bits = __float_as_uint( r2f );
+  for( size_t qi = warp; qi < nq; qi += n_warps )
+  {
+    float px = __ldg( q + 3 * qi ), py = __ldg( q + 3 * qi + 1 ), pz = __ldg( q + 3 * qi + 2 );
+    CellWindow w = make_window( g, px, py, pz, radius );
+    WarpList<EPL> list; list.init();
+    unsigned long long thr = KEY_INF;
+    uint32_t seen = 0;
+    for( int base = 0; base < w.n_cells; base += 32 )
+    {
+      uint32_t s, t; float gap2;
+      window_cell( g, w, base + lane, s, t, gap2 );
+      uint32_t gbits = ( s < t && gap2 < r2f ) ? __float_as_uint( gap2 ) : RS_INF_BITS;
+      while( true )
+      {
+        uint32_t gmin = __reduce_min_sync( RS_FULL, gbits );
+        if( gmin == RS_INF_BITS || ( thr != KEY_INF && gmin >= (uint32_t)( thr >> 32 ) ) ) { break; }
+        int src = __ffs( __ballot_sync( RS_FULL, gbits == gmin ) ) - 1;
+        if( lane == src ) { gbits = RS_INF_BITS; }
+        // the chosen cell: its index in the window -> grid coordinates (enumeration of window_cell: x fastest)
+        const int e = base + src;
+        const int ix = e % w.nx, rr = e / w.nx, iy = rr % w.ny, iz = rr / w.ny;
+        const int cx = w.lox + ix, cy = w.loy + iy, cz = w.loz + iz;
+        const size_t cid = ( (size_t)cz * g.H + cy ) * g.W + cx;
+        // the cell's 64 sub-cells, two per lane: range and conservative squared gap
+        uint32_t ss[2], se[2], sg[2];
+#pragma unroll
+        for( int h = 0; h < 2; ++h )
+        {
+          const int sub = lane + 32 * h;
+          ss[h] = __ldg( sub_off + cid * SUB_CELLS + sub ); se[h] = __ldg( sub_off + cid * SUB_CELLS + sub + 1 );
+          const int sx = sub % SUB_N, sy = ( sub / SUB_N ) % SUB_N, sz = sub / ( SUB_N * SUB_N );
+          const float lx = (float)cx * cellf + (float)sx * subf, ly = (float)cy * cellf + (float)sy * subf, lz = (float)cz * cellf + (float)sz * subf;
+          const float dx = fmaxf( fmaxf( lx - w.qx, w.qx - ( lx + subf ) ) - margin, 0.0f );
+          const float dy = fmaxf( fmaxf( ly - w.qy, w.qy - ( ly + subf ) ) - margin, 0.0f );
+          const float dz = fmaxf( fmaxf( lz - w.qz, w.qz - ( lz + subf ) ) - margin, 0.0f );
+          const uint32_t gb = __float_as_uint( dx * dx + dy * dy + dz * dz ) & 0xffffff00u; // rounded down: still a lower bound
+          sg[h] = ( ss[h] < se[h] && gb < r2bits ) ? gb : RS_INF_BITS;
+        }
+        while( true )
+        {
+          const uint32_t m2 = __reduce_min_sync( RS_FULL, min( sg[0], sg[1] ) );
+          if( m2 == RS_INF_BITS || ( thr != KEY_INF && m2 >= (uint32_t)( thr >> 32 ) ) ) { break; }
+          const unsigned b0 = __ballot_sync( RS_FULL, sg[0] == m2 ), b1 = __ballot_sync( RS_FULL, sg[1] == m2 );
+          const int h = b0 ? 0 : 1;
+          const int sl = __ffs( b0 ? b0 : b1 ) - 1;
+          const uint32_t cs = __shfl_sync( RS_FULL, h == 0 ? ss[0] : ss[1], sl ), ce = __shfl_sync( RS_FULL, h == 0 ? se[0] : se[1], sl );
+          if( lane == sl ) { if( h == 0 ) { sg[0] = RS_INF_BITS; } else { sg[1] = RS_INF_BITS; } }
+          sweep_cell<EPL>( gs, cs, ce, px, py, pz, true, r2f, k, lane, list, thr, seen );
+        }
       }
     }
     uint32_t count = seen < (uint32_t)k ? seen : (uint32_t)k;
@@ -338,6 +455,56 @@ int launch_search( bool knn, const GridView& g, const float* d_q, size_t nq, dou
   return RSGPU_OK;
 }
 
+// the sub-cell ordered copy of a grid's records (see radius_search_sub_kernel); 1 = available, -1 = not for this grid
+int ensure_sub_cells( const rsgpu_grid_t* grid )
+{
+  std::lock_guard<std::mutex> lk( grid->sub_mu );
+  if( grid->sub_state != 0 ) { return grid->sub_state; }
+  const size_t n_cells = (size_t)grid->info.width * grid->info.height * grid->info.depth;
+  const size_t n = (size_t)grid->info.n_pts;
+  if( n == 0 || n_cells * SUB_CELLS + 1 > ( (size_t)1 << 28 ) ) { grid->sub_state = -1; return -1; }
+  cudaStream_t st = rt().stream;
+  const GridView g = grid->view();
+  DevBuf<uint32_t> k0, k1, v0, v1, counts;
+  if( k0.alloc( n ) != cudaSuccess || k1.alloc( n ) != cudaSuccess || v0.alloc( n ) != cudaSuccess || v1.alloc( n ) != cudaSuccess ||
+      counts.alloc( n_cells * SUB_CELLS + 1 ) != cudaSuccess || grid->sub_off.alloc( n_cells * SUB_CELLS + 1 ) != cudaSuccess ||
+      grid->sub_recs.alloc( n ) != cudaSuccess )
+  {
+    cudaGetLastError(); grid->sub_recs.release(); grid->sub_off.release(); grid->sub_state = -1; return -1; // no room: the flat kernel serves
+  }
+  cudaMemsetAsync( counts.p, 0, sizeof( uint32_t ) * ( n_cells * SUB_CELLS + 1 ), st );
+  sub_key_kernel<<<(unsigned)( ( n_cells + 127 ) / 128 ), 128, 0, st>>>( g.recs, g.cell_start, n_cells, g.W, g.H, g.mnx, g.mny, g.mnz, (float)g.inv_cell, k0.p, v0.p, counts.p );
+  count_launch();
+  size_t scan_bytes = 0, sort_bytes = 0;
+  int end_bit = 1;
+  while( end_bit < 32 && ( (size_t)1 << end_bit ) < n_cells * SUB_CELLS ) { ++end_bit; }
+  cub::DeviceScan::ExclusiveSum( nullptr, scan_bytes, counts.p, grid->sub_off.p, (int64_t)( n_cells * SUB_CELLS + 1 ), st );
+  cub::DeviceRadixSort::SortPairs( nullptr, sort_bytes, k0.p, k1.p, v0.p, v1.p, (int64_t)n, 0, end_bit, st );
+  DevBuf<unsigned char> tmp;
+  if( tmp.alloc( std::max( scan_bytes, sort_bytes ) ) != cudaSuccess ) { cudaGetLastError(); grid->sub_recs.release(); grid->sub_off.release(); grid->sub_state = -1; return -1; }
+  cub::DeviceScan::ExclusiveSum( tmp.p, scan_bytes, counts.p, grid->sub_off.p, (int64_t)( n_cells * SUB_CELLS + 1 ), st );
+  // stable: records with equal (cell, sub-cell) keep their order = ascending original index (the reference's bin order)
+  cub::DeviceRadixSort::SortPairs( tmp.p, sort_bytes, k0.p, k1.p, v0.p, v1.p, (int64_t)n, 0, end_bit, st );
+  sub_gather_kernel<<<(unsigned)( ( n + 255 ) / 256 ), 256, 0, st>>>( g.recs, v1.p, (int)n, grid->sub_recs.p );
+  count_launch();
+  const cudaError_t e = cudaStreamSynchronize( st ); // other lanes / streams may search this grid next
+  if( e != cudaSuccess || cudaGetLastError() != cudaSuccess ) { grid->sub_recs.release(); grid->sub_off.release(); grid->sub_state = -1; return -1; }
+  grid->sub_state = 1;
+  return 1;
+}
+
+template <int EPL>
+int launch_search_sub( const rsgpu_grid_t* grid, const GridView& g, const float* d_q, size_t nq, double radius, float r2f, int k, float* d_d2,
+                       int32_t* d_idx, unsigned long long* d_nn, unsigned long long* d_total )
+{
+  size_t blocks = ( nq + 3 ) / 4;
+  const size_t max_blocks = 148 * 64;
+  if( blocks > max_blocks ) { blocks = max_blocks; }
+  radius_search_sub_kernel<EPL><<<(unsigned)blocks, 128, 0, rt().stream>>>( g, grid->sub_recs.p, grid->sub_off.p, d_q, nq, radius, r2f, k, d_d2, d_idx, d_nn, d_total );
+  RS_CHECK_LAUNCH();
+  return RSGPU_OK;
+}
+
 int search_dev( bool knn, const rsgpu_grid_t* grid, const float* d_q, size_t nq, float radius, size_t k, float* d_d2,
                 int32_t* d_idx, unsigned long long* d_nn, size_t* total )
 {
@@ -365,7 +532,20 @@ int search_dev( bool knn, const rsgpu_grid_t* grid, const float* d_q, size_t nq,
     const double est_candidates = pts_per_bin * cells_axis * cells_axis; // surfaces: ~2-D occupancy
     // measured crossovers on B200 (profiles/nn_sweep_r01.md): ~300 candidate points per query for k <= 4, ~60 for k <= 16
     const bool lane = !knn && kk <= 16 && ( impl_env == 1 || ( impl_env == 0 && est_candidates <= ( kk <= 4 ? 320.0 : 64.0 ) ) );
-    if( lane )
+    // cells with hundreds of points (cell edge = 2 x the build radius, fixed by the reference's API): rank sub-cells first.
+    // "search_sub" = "0" / "1" forces the choice; otherwise from ~96 points per non-empty cell on, once per grid.
+    const std::string osub = option( "search_sub" );
+    const bool want_sub = !knn && !lane && kk <= 512 && ( osub == "1" || ( osub != "0" && pts_per_bin >= 96.0 && nq >= 4096 ) );
+    const bool use_sub = want_sub && ensure_sub_cells( grid ) == 1;
+    if( use_sub )
+    {
+      if( kk <= 32 ) { s = launch_search_sub<1>( grid, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else if( kk <= 64 ) { s = launch_search_sub<2>( grid, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else if( kk <= 128 ) { s = launch_search_sub<4>( grid, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else if( kk <= 256 ) { s = launch_search_sub<8>( grid, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+      else { s = launch_search_sub<16>( grid, g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
+    }
+    else if( lane )
     {
       if( kk <= 1 ) { s = launch_search_lane<1>( g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }
       else if( kk <= 4 ) { s = launch_search_lane<4>( g, d_q, nq, r, r2f, kk, d_d2, d_idx, d_nn, d_total.p ); }

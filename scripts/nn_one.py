@@ -29,3 +29,4 @@ for _ in range(2):
     total = grid.radius_search_dev(dq.data_ptr(), nq, np.float32(r), k, d2.data_ptr(), idx.data_ptr(), nn.data_ptr())
     api.profile_enable(False)
     print(f"points {n} r {r} k {k} queries {nq}: {api.profile_get('search')[0]:.3f} ms, {total} neighbours")
+grid.close()

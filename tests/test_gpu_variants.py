@@ -21,7 +21,7 @@ def scene():
 @pytest.fixture(autouse=True)
 def _restore_options():
     yield
-    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps", "icp_ctas", "dense_scratch", "dense_sub", "dense_serial", "nms_impl"):
+    for name in ("search_impl", "score_impl", "prune", "icp_impl", "search", "score_g", "score_minb", "score_warps", "dense_impl", "dense_cap", "dense_bps", "icp_ctas", "dense_scratch", "dense_sub", "dense_serial", "nms_impl", "search_sub"):
         api.set_option(name, None)
 
 
@@ -177,3 +177,29 @@ def test_translation_order_does_not_change_proposals():
                 assert (gid == bid).all() and (got == base).all()
                 n_checked += len(base)
     assert n_checked > 0
+
+
+@pytest.mark.parametrize("n_pts,radius", [(400_000, 0.10), (150_000, 0.25)])
+def test_sub_cell_radius_search_equals_flat(n_pts, radius):
+    """radius search over cells with hundreds of points: the sub-cell ranked kernel ("search_sub" = "1", the default choice there)
+    returns the rows of the flat warp-per-query kernel bit for bit - indices, distances, counts, total - for k from 1 to 200,
+    queries inside, on the border of and outside the cloud, and with fewer than k points in range"""
+    import bench
+    rng = np.random.default_rng(n_pts)
+    cloud = bench.surface_cloud(n_pts, rng, (4.0, 2.5, 3.0))
+    grid = api.HashGrid(cloud, np.float32(radius))
+    q = np.concatenate([cloud[rng.integers(0, n_pts, 6000)] + rng.uniform(-radius, radius, (6000, 3)).astype(np.float32),
+                        rng.uniform(-0.5, 4.5, (1500, 3)).astype(np.float32),      # mostly empty space
+                        cloud[:500]]).astype(np.float32)                            # exact hits (distance 0)
+    for k in (1, 16, 64, 200):
+        for r in (radius, radius * 0.37):
+            api.set_option("search_sub", "0")
+            a = grid.radius_search(q, float(np.float32(r)), k)
+            api.set_option("search_sub", "1")
+            b = grid.radius_search(q, float(np.float32(r)), k)
+            api.set_option("search_sub", None)
+            assert a[3] == b[3] and (a[2] == b[2]).all(), (k, r)
+            m = np.arange(k)[None, :] < a[2][:, None]
+            assert (a[0][m] == b[0][m]).all() and (a[1][m] == b[1][m]).all(), (k, r)
+            assert a[3] > 0
+    grid.close()

@@ -641,6 +641,97 @@ __global__ void __launch_bounds__( ICP_THREADS ) icp_solve_kernel( GridView g, c
   }
 }
 
+// ---- the split variant as a CUDA graph: the two launches of an iteration are the same every time once their arguments live
+// in device memory (a descriptor per lane and partition; the iteration number the stopping rule needs is the alignment's
+// own step count), so four iterations - eight kernel nodes - are captured once per lane and partition and replayed with ONE
+// driver call.  With eight objects' chains in flight the host threads issue ~1 300 ICP launches per C2 step; funnelled
+// through the driver they, not the device, set the pace of the chains (eight batches side by side took 8-16 ms each, 3.6 ms
+// alone).  Grids are fixed at capture (grid-stride loops inside), finished alignments are counted in the descriptor.
+struct IcpDesc
+{
+  GridView g;
+  const IcpBlock* blocks; IcpState* state; const int* ids; const unsigned* task_start;
+  int n_align, pts_per_task, max_iter;
+  const float* T2i; float dot_thr;
+  float4* sq; uint2* sm; float4* sp; float4* sn;
+  int* n_done;
+};
+
+__global__ void __launch_bounds__( ICP_THREADS ) icp_search_desc_kernel( const IcpDesc* __restrict__ dp )
+{
+  __shared__ uint4 s_cand[ICP_WARPS][rsg::GroupCfg<ICP_G>::CAND_WORDS];
+  __shared__ unsigned char s_slot[ICP_WARPS][32];
+  __shared__ float s_T[ICP_WARPS][16], s_M[16];
+  __shared__ IcpDesc d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for( int i = threadIdx.x; i < (int)( sizeof( IcpDesc ) / 4 ); i += ICP_THREADS ) { ( (uint32_t*)&d )[i] = ( (const uint32_t*)dp )[i]; }
+  __syncthreads();
+  if( threadIdx.x < 16 ) { s_M[threadIdx.x] = d.T2i[threadIdx.x]; }
+  __syncthreads();
+  const unsigned n_tasks = d.task_start[d.n_align];
+  for( unsigned task = blockIdx.x * ICP_WARPS + warp; task < n_tasks; task += gridDim.x * ICP_WARPS )
+  {
+    int lo = 0, hi = d.n_align;
+    while( hi - lo > 1 ) { int mid = ( lo + hi ) >> 1; if( __ldg( d.task_start + mid ) <= task ) { lo = mid; } else { hi = mid; } }
+    const int a = d.ids[lo];
+    if( !d.state[a].active ) { continue; }
+    const IcpBlock blk = d.blocks[a];
+    if( lane < 16 ) { s_T[warp][lane] = d.state[a].T[lane]; }
+    __syncwarp();
+    const double radius = (double)d.state[a].max_dist;
+    const float r2f = (float)__dmul_rn( radius, radius );
+    icp_correspond_batch( d.g, s_T[warp], s_M, blk.p1, blk.n1, blk.n, (int)( task - __ldg( d.task_start + lo ) ) * d.pts_per_task, d.pts_per_task,
+                          d.state[a].steps > 0, radius, r2f, d.dot_thr, d.sq + blk.scratch_off, d.sm + blk.scratch_off, d.sp + blk.scratch_off,
+                          d.sn + blk.scratch_off, s_cand[warp], s_slot[warp] );
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__( ICP_THREADS ) icp_solve_desc_kernel( const IcpDesc* __restrict__ dp )
+{
+  __shared__ IcpShared sh;
+  extern __shared__ float tile[];
+  __shared__ float fout[32];
+  __shared__ double dout[32];
+  __shared__ IcpDesc d;
+  const int tid = threadIdx.x;
+  for( int i = tid; i < (int)( sizeof( IcpDesc ) / 4 ); i += ICP_THREADS ) { ( (uint32_t*)&d )[i] = ( (const uint32_t*)dp )[i]; }
+  __syncthreads();
+  for( int bi = blockIdx.x; bi < d.n_align; bi += gridDim.x )
+  {
+    const int a = d.ids[bi];
+    if( !d.state[a].active ) { continue; } // block-uniform
+    const IcpBlock blk = d.blocks[a];
+    const int it = d.state[a].steps; // a running alignment has made one step per iteration
+    if( tid < 16 ) { sh.T[tid] = d.state[a].T[tid]; }
+    if( tid == 0 ) { sh.max_dist = d.state[a].max_dist; sh.prev_err = d.state[a].err; sh.err = d.state[a].err; sh.stop = 0; sh.steps = it; }
+    __syncthreads();
+    const bool updated = icp_update<EXACT>( d.g, blk.n, d.sq + blk.scratch_off, d.sm + blk.scratch_off, d.sp + blk.scratch_off, d.sn + blk.scratch_off,
+                                                it, sh, tile, fout, dout );
+    __syncthreads();
+    if( tid < 16 ) { d.state[a].T[tid] = sh.T[tid]; }
+    if( tid == 0 )
+    {
+      const int active = ( updated && !sh.stop && it + 1 < d.max_iter ) ? 1 : 0;
+      d.state[a].max_dist = sh.max_dist; d.state[a].prev_err = sh.prev_err; d.state[a].err = sh.err; d.state[a].steps = sh.steps;
+      d.state[a].active = active;
+      if( !active ) { atomicAdd( d.n_done, 1 ); }
+    }
+    __syncthreads();
+  }
+}
+
+// per calling thread (= lane): the device descriptors and the instantiated graphs of its partitions
+struct IcpGraphCache
+{
+  IcpDesc* d_desc[4] = { nullptr, nullptr, nullptr, nullptr };
+  IcpDesc* h_desc = nullptr;   // pinned staging, 4 descriptors
+  int* d_done[4] = { nullptr, nullptr, nullptr, nullptr };
+  int* h_done = nullptr;       // pinned, 4 counters
+  cudaGraphExec_t exec[4][2] = { { nullptr, nullptr }, { nullptr, nullptr }, { nullptr, nullptr }, { nullptr, nullptr } };
+};
+constexpr int ICP_GRAPH_ITERS = 4;
+
 // ---- variant 3 (default): ONE persistent launch per batch, driven by a device-side work queue.  The iteration-
 // synchronous split needs two launches per iteration and a host look at the running count every four: with eight objects'
 // batches in flight that is ~1 300 launches per C2 step funnelled through the driver from eight host threads, and every
@@ -852,7 +943,8 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
   if( max_iter <= 0 ) { max_iter = 100; }
   // RSGPU_ICP_SUMS=fp64 selects block-wide fp64 shuffle reductions instead of the reference-order float sums
   const bool exact = option( "icp_sums" ) != "fp64";
-  // "icp_impl": default ("split") = two launches per iteration over all running alignments; "persistent" = one launch per
+  // "icp_impl": default = two launches per iteration over all running alignments, four iterations replayed as one captured CUDA
+  // graph; "split" = the same launches issued one by one (round 1); "persistent" = one launch per
   // batch with a device-side work queue (no host in the loop; measured slower on one GPU - its hand-offs cost more than the
   // launches they replace, and resident blocks that mostly wait take issue slots from the dense search - kept for hosts
   // whose cores are oversubscribed by ranks x lanes); "block" = one resident block per alignment
@@ -992,7 +1084,11 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
       RS_CUDA( cudaMemcpyAsync( dtask[p].p, part_task[p].data(), sizeof( unsigned ) * ( np + 1 ), cudaMemcpyHostToDevice, st ) );
       RS_CUDA( cudaMemsetAsync( dact[p].p, 0, sizeof( int ) * (size_t)max_iter, st ) );
     }
-    if( exact ) { RS_CUDA( cudaFuncSetAttribute( icp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) ); }
+    if( exact )
+    {
+      RS_CUDA( cudaFuncSetAttribute( icp_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
+      RS_CUDA( cudaFuncSetAttribute( icp_solve_desc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes ) );
+    }
     int n_sm = 148;
     cudaDeviceGetAttribute( &n_sm, cudaDevAttrMultiProcessorCount, rt().device );
     cudaStream_t* aux = nullptr;
@@ -1009,7 +1105,72 @@ int icp_run( const rsgpu_icp_job_t* jobs, int32_t n_jobs, const rsgpu_grid_t* sc
       const int CHECK = 4;
       std::vector<char> done( NPART, 0 );
       const bool phase_prof = rt().profile && option( "icp_phases" ) == "1";
-      for( int it = 0; it < max_iter && status == RSGPU_OK; ++it )
+      const bool use_graph = impl != "split" && !phase_prof;
+      if( use_graph )
+      {
+        // four iterations per driver call: the captured graph of this lane and partition, arguments through the descriptor
+        static thread_local IcpGraphCache gc;
+        if( !gc.h_desc )
+        {
+          if( cudaHostAlloc( (void**)&gc.h_desc, sizeof( IcpDesc ) * 4, cudaHostAllocDefault ) != cudaSuccess ||
+              cudaHostAlloc( (void**)&gc.h_done, sizeof( int ) * 4, cudaHostAllocDefault ) != cudaSuccess )
+          {
+            gc.h_desc = nullptr; status = cuda_fail( cudaGetLastError(), "icp graph staging", __FILE__, __LINE__ );
+          }
+          for( int p = 0; p < 4 && status == RSGPU_OK; ++p )
+          {
+            if( cudaMalloc( (void**)&gc.d_desc[p], sizeof( IcpDesc ) ) != cudaSuccess || cudaMalloc( (void**)&gc.d_done[p], sizeof( int ) ) != cudaSuccess )
+            {
+              status = cuda_fail( cudaGetLastError(), "icp graph descriptors", __FILE__, __LINE__ );
+            }
+          }
+        }
+        const int ex = exact ? 1 : 0;
+        for( int p = 0; p < NPART && status == RSGPU_OK; ++p )
+        {
+          IcpDesc& D = gc.h_desc[p];
+          D.g = scan->view(); D.blocks = dB.p; D.state = dS.p; D.ids = dids[p].p; D.task_start = dtask[p].p;
+          D.n_align = (int)part_ids[p].size(); D.pts_per_task = TPT; D.max_iter = max_iter; D.T2i = dT2i.p; D.dot_thr = dot_thr;
+          D.sq = sq.p; D.sm = sm.p; D.sp = sp.p; D.sn = sn.p; D.n_done = gc.d_done[p];
+          cudaMemcpyAsync( gc.d_desc[p], &D, sizeof( IcpDesc ), cudaMemcpyHostToDevice, aux[p] );
+          cudaMemsetAsync( gc.d_done[p], 0, sizeof( int ), aux[p] );
+          if( !gc.exec[p][ex] )
+          {
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture( aux[p], cudaStreamCaptureModeThreadLocal );
+            for( int i = 0; i < ICP_GRAPH_ITERS && ce == cudaSuccess; ++i )
+            {
+              icp_search_desc_kernel<<<(unsigned)n_sm * 4, ICP_THREADS, 0, aux[p]>>>( gc.d_desc[p] );
+              if( exact ) { icp_solve_desc_kernel<true><<<64, ICP_THREADS, tile_bytes, aux[p]>>>( gc.d_desc[p] ); }
+              else { icp_solve_desc_kernel<false><<<64, ICP_THREADS, 0, aux[p]>>>( gc.d_desc[p] ); }
+            }
+            if( ce == cudaSuccess ) { ce = cudaStreamEndCapture( aux[p], &graph ); }
+            if( ce == cudaSuccess ) { ce = cudaGraphInstantiate( &gc.exec[p][ex], graph, 0 ); }
+            if( graph ) { cudaGraphDestroy( graph ); }
+            if( ce != cudaSuccess ) { gc.exec[p][ex] = nullptr; status = cuda_fail( ce, "icp graph capture", __FILE__, __LINE__ ); }
+          }
+        }
+        const int rounds = ( max_iter + ICP_GRAPH_ITERS - 1 ) / ICP_GRAPH_ITERS;
+        for( int r = 0; r < rounds && status == RSGPU_OK; ++r )
+        {
+          for( int p = 0; p < NPART; ++p )
+          {
+            if( done[p] ) { continue; }
+            if( cudaGraphLaunch( gc.exec[p][ex], aux[p] ) != cudaSuccess ) { status = cuda_fail( cudaGetLastError(), "icp graph launch", __FILE__, __LINE__ ); break; }
+            for( int i = 0; i < 2 * ICP_GRAPH_ITERS; ++i ) { count_launch(); }
+            cudaMemcpyAsync( &gc.h_done[p], gc.d_done[p], sizeof( int ), cudaMemcpyDeviceToHost, aux[p] );
+          }
+          bool all_done = true;
+          for( int p = 0; p < NPART && status == RSGPU_OK; ++p )
+          {
+            if( done[p] ) { continue; }
+            if( rs::stream_sync( aux[p] ) != cudaSuccess ) { status = cuda_fail( cudaGetLastError(), "icp partition", __FILE__, __LINE__ ); }
+            if( gc.h_done[p] >= (int)part_ids[p].size() ) { done[p] = 1; } else { all_done = false; }
+          }
+          if( all_done ) { break; }
+        }
+      }
+      for( int it = 0; !use_graph && it < max_iter && status == RSGPU_OK; ++it )
       {
         for( int p = 0; p < NPART; ++p )
         {

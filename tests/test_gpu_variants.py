@@ -134,9 +134,10 @@ def test_icp_variants_bit_identical(scene):
         starts.append(np.stack([common.colmajor(m) for _, m in common.perturbed_poses(rng, type("S", (), {"objects": [o]})(), 5, 0.03, 0.08)]))
     ang = np.float32(np.deg2rad(60.0))
     base = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
-    # default = two launches per iteration; "persistent" = one launch with a device work queue; "block" = one resident
+    # default = two launches per iteration, four iterations replayed as one CUDA graph; "split" = the same launches one by one;
+    # "persistent" = one launch with a device work queue; "block" = one resident
     # block per alignment; "icp_ctas" = size of the persistent grid (1 block: every chunk and every solve on the same block)
-    for opt, val in (("icp_impl", "block"), ("icp_impl", "persistent"), ("icp_ctas", "1"), ("icp_ctas", "7"), ("icp_ctas", "512")):
+    for opt, val in (("icp_impl", "block"), ("icp_impl", "split"), ("icp_impl", "persistent"), ("icp_ctas", "1"), ("icp_ctas", "7"), ("icp_ctas", "512")):
         api.set_option("icp_impl", "persistent")
         api.set_option(opt, val)
         alt = api.icp_align_multi(objs, grid, [s.copy() for s in starts], 0.10, ang)
@@ -147,10 +148,11 @@ def test_icp_variants_bit_identical(scene):
     # an iteration cap below the natural count stops both variants at the same iteration
     o = objs[0]
     a = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
-    api.set_option("icp_impl", "persistent")
-    b = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
-    api.set_option("icp_impl", None)
-    assert (a[2] == b[2]).all() and (a[0] == b[0]).all() and (a[1] == b[1]).all() and int(a[2].max()) <= 7
+    for other in ("persistent", "split"):
+        api.set_option("icp_impl", other)
+        b = api.icp_align(o, grid, starts[0].copy(), 0.10, ang, max_iter=7)
+        api.set_option("icp_impl", None)
+        assert (a[2] == b[2]).all() and (a[0] == b[0]).all() and (a[1] == b[1]).all() and int(a[2].max()) <= 7, other
     assert max(int(i.max()) for _, _, i in base) > 6
 
 

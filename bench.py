@@ -354,7 +354,7 @@ def run_nn_workload(args, rank, world, local_rank, device, dist):
             "e2e": {"value": nq_all * args.steps / (ms_e2e * 1e-3), "unit": NN_UNIT, "h2d_bytes_per_step": 12 * nq_all,
                     "d2h_bytes_per_step": (8 * k + 8) * nq_all, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "kernel": "radius_search_kernel (warp per query, k-list in registers)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "radius_search_sub_kernel (warp per query, sub-cells ranked by gap, k-list in registers)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_frac_of_peak": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic and avg_ms > 0 else None,
                          "traffic_source": ctr.get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,

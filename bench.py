@@ -544,7 +544,9 @@ def main():
         dense_ms, dense_launches = prof["score_dense"]
         per_step_alg = dense_bytes
         alg_tput = per_step_alg * n_prof_steps / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
-        ctr = kernel_counters(f"{name}:dense_search") or kernel_counters("C2:dense_search") or {}
+        # counters exist for the workload they were captured on (C2: profiles/r02_dense_c2_metrics.csv); a line of another
+        # workload carries no issue-rate fraction rather than one scaled from C2
+        ctr = kernel_counters(f"{name}:dense_search") or {}
         sm_mhz = (clk.get("sm_mhz") or 1965.0)
         issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions/s: 4 schedulers per SM, one instruction per cycle each
         avg_launch_ms = dense_ms / max(dense_launches, 1)

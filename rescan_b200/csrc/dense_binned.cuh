@@ -44,7 +44,10 @@ constexpr int DB_THREADS = 32 * ( DB_WARPS + 1 ); // + the producer warp
 #define RS_DB_BPS 3
 #endif
 constexpr int DB_CAP = RS_DB_CAP;                 // points staged per buffer (records + normals: 32 B each)
-constexpr int DB_QCHUNK = 512;                    // queries per work item
+#ifndef RS_DB_QCHUNK
+#define RS_DB_QCHUNK 512
+#endif
+constexpr int DB_QCHUNK = RS_DB_QCHUNK;           // queries per work item
 constexpr int DB_PTS_BITS = 12;                   // object points per cloud on this path: <= 4096
 constexpr int DB_MAX_PTS = 1 << DB_PTS_BITS;
 constexpr uint32_t DB_POSE_MAX = 1u << ( 32 - DB_PTS_BITS ); // poses per chunk
@@ -255,11 +258,25 @@ __device__ __forceinline__ void db_mbar_arrive( uint64_t* bar )
 {
   asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( db_smem_u32( bar ) ) : "memory" );
 }
+#ifdef RS_DB_WAIT_HINT
+// consumers: the probe carries a suspend-time hint as well, so a warp that arrives before its block is staged sleeps in the
+// barrier unit instead of spinning through issue slots the other warps could use
+__device__ __forceinline__ void db_mbar_wait( uint64_t* bar, unsigned parity )
+{
+  unsigned ok = 0;
+  while( !ok )
+  {
+    asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                  : "=r"( ok ) : "r"( db_smem_u32( bar ) ), "r"( parity ), "r"( (unsigned)RS_DB_WAIT_HINT ) : "memory" );
+  }
+}
+#else
 __device__ __forceinline__ void db_mbar_wait( uint64_t* bar, unsigned parity )
 {
   asm volatile( "{\n\t.reg .pred p;\n\tDB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DB_DONE;\n\tbra DB_WAIT;\n\tDB_DONE:\n\t}"
                 ::"r"( db_smem_u32( bar ) ), "r"( parity ) : "memory" );
 }
+#endif
 // the producer warp waits for whole items to be consumed (tens of microseconds): the probe carries a suspend-time hint, so
 // the hardware parks the warp instead of letting it spin through issue slots; one lane probes, the warp follows
 __device__ __forceinline__ void db_mbar_wait_parked( uint64_t* bar, unsigned parity )

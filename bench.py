@@ -59,7 +59,7 @@ def workload_config(name, world, nms=True, exchange="nvlink", scaling="strong"):
     return {"workload": f"{name}: pose_proposal on one synthetic scene pair", "scan_points_target": sc.get("target_points"),
             "objects": sc["n_objects"], "static_objects": sc["n_static"], "rotations": cfg["n_rot"],
             "translation_seeds_total": total, "translation_seeds_per_gpu": -(-total // world),
-            "top_k": 64, "parallelism": f"pose-sharded x{world}", "exchange": exchange if world > 1 else None,
+            "top_k": 64, "parallelism": f"pose-sharded x{world} (blocks of 256 translations of the Z-order curve dealt round the ranks)", "exchange": exchange if world > 1 else None,
             "stages": "grid build, dense search lvl 4, verification lvl 3/2, top-k" + (", NMS" if nms else "") + ", ICP, rescoring lvl 1"
                       + (", NMS" if nms else "") + ", sort",
             "l2": "flushed between steps (256 MiB write inside the timed region); working set is L2-resident within a step"}
@@ -478,12 +478,12 @@ def main():
 
     # algorithmic bytes of the dense level-4 scoring (what the reference's search reads for the same poses), exact census on
     # this rank's shard, untimed; big pose grids are counted on every `cstride`-th translation and scaled
-    lo, hi = pipeline.shard_range(len(translations), rank, world)
-    cstride = max(1, (hi - lo) // 2048)
+    my_ids = pipeline.shard_translations(translations, rank, world)
+    cstride = max(1, len(my_ids) // 2048)
     g1 = api.HashGrid(p1, 0.05, normals=n1)
-    census = [api.score_pose_grid_count(m.levels[4], g1, rotations, np.ascontiguousarray(translations[lo:hi:cstride])) for m in models if not m.is_static]
+    census = [api.score_pose_grid_count(m.levels[4], g1, rotations, np.ascontiguousarray(translations[my_ids[::cstride]])) for m in models if not m.is_static]
     g1.close()
-    cscale = (hi - lo) / max(len(range(lo, hi, cstride)), 1)
+    cscale = len(my_ids) / max(len(my_ids[::cstride]), 1)
     dense_bytes = sum(c["bytes"] for c in census) * cscale
     dense_queries = sum(c["queries"] for c in census) * cscale
 

@@ -61,6 +61,21 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+SHARD_BLOCK = 256  # translations per block of the Z-order curve dealt to one rank
+
+
+def shard_translations(translations, rank, world, spatial=True):
+    """indices (caller's numbering) of the translations `rank` of `world` searches, in the order it hands them to the search:
+    the Z-order curve over (x, z) cut into blocks of SHARD_BLOCK, block b to rank b % world (spatial=False: the caller's order
+    cut the same way).  Every translation belongs to exactly one rank; world = 1 gives the whole curve."""
+    n = len(translations)
+    order = posegrid.spatial_order(translations) if spatial else np.arange(n, dtype=np.int64)
+    if world <= 1:
+        return np.ascontiguousarray(order, np.int64)
+    block = np.arange(n, dtype=np.int64) // SHARD_BLOCK
+    return np.ascontiguousarray(order[block % world == rank], np.int64)
+
+
 def merge_topk(per_rank_props, per_rank_ids, top_k):
     """deterministic merge of per-rank proposal lists (identical on every rank), in the order a single rank's
     rsgpu_propose_poses returns the same list: top_k > 0 descending score with ties by pose id; top_k <= 0 (the reference's
@@ -247,12 +262,15 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
     if trace:
         events.append((-1, "grids", t_g - t_step, time.perf_counter() - t_step))
     n_rot = len(rotations)
-    lo, hi = shard_range(len(translations), rank, world)
-    my_trans = np.ascontiguousarray(translations[lo:hi])
-    # handed to the dense search along a Z-order curve (neighbouring launches search neighbouring scan cells: -9 % on the C2
-    # dense launches); translation_ids keeps every id, order and tie in the caller's numbering
-    walk = posegrid.spatial_order(my_trans) if os.environ.get("RSGPU_SPATIAL_ORDER", "1") != "0" else None
-    walk_trans = np.ascontiguousarray(my_trans[walk]) if walk is not None else my_trans
+    # The translations are handed to the dense search along a Z-order curve (neighbouring poses search neighbouring scan cells;
+    # the cell-binned search lives on many queries per staged block of cells), and a rank's share is every world-th BLOCK of
+    # that curve: compact pieces of the scene, so the query density per cell is what it is on one GPU (contiguous shares of
+    # the caller's - unordered - list spread a rank's poses over the whole scan: 1.8 x the search time per pose at N = 8),
+    # dealt round the ranks, so the shares cost the same.  translation_ids carries the caller's numbering: ids, order and
+    # every tie are those of the caller's own order.
+    my_ids = shard_translations(translations, rank, world, spatial=os.environ.get("RSGPU_SPATIAL_ORDER", "1") != "0")
+    my_trans = walk_trans = np.ascontiguousarray(translations[my_ids])
+    walk = my_ids
     stats["h2d"] += rotations.nbytes + my_trans.nbytes
     dyn = [m for m in models if not m.is_static]  # pose_proposal.cpp:198
     lanes = default_lanes() if lanes is None else lanes
@@ -272,7 +290,7 @@ def run_step(scan_lvl1, scan_lvl2, models, rotations, translations, top_k=64, ic
         """dense search + verification on this rank's block of translations"""
         props, ids = api.propose_poses(m.levels[4], m.levels[3], m.levels[2], g1, rotations, walk_trans, top_k=top_k, translation_ids=walk)
         add(d2h=props.nbytes + ids.nbytes, n_eval=n_rot * len(my_trans), n_query=n_rot * len(my_trans) * len(m.levels[4]))
-        return props, ids + lo * n_rot
+        return props, ids
 
     def suppress(m, props, ids):
         if nms and len(props):

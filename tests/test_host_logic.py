@@ -280,3 +280,20 @@ def test_coverage_grid_host_arithmetic_matches_oracle():
             ro, oo, _ = O.cov_grid(mn, mx, voxel)
             assert (res == ro).all() and (origin == oo).all()
     assert api.coverage_score(np.zeros((0, 3), np.uint32), 10) == 0 and api.coverage_score(np.array([[1, 0], [2, 0]], np.uint32), 4) == np.float32(0.5)
+
+
+def test_shard_translations_partitions_every_translation_once():
+    """the pose-sharded step's shares: blocks of the Z-order curve dealt round the ranks - a partition of the caller's ids for every
+    world size, balanced to one block, the whole curve for one rank, the caller's order when spatial ordering is off"""
+    from rescan_b200 import pipeline, posegrid
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 255, 256, 257, 5000):
+        t = rng.uniform(0, 9, (n, 3)).astype(np.float32)
+        assert (pipeline.shard_translations(t, 0, 1) == posegrid.spatial_order(t)).all()
+        for world in (2, 3, 8):
+            parts = [pipeline.shard_translations(t, r, world) for r in range(world)]
+            allids = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+            assert sorted(allids.tolist()) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= pipeline.SHARD_BLOCK
+            plain = [pipeline.shard_translations(t, r, world, spatial=False) for r in range(world)]
+            assert all((np.diff(p) > 0).all() for p in plain if len(p) > 1)

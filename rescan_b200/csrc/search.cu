@@ -42,13 +42,13 @@ __device__ __forceinline__ void sweep_cell( const GridView& g, uint32_t cs, uint
     unsigned m = __ballot_sync( RS_FULL, ok && key < thr );
     while( m )
     {
+      // every candidate left in the mask beats the current k-th best: insert the first, then drop the ones the new k-th best
+      // rules out in one vote (half of the candidates that pass the first vote never make the list - profiles/kernels_r02.md)
       int src = __ffs( m ) - 1; m &= m - 1;
       unsigned long long x = __shfl_sync( RS_FULL, key, src );
-      if( x < thr )
-      {
-        list.insert( x, lane );
-        thr = list.get( k - 1 );
-      }
+      list.insert( x, lane );
+      thr = list.get( k - 1 );
+      m &= __ballot_sync( RS_FULL, key < thr );
     }
   }
 }

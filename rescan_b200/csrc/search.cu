@@ -533,9 +533,11 @@ int search_dev( bool knn, const rsgpu_grid_t* grid, const float* d_q, size_t nq,
     // measured crossovers on B200 (profiles/nn_sweep_r01.md): ~300 candidate points per query for k <= 4, ~60 for k <= 16
     const bool lane = !knn && kk <= 16 && ( impl_env == 1 || ( impl_env == 0 && est_candidates <= ( kk <= 4 ? 320.0 : 64.0 ) ) );
     // cells with hundreds of points (cell edge = 2 x the build radius, fixed by the reference's API): rank sub-cells first.
-    // "search_sub" = "0" / "1" forces the choice; otherwise from ~96 points per non-empty cell on, once per grid.
+    // "search_sub" = "0" / "1" forces the choice; otherwise from 256 points per non-empty cell on (surfaces fill ~16 of a cell's
+    // 64 sub-cells: below that a sub-cell holds fewer than 16 points and its sweep step runs with most lanes idle - measured
+    // on the 10 M-point sweep: 1.5 - 2.2 x faster at 500 points per cell, 0.8 - 0.97 x at 126), once per grid.
     const std::string osub = option( "search_sub" );
-    const bool want_sub = !knn && !lane && kk <= 512 && ( osub == "1" || ( osub != "0" && pts_per_bin >= 96.0 && nq >= 4096 ) );
+    const bool want_sub = !knn && !lane && kk <= 512 && ( osub == "1" || ( osub != "0" && pts_per_bin >= 256.0 && nq >= 4096 ) );
     const bool use_sub = want_sub && ensure_sub_cells( grid ) == 1;
     if( use_sub )
     {

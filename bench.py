@@ -274,8 +274,10 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ C5: NN search
-def run_nn_workload(args, rank, world, local_rank, device, dist):
-    """query-sharded radius search, no collective on the data path: every rank holds the whole grid"""
+def run_nn_workload(args, rank, world, local_rank, device, dist, emit=True, with_clocks=True):
+    """query-sharded radius search, no collective on the data path: every rank holds the whole grid.  emit=False returns the
+    line instead of printing it (the default C2 run embeds it as `nn_search_c5`, so that the HBM-regime kernel is measured
+    in the same driver-run record)"""
     import torch
     from rescan_b200 import api, pipeline
     cloud, q_all = c5_inputs(args.c5_points, args.c5_queries)
@@ -320,8 +322,9 @@ def run_nn_workload(args, rank, world, local_rank, device, dist):
 
     for _ in range(args.warmup):
         step(True)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks = ClockSampler(local_rank) if with_clocks else None
+    if clocks:
+        clocks.start()
     l0 = api.launch_count()
     api.profile_reset()
     api.profile_enable(True)
@@ -332,7 +335,7 @@ def run_nn_workload(args, rank, world, local_rank, device, dist):
     hits = totals[-1]
     step(False)
     ms_e2e = timed(False, args.steps)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
 
     def total(x):
         t = torch.tensor([x], dtype=torch.float64, device=device)
@@ -364,9 +367,12 @@ def run_nn_workload(args, rank, world, local_rank, device, dist):
                                  "(SURVEY.md 8d, no early-out credit), rank 0 shard; traffic = dram__bytes_read + dram__bytes_write of one launch "
                                  "from the committed ncu capture of the same launch"},
             "clocks": clk}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and emit:
         rate, info, _ = cpu_nn_rate(cloud, q_all, target_seconds=10.0)
         line["cpu_baseline"] = dict(info, value=rate, unit=NN_UNIT)
+    grid.close()
+    if not emit:
+        return line
     print(json.dumps(line), flush=True)
 
 
@@ -381,6 +387,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the named problem split over the ranks (default); weak = every rank gets the named number of seeds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nn", action="store_true", help="N = 1, C2: skip the embedded C5 NN-search measurement (`nn_search_c5`)")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same problem on rank 0")
     ap.add_argument("--lanes", type=int, default=None, help="objects in flight at once (default RSGPU_LANES or 8); 1 = serial object loop")
     ap.add_argument("--exchange", default="nvlink", choices=["nvlink", "host", "nccl"],
@@ -591,6 +598,17 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             rate, info, _ = cpu_reference_rate(scene, rotations, translations, target_seconds=15.0)
             line["cpu_baseline"] = dict(info, value=rate, unit=UNIT)
+        if world == 1 and name == "C2" and not args.no_nn:
+            # the HBM-regime kernel of the same path (C5: 10 M points, r = 0.10 m, k = 64, 4 M queries) measured in the same run;
+            # `bench.py --workload C5` prints it as a line of its own (with its cpu_baseline)
+            try:
+                del dev, pinned, flush
+                torch.cuda.empty_cache()
+                nn_args = argparse.Namespace(**dict(vars(args), steps=3, warmup=3))
+                nn = run_nn_workload(nn_args, rank, world, local_rank, device, dist, emit=False, with_clocks=False)
+                line["nn_search_c5"] = {k: nn[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches", "roofline", "config")}
+            except Exception as e:  # the pose line stands on its own
+                line["nn_search_c5"] = {"unavailable": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if peer is not None:
         peer.close()

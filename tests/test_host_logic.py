@@ -297,3 +297,67 @@ def test_shard_translations_partitions_every_translation_once():
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= pipeline.SHARD_BLOCK
             plain = [pipeline.shard_translations(t, r, world, spatial=False) for r in range(world)]
             assert all((np.diff(p) > 0).all() for p in plain if len(p) > 1)
+
+
+def test_nms_pair_table_gives_the_greedy_result():
+    """the claim behind rsgpu_nms's one-launch path (csrc/nms.cu), checked with the oracle on the CPU: every overlap factor the
+    greedy loop of mgs_non_maxima_suppresion (pose_proposal.cpp:371-452) can ask for belongs to a pair {i < j : both scores >=
+    0.01, centroids >= dist_threshold apart}, the factor is symmetric in the pair, and the loop run from that table keeps what
+    the reference's round-by-round loop keeps"""
+    from oracle import orcbind as O
+    from rescan_b200 import synth
+    from tests import common
+    scene = common.tiny_scene()
+    rng = np.random.default_rng(23)
+    thr = 0.2
+    for o in scene.objects[:2]:
+        n = 14
+        props = np.zeros((n, 17), np.float32)
+        for j in range(n):
+            d = synth.yaw_pose(rng.uniform(-3.1, 3.1), rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.02, 0.02))
+            props[j, :16] = common.colmajor((d.astype(np.float64) @ o.pose.astype(np.float64)).astype(np.float32))
+            props[j, 16] = np.float32(rng.uniform(0.0, 1.0)) if j % 5 else np.float32(-1.0)
+        props[3, 16] = props[8, 16]  # a tie: the first index wins
+        p3, p1 = o.cloud.pos(3), o.cloud.pos(1)
+        cen = O.centroid(o.cloud.pos(0))
+        want = O.nms(p3, p1, cen, props, thr)
+        # centroid under every pose: msh_mat4_vec3_mul in float, left to right (column-major 4x4)
+        cpos = np.zeros((n, 3), np.float32)
+        for j in range(n):
+            m = props[j, :16]
+            for r in range(3):
+                s = np.float32(m[r] * cen[0]); s = np.float32(s + np.float32(m[4 + r] * cen[1]))
+                s = np.float32(s + np.float32(m[8 + r] * cen[2])); cpos[j, r] = np.float32(s + m[12 + r])
+
+        def dist(a, b):
+            v = (cpos[a] - cpos[b]).astype(np.float32)
+            s = np.float32(np.float32(np.float32(v[0] * v[0]) + np.float32(v[1] * v[1])) + np.float32(v[2] * v[2]))
+            return np.float32(np.sqrt(np.float64(s)))
+        table, asked = {}, 0
+        for i in range(n):
+            for j in range(i + 1, n):
+                if props[i, 16] >= 0.01 and props[j, 16] >= 0.01 and not dist(i, j) < thr:
+                    table[(i, j)] = O.overlap_factor(p3, p1, props[i, :16], props[j, :16])
+        # symmetry of the factor (union box, max of the two counts)
+        for (i, j) in list(table)[:6]:
+            assert table[(i, j)] == O.overlap_factor(p3, p1, props[j, :16], props[i, :16])
+        mark = np.zeros(n, np.int8)
+        while (mark == 0).any():
+            best, bs = -1, np.float32(-1e9)
+            for i in range(n):
+                if mark[i] == 0 and props[i, 16] > bs:
+                    best, bs = i, props[i, 16]
+            mark[best] = 1
+            for i in range(n):
+                if mark[i]:
+                    continue
+                if dist(best, i) < thr or props[i, 16] < 0.01:
+                    mark[i] = 2
+                    continue
+                key = (min(best, i), max(best, i))
+                assert key in table, "the loop asked for a pair outside the pre-computed set"
+                asked += 1
+                if table[key] > 0.5:
+                    mark[i] = 2
+        assert ((mark == 1) == np.asarray(want, bool)).all()
+        assert asked > 0 and 0 < (mark == 1).sum() < n

@@ -361,3 +361,43 @@ def test_nms_pair_table_gives_the_greedy_result():
                     mark[i] = 2
         assert ((mark == 1) == np.asarray(want, bool)).all()
         assert asked > 0 and 0 < (mark == 1).sum() < n
+
+
+def test_sub_cell_gap_is_a_lower_bound():
+    """the pruning bound of radius_search_sub_kernel (csrc/search.cu), restated in numpy float32 on the CPU: the squared gap from
+    a query to a 4x4x4 sub-cell's box - shrunk by the margin, low mantissa bits dropped - never exceeds the exact squared
+    distance (msh_hash_grid.h:852-855 expression) to any point that sub_key_kernel's float arithmetic assigns to that sub-cell,
+    also for points on sub-cell faces and in grids thousands of cells wide (without the margin the same check fails on 1 % of
+    the points)"""
+    f32 = np.float32
+    rng = np.random.default_rng(8)
+    worst = 0.0
+    for cell, extent in ((0.1, 8.0), (0.2, 40.0), (0.1, 400.0), (0.5, 900.0)):
+        mn = rng.uniform(-5, 5, 3).astype(f32)
+        n = 20000
+        pts = (mn + rng.uniform(0, extent, (n, 3))).astype(f32)
+        # a third of the points exactly on sub-cell faces of their axis
+        k = n // 3
+        sub = f32(cell / 4)
+        pts[:k] = (mn + np.round((pts[:k] - mn) / sub).astype(f32) * sub).astype(f32)
+        inv_cell_d = 1.0 / np.float64(cell)
+        inv_cell_f, cellf = f32(inv_cell_d), f32(cell)
+        subf = f32(cellf * f32(0.25))
+        W = int(extent / cell) + 2
+        margin = f32(cellf * max(f32(1e-3), f32(5e-7) * f32(W)))
+        rel = (pts - mn).astype(f32)                                   # float subtraction, like the grid build
+        c = np.trunc(rel.astype(np.float64) * inv_cell_d).astype(np.int64)  # the cell of the reference: double product, truncation
+        s = np.clip(np.floor(((rel * inv_cell_f).astype(f32) - c.astype(f32)).astype(f32) * f32(4)).astype(np.int64), 0, 3)
+        # queries near the points
+        q = (pts + rng.uniform(-cell, cell, (n, 3))).astype(f32)
+        qrel = (q - mn).astype(f32)
+        lo = ((c.astype(f32) * cellf).astype(f32) + (s.astype(f32) * subf).astype(f32)).astype(f32)
+        d = np.maximum(np.maximum((lo - qrel).astype(f32), (qrel - (lo + subf).astype(f32)).astype(f32)) - margin, f32(0)).astype(f32)
+        gap = ((d[:, 0] * d[:, 0]).astype(f32) + (d[:, 1] * d[:, 1]).astype(f32)).astype(f32)
+        gap = (gap + (d[:, 2] * d[:, 2]).astype(f32)).astype(f32)
+        gap_bits = gap.view(np.uint32) & np.uint32(0xFFFFFF00)
+        v = (pts - q).astype(f32)
+        d2 = (((v[:, 0] * v[:, 0]).astype(f32) + (v[:, 1] * v[:, 1]).astype(f32)).astype(f32) + (v[:, 2] * v[:, 2]).astype(f32)).astype(f32)
+        assert (gap_bits <= d2.view(np.uint32)).all(), (cell, extent, int((gap_bits > d2.view(np.uint32)).sum()))
+        worst = max(worst, float((gap_bits.view(f32) / np.maximum(d2, f32(1e-30))).max()))
+    assert worst <= 1.0
